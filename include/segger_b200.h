@@ -1,0 +1,218 @@
+/*
+ * libsegger_b200 -- C ABI of the B200-native segger hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers and sizes (no torch types),
+ * enqueues its work on the `stream` passed in (a cudaStream_t) and returns 0 on success or a
+ * negative SGB_ERR_* code; the message is available from sgb_last_error() (thread-local).
+ * The library never allocates, frees or retains device memory: outputs and workspaces are
+ * caller-owned (torch caching allocator / RMM compatible, CUDA-graph capturable).
+ *
+ * Each function cites the reference interface (file:line under /root/reference/src/segger) it
+ * replaces.  Where the arithmetic lives in a third-party dependency of the reference
+ * (torch_geometric 2.7.0, torch_scatter 2.1.2, scipy cKDTree) the citation is segger's call site.
+ */
+#ifndef SEGGER_B200_H_
+#define SEGGER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGB_VERSION 100
+
+#if defined(__GNUC__)
+#define SGB_API __attribute__((visibility("default")))
+#else
+#define SGB_API
+#endif
+
+#define SGB_OK 0
+#define SGB_ERR_ARG -1
+#define SGB_ERR_ALIGN -2
+#define SGB_ERR_RANGE -3
+#define SGB_ERR_WORKSPACE -4
+#define SGB_ERR_CUDA -5
+
+/* activation selectors for the fused GEMM epilogues */
+#define SGB_ACT_NONE 0
+#define SGB_ACT_GELU 1 /* exact erf GELU (F.gelu default, models/ist_encoder.py:320,325) */
+#define SGB_ACT_SILU 2 /* torch.nn.SiLU (models/ist_encoder.py:45) */
+
+SGB_API int sgb_version(void);
+SGB_API const char* sgb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph layout: COO edge_index -> dst-sorted CSR (+ src-sorted transposed CSR).
+ * Replaces the per-call gather/scatter indexing of PyG MessagePassing.propagate reached from
+ * models/ist_encoder.py:183-189.  edge_index is [2,E] int32 or int64 (idx_bytes 4|8) with
+ * arbitrary element strides (row_stride between the two rows, col_stride between edges), so
+ * `.T` views (data/utils/neighbors.py:196) are accepted without a copy.
+ * Stable: edges of a row keep their original order.  status (optional int32 on device) gets bit 0
+ * set if any index was out of range (indices are clamped so the call never faults).
+ * Transposed outputs may be NULL (inference).  src_pos[k] = position of that edge in the dst CSR.
+ * ---------------------------------------------------------------------------------------- */
+SGB_API size_t sgb_csr_workspace_bytes(int64_t E);
+SGB_API int sgb_csr_build(const void* edge_index, int idx_bytes, int64_t row_stride, int64_t col_stride,
+                  int64_t E, int64_t n_src, int64_t n_dst,
+                  int32_t* dst_rowptr /*[n_dst+1]*/, int32_t* dst_col /*[E] source ids*/,
+                  int32_t* dst_eid /*[E] original edge ids*/,
+                  int32_t* src_rowptr /*[n_src+1] or NULL*/, int32_t* src_dst /*[E]*/,
+                  int32_t* src_pos /*[E]*/, int32_t* status, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused GATv2 attention + aggregation (everything in GATv2Conv.forward after lin_l/lin_r):
+ *   e_ij = att . leaky_relu(x_l[j] + x_r[i]);  alpha = segment softmax over edges into i (+1e-16);
+ *   dropout(alpha);  out_i = sum_j alpha_ij x_l[j] + bias.
+ * Replaces torch_geometric GATv2Conv edge_updater/softmax/propagate as configured at
+ * models/ist_encoder.py:111-131.  One pass, no per-edge tensors.
+ * x_l [n_src, H*C] / x_r [n_dst, H*C] fp32 with leading dimensions ld_* (floats, multiple of 4 for
+ * the vector path), so column slices of a concatenated projection buffer can be passed directly.
+ * out = pre-activation (o + bias); out_act (optional) = GELU(out) (fuses ist_encoder.py:325).
+ * stat_max/stat_den [n_dst,H] are saved for the backward.  seed/p_drop/training drive the
+ * counter-based dropout keyed on (seed, original edge id, head).
+ * ---------------------------------------------------------------------------------------- */
+SGB_API int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, int64_t ld_r, const float* att,
+                  const float* bias /*or NULL*/, const int32_t* dst_rowptr, const int32_t* dst_col,
+                  const int32_t* dst_eid, int64_t n_dst, int64_t E, int H, int C, float negative_slope,
+                  float p_drop, uint64_t seed, int training, float* out, int64_t ld_out,
+                  float* out_act /*or NULL*/, int64_t ld_act, float* stat_max, float* stat_den,
+                  void* stream);
+
+/* attention coefficients alpha [E,H] in ORIGINAL edge order (return_attention_weights=True path of
+ * GATv2Conv; SkipGAT.attention_weights, models/ist_encoder.py:192-211).  Pre-dropout alpha. */
+SGB_API int sgb_gatv2_alpha(const float* x_l, int64_t ld_l, const float* x_r, int64_t ld_r, const float* att,
+                    const int32_t* dst_rowptr, const int32_t* dst_col, const int32_t* dst_eid,
+                    int64_t n_dst, int64_t E, int H, int C, float negative_slope,
+                    const float* stat_max, const float* stat_den, float* alpha, void* stream);
+
+/* Deterministic backward of sgb_gatv2_fwd (autograd of the PyG ops above).
+ * grad_out: dL/d(out) -- or, if gelu_fused != 0, dL/d(out_act); then g = grad_out * gelu'(out) is
+ * formed in-kernel and written to g_buf [n_dst, ld_g] (g_buf may alias grad_out; required when
+ * gelu_fused).  Two passes: dst-CSR (grad_x_r, grad_att, grad_bias, per-edge scalars) and src-CSR
+ * (grad_x_l); both row-owner reductions, no atomics.  grad_att/grad_bias are [H*C], overwritten.
+ * n_src rows of grad_x_l are all written (zeros for sources without edges). */
+SGB_API size_t sgb_gatv2_bwd_workspace_bytes(int64_t n_dst, int64_t E, int H, int C);
+SGB_API int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, int64_t ld_r, const float* att,
+                  const float* bias /*or NULL*/, const float* out, int64_t ld_out,
+                  const float* grad_out, int64_t ld_g, int gelu_fused, float* g_buf,
+                  const int32_t* dst_rowptr, const int32_t* dst_col, const int32_t* dst_eid,
+                  const int32_t* src_rowptr, const int32_t* src_dst, const int32_t* src_pos,
+                  int64_t n_src, int64_t n_dst, int64_t E, int H, int C, float negative_slope,
+                  float p_drop, uint64_t seed, int training, const float* stat_max,
+                  const float* stat_den, float* grad_x_l, int64_t ld_gl, float* grad_x_r,
+                  int64_t ld_gr, float* grad_att, float* grad_bias /*or NULL*/, void* ws,
+                  size_t ws_bytes, void* stream);
+
+/* The keep mask the kernels use, [E,H] uint8 in ORIGINAL edge order (test hook: lets the oracle
+ * replay the identical dropout realisation). */
+SGB_API int sgb_dropout_mask(uint64_t seed, int64_t E, int H, float p_drop, uint8_t* mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense projections y = x W^T + b (PyG Linear / HeteroDictLinear / GATv2Conv.lin_l, lin_r /
+ * torch.nn.Linear of the positional MLP; models/ist_encoder.py:43-47,261,282-286 and the
+ * GATv2Conv constructors at :111-131).  x [M,K] ldx, w [N,K] ldw, y [M,N] ldy, fp32 in/out.
+ * Error-compensated 3xTF32 on tcgen05 when the tile is a real dense GEMM, fp32 SIMT otherwise.
+ * y_act (optional) receives act(y).
+ * ---------------------------------------------------------------------------------------- */
+SGB_API int sgb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b /*or NULL*/,
+                   int64_t M, int64_t N, int64_t K, float* y, int64_t ldy, int act,
+                   float* y_act /*or NULL*/, int64_t ldya, void* stream);
+/* dx = dy W (+ dx if accumulate) ; if act_pre != NULL: dx *= act'(act_pre) (GELU/SiLU backward
+ * fused as epilogue).  dy [M,N], w [N,K], dx [M,K]. */
+SGB_API int sgb_linear_dgrad(const float* dy, int64_t ldy, const float* w, int64_t ldw, int64_t M, int64_t N,
+                     int64_t K, float* dx, int64_t ldx, int accumulate, int act,
+                     const float* act_pre /*or NULL*/, int64_t ld_pre, void* stream);
+/* dw = dy^T x (+ dw if accumulate), db = column sums of dy (+ db if accumulate); deterministic split-K. */
+SGB_API size_t sgb_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
+SGB_API int sgb_linear_wgrad(const float* dy, int64_t ldy, const float* x, int64_t ldx, int64_t M, int64_t N,
+                     int64_t K, float* dw, int64_t lddw, float* db /*or NULL*/, int accumulate,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Element-wise / row-wise pieces of ISTEncoder.forward (models/ist_encoder.py:312-333).
+ * ---------------------------------------------------------------------------------------- */
+/* y = act(x) and dx = dy * act'(x) over [M,N] with leading dimensions. */
+SGB_API int sgb_act_fwd(const float* x, int64_t ldx, int64_t M, int64_t N, int act, float* y, int64_t ldy, void* stream);
+SGB_API int sgb_act_bwd(const float* dy, int64_t ldy, const float* x, int64_t ldx, int64_t M, int64_t N, int act,
+                float* dx, int64_t lddx, void* stream);
+/* Embedding gather (lin_first['tx'], ist_encoder.py:260,312): out[i, 0:D] = table[ids[i], :];
+ * optional fused GELU into out_act.  ids int32 or int64. */
+SGB_API int sgb_embedding_fwd(const float* table, int64_t n_rows, int D, const void* ids, int idx_bytes, int64_t N,
+                      float* out, int64_t ldo, float* out_act, int64_t lda, int act, void* stream);
+/* grad_table[n_rows,D] = segment sum of dy rows by id (deterministic: sort by id + row-owner sum).
+ * If table != NULL the rows are first multiplied by act'(table[id]) (backward of the fused
+ * activation of sgb_embedding_fwd's out_act). */
+SGB_API size_t sgb_embedding_bwd_workspace_bytes(int64_t N, int D, int64_t n_rows);
+SGB_API int sgb_embedding_bwd(const float* dy, int64_t ldy, const void* ids, int idx_bytes, int64_t N, int D,
+                      int64_t n_rows, const float* table /*or NULL*/, int act, float* grad_table,
+                      void* ws, size_t ws_bytes, void* stream);
+/* Positional2dEmbedder front end (ist_encoder.py:22-31,57-79): per-tile min/max normalisation of
+ * pos [N,2] by batch id (NULL batch = one global tile without the 1e-8 eps, :63-65), then the
+ * sinusoid cos(p*freqs) | sin(p*freqs) per coordinate -> feat [2][N][dim] (coordinate-major: the
+ * x features of all nodes, then the y features).  freqs [dim/2] is the frequency table of
+ * sinusoidal_embedding (computed once on the host with the reference's own formula). */
+SGB_API size_t sgb_posfreq_workspace_bytes(int64_t n_batches);
+SGB_API int sgb_posfreq_fwd(const float* pos, int64_t N, const void* batch, int idx_bytes, int64_t n_batches,
+                    int dim, const float* freqs, float* feat, int64_t ldf, void* ws, size_t ws_bytes,
+                    void* stream);
+/* F.normalize(x, dim=-1, eps=1e-12) forward / backward (ist_encoder.py:331-332). */
+SGB_API int sgb_l2norm_fwd(const float* x, int64_t ldx, int64_t M, int D, float eps, float* y, int64_t ldy,
+                   float* norm /*[M]*/, void* stream);
+SGB_API int sgb_l2norm_bwd(const float* dy, int64_t ldy, const float* y, int64_t ldyy, const float* norm, int64_t M,
+                   int D, float eps, float* dx, int64_t lddx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * tx<->cell scoring: cosine similarity over candidate edges + per-transcript max / arg-max +
+ * cell-id lookup.  Replaces torch.cosine_similarity + torch_scatter.scatter_max + the index
+ * plumbing of LitISTEncoder.predict_step (models/lightning_model.py:275-293).
+ * Candidates come as a CSR over transcripts (sgb_csr_build with dst := transcript, i.e. call it
+ * with the edge_index rows swapped; cand_eid = original edge ids).  Ties -> lowest original edge
+ * id.  Transcripts without candidates: max_sim = 0, arg_edge = E, seg = -1.
+ * min_similarity: NaN disables the filter.
+ * ---------------------------------------------------------------------------------------- */
+SGB_API int sgb_score_argmax(const float* emb_tx, int64_t ld_tx, const float* emb_bd, int64_t ld_bd, int D,
+                     const int32_t* cand_rowptr, const int32_t* cand_col, const int32_t* cand_eid,
+                     int64_t n_tx, int64_t E, float eps, const void* bd_index, int bd_index_bytes,
+                     float min_similarity, float* max_sim, int64_t* arg_edge, int64_t* seg_idx,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 2-D k-nearest-neighbour graph with radius cap: replaces scipy cKDTree.query as called from
+ * kdtree_neighbors (data/utils/neighbors.py:139-150) and knn_to_edge_index (:54-92).
+ * Uniform grid (cell >= max_dist), float64 distances of the float32/float64 coordinates,
+ * neighbour accepted iff d < max_dist (strict), rows ordered by (d^2, index), padded with n_points.
+ * sgb_knn2d_plan computes the bounding box on the device and synchronises the stream once to
+ * size the grid; the plan is a small host struct.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sgb_knn_plan {
+  double xmin, ymin, cell; /* cell edge (>= max_dist) */
+  int64_t nx, ny;          /* grid dimensions */
+  int64_t n_points, n_query;
+  int k;
+  double max_dist;
+} sgb_knn_plan;
+SGB_API int sgb_knn2d_plan(const void* points, int is_f64, int64_t n_points, const void* query /*or NULL*/,
+                   int64_t n_query, int k, double max_dist, sgb_knn_plan* plan, void* ws64 /*>=64 B device*/,
+                   void* stream);
+SGB_API size_t sgb_knn2d_workspace_bytes(const sgb_knn_plan* plan);
+SGB_API int sgb_knn2d(const sgb_knn_plan* plan, const void* points, int is_f64, const void* query /*or NULL*/,
+              int64_t* table /*[n_query,k]*/, int32_t* count /*[n_query]*/, void* ws, size_t ws_bytes,
+              void* stream);
+/* padded table -> COO (query-major) with offsets = exclusive scan of count: edge_index [2,E] int64
+ * contiguous, index_ptr [n_query+1] int64 (knn_to_edge_index, neighbors.py:54-92). total E is
+ * returned through *n_edges_host after a stream synchronise when n_edges_host != NULL. */
+SGB_API int sgb_knn_count_valid(const int64_t* table, int64_t n, int k, int64_t pad_value, int32_t* count, void* stream);
+SGB_API size_t sgb_knn_coo_workspace_bytes(int64_t n_query);
+SGB_API int sgb_knn_count_edges(const int32_t* count, int64_t n_query, int64_t* index_ptr, int64_t* n_edges_host,
+                        void* ws, size_t ws_bytes, void* stream);
+SGB_API int sgb_knn_table_to_coo(const int64_t* table, const int64_t* index_ptr, int64_t n_query, int k,
+                         int64_t pad_value, int64_t row_offset, int64_t E, int64_t* edge_index /*[2,E]*/,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGGER_B200_H_ */

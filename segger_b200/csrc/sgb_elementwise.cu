@@ -1,0 +1,386 @@
+// Element-wise / row-wise stages of ISTEncoder.forward and their backward passes:
+// activations, embedding gather + deterministic segment-sum backward, positional min/max
+// normalisation + sinusoid features, L2 normalisation.
+// Reference: /root/reference/src/segger/models/ist_encoder.py:22-31 (sinusoid), :57-79 (per-tile
+// normalisation), :312 (Embedding), :320,325 (GELU), :331-332 (F.normalize).
+#include "sgb_api_internal.cuh"
+#include "sgb_sort.cuh"
+
+namespace sgb {
+namespace {
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == SGB_ACT_GELU) return gelu_erf(x);
+  if (act == SGB_ACT_SILU) return x / (1.0f + __expf(-x));
+  return x;
+}
+__device__ __forceinline__ float act_grad(float x, int act) {
+  if (act == SGB_ACT_GELU) return gelu_erf_grad(x);
+  if (act == SGB_ACT_SILU) {
+    const float s = 1.0f / (1.0f + __expf(-x));
+    return s * (1.0f + x * (1.0f - s));
+  }
+  return 1.0f;
+}
+
+__global__ void act_fwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t M, int64_t N, int act,
+                               float* __restrict__ y, int64_t ldy) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const int64_t r = i / N, c = i % N;
+  y[r * ldy + c] = act_apply(x[r * ldx + c], act);
+}
+__global__ void act_bwd_kernel(const float* __restrict__ dy, int64_t ldy, const float* __restrict__ x, int64_t ldx,
+                               int64_t M, int64_t N, int act, float* __restrict__ dx, int64_t lddx) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const int64_t r = i / N, c = i % N;
+  dx[r * lddx + c] = dy[r * ldy + c] * act_grad(x[r * ldx + c], act);
+}
+
+template <typename IdxT>
+__global__ void embedding_fwd_kernel(const float* __restrict__ table, int64_t n_rows, int D, const IdxT* __restrict__ ids,
+                                     int64_t N, float* __restrict__ out, int64_t ldo, float* __restrict__ out_act,
+                                     int64_t lda, int act) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= N * D) return;
+  const int64_t r = i / D;
+  const int c = static_cast<int>(i % D);
+  int64_t g = static_cast<int64_t>(ids[r]);
+  g = g < 0 ? 0 : (g >= n_rows ? n_rows - 1 : g);
+  const float v = __ldg(table + g * D + c);
+  if (out) out[r * ldo + c] = v;
+  if (out_act) out_act[r * lda + c] = act_apply(v, act);
+}
+
+template <typename IdxT>
+__global__ void ids_to_u32_kernel(const IdxT* __restrict__ ids, int64_t N, int64_t n_rows, uint32_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int64_t g = static_cast<int64_t>(ids[i]);
+  g = g < 0 ? 0 : (g >= n_rows ? n_rows - 1 : g);
+  out[i] = static_cast<uint32_t>(g);
+}
+
+constexpr int kEmbChunk = 64;  // sorted rows per warp in the segment-sum backward
+
+// Stage 1: warp per chunk of the id-sorted row list.  Complete segments are written straight to
+// grad_table; the (at most two) segments that continue into neighbouring chunks go to part[c][0|1].
+__global__ void __launch_bounds__(256)
+embedding_bwd_stage1_kernel(const float* __restrict__ dy, int64_t ldy, const uint32_t* __restrict__ sid,
+                            const uint32_t* __restrict__ perm, const int32_t* __restrict__ rowptr, int64_t N, int D,
+                            const float* __restrict__ table, int act, float* __restrict__ grad_table,
+                            float* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t s0 = chunk * kEmbChunk;
+  if (s0 >= N) return;
+  const int64_t s1 = min(N, s0 + kEmbChunk);
+  for (int d0 = 0; d0 < D; d0 += 256) {
+    float acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+    int64_t run_start = s0;
+    uint32_t g = sid[s0];
+    for (int64_t s = s0; s <= s1; ++s) {
+      const bool at_end = (s == s1);
+      const uint32_t gs = at_end ? 0xffffffffu : sid[s];
+      if (at_end || gs != g) {
+        // flush run [run_start, s) of gene g
+        const bool complete = (rowptr[g] == run_start) && (rowptr[g + 1] == s);
+        float* dst = complete ? grad_table + static_cast<int64_t>(g) * D
+                              : part + (chunk * 2 + (run_start == s0 ? 0 : 1)) * D;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int c = d0 + lane + 32 * t;
+          if (c < D) dst[c] = acc[t];
+          acc[t] = 0.f;
+        }
+        if (at_end) break;
+        g = gs;
+        run_start = s;
+      }
+      const int64_t r = perm[s];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int c = d0 + lane + 32 * t;
+        if (c < D) {
+          float v = __ldg(dy + r * ldy + c);
+          if (act != SGB_ACT_NONE) v *= act_grad(__ldg(table + static_cast<int64_t>(g) * D + c), act);
+          acc[t] += v;
+        }
+      }
+    }
+  }
+}
+
+// Stage 2: warp per table row; segments spanning several chunks are summed in chunk order.
+__global__ void __launch_bounds__(256)
+embedding_bwd_stage2_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int D, const float* __restrict__ part,
+                            float* __restrict__ grad_table) {
+  const int lane = threadIdx.x & 31;
+  const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (g >= n_rows) return;
+  const int64_t s = rowptr[g], e = rowptr[g + 1];
+  float* dst = grad_table + g * D;
+  if (s == e) {
+    for (int c = lane; c < D; c += 32) dst[c] = 0.f;
+    return;
+  }
+  const int64_t c_first = s / kEmbChunk, c_last = (e - 1) / kEmbChunk;
+  if (c_first == c_last) return;  // written by stage 1
+  for (int c = lane; c < D; c += 32) {
+    float acc = 0.f;
+    for (int64_t ch = c_first; ch <= c_last; ++ch) {
+      const int slot = (ch == c_first && s != ch * kEmbChunk) ? 1 : 0;
+      acc += part[(ch * 2 + slot) * D + c];
+    }
+    dst[c] = acc;
+  }
+}
+
+// ---- positional features ----
+__device__ __forceinline__ int f2ord(float f) {  // order-preserving float -> int
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void minmax_init_kernel(int* __restrict__ mm, int64_t n_batches) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_batches * 4) return;
+  mm[i] = (i % 4 < 2) ? f2ord(INFINITY) : f2ord(-INFINITY);  // [b][minx,miny,maxx,maxy]
+}
+
+template <typename IdxT>
+__global__ void minmax_kernel(const float* __restrict__ pos, int64_t N, const IdxT* __restrict__ batch,
+                              int64_t n_batches, int* __restrict__ mm) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = i < N;
+  int64_t b = 0;
+  float x = 0.f, y = 0.f;
+  if (valid) {
+    b = batch ? static_cast<int64_t>(batch[i]) : 0;
+    b = b < 0 ? 0 : (b >= n_batches ? n_batches - 1 : b);
+    x = pos[2 * i];
+    y = pos[2 * i + 1];
+  }
+  // warp-aggregate when the whole warp is one tile (the common, tile-major case)
+  const unsigned act = __ballot_sync(kFull, valid);
+  if (!valid) return;
+  const int b0 = __shfl_sync(act, static_cast<int>(b), __ffs(act) - 1);
+  const bool uniform = __all_sync(act, static_cast<int>(b) == b0);
+  if (uniform) {
+    float mnx = x, mny = y, mxx = x, mxy = y;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const float a = __shfl_xor_sync(act, mnx, o), c = __shfl_xor_sync(act, mny, o);
+      const float d = __shfl_xor_sync(act, mxx, o), e = __shfl_xor_sync(act, mxy, o);
+      const bool ok = (act >> ((threadIdx.x & 31) ^ o)) & 1u;
+      if (ok) { mnx = fminf(mnx, a); mny = fminf(mny, c); mxx = fmaxf(mxx, d); mxy = fmaxf(mxy, e); }
+    }
+    if ((threadIdx.x & 31) == __ffs(act) - 1) {
+      atomicMin(mm + b * 4 + 0, f2ord(mnx)); atomicMin(mm + b * 4 + 1, f2ord(mny));
+      atomicMax(mm + b * 4 + 2, f2ord(mxx)); atomicMax(mm + b * 4 + 3, f2ord(mxy));
+    }
+  } else {
+    atomicMin(mm + b * 4 + 0, f2ord(x)); atomicMin(mm + b * 4 + 1, f2ord(y));
+    atomicMax(mm + b * 4 + 2, f2ord(x)); atomicMax(mm + b * 4 + 3, f2ord(y));
+  }
+}
+
+// feat[d][i][0:half] = cos(p*freq), feat[d][i][half:2half] = sin(p*freq), optional zero pad
+template <typename IdxT>
+__global__ void posfreq_kernel(const float* __restrict__ pos, int64_t N, const IdxT* __restrict__ batch,
+                               int64_t n_batches, const int* __restrict__ mm, const float* __restrict__ freqs, int dim,
+                               float* __restrict__ feat, int64_t ldf) {
+  const int half = dim / 2;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= 2 * N * half) return;
+  const int k = static_cast<int>(i % half);
+  const int64_t node2 = i / half;  // d * N + node
+  const int d = static_cast<int>(node2 / N);
+  const int64_t node = node2 % N;
+  int64_t b = batch ? static_cast<int64_t>(batch[node]) : 0;
+  b = b < 0 ? 0 : (b >= n_batches ? n_batches - 1 : b);
+  const float mn = ord2f(mm[b * 4 + d]), mx = ord2f(mm[b * 4 + 2 + d]);
+  const float v = pos[2 * node + d];
+  // batch given: (pos - min) / (max - min + 1e-8);  batch None: (pos - min) / max(pos - min)
+  const float pn = batch ? (v - mn) / (mx - mn + 1e-8f) : (v - mn) / (mx - mn);
+  const float arg = pn * __ldg(freqs + k);
+  float sn, cs;
+  sincosf(arg, &sn, &cs);
+  float* row = feat + node2 * ldf;
+  row[k] = cs;
+  row[half + k] = sn;
+  if ((dim & 1) && k == 0) row[dim - 1] = 0.f;
+}
+
+// ---- L2 normalise ----
+__global__ void __launch_bounds__(256)
+l2norm_fwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t M, int D, float eps, float* __restrict__ y,
+                  int64_t ldy, float* __restrict__ norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (r >= M) return;
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) { const float v = x[r * ldx + c]; ss += v * v; }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
+  const float nrm = sqrtf(ss);
+  const float inv = 1.0f / fmaxf(nrm, eps);
+  for (int c = lane; c < D; c += 32) y[r * ldy + c] = x[r * ldx + c] * inv;
+  if (lane == 0 && norm) norm[r] = nrm;
+}
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(const float* __restrict__ dy, int64_t ldy, const float* __restrict__ y, int64_t ldyy,
+                  const float* __restrict__ norm, int64_t M, int D, float eps, float* __restrict__ dx, int64_t lddx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (r >= M) return;
+  const float nrm = norm[r];
+  float dot = 0.f;
+  for (int c = lane; c < D; c += 32) dot += dy[r * ldy + c] * y[r * ldyy + c];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(kFull, dot, o);
+  const bool clamped = !(nrm > eps);
+  const float inv = 1.0f / fmaxf(nrm, eps);
+  for (int c = lane; c < D; c += 32) {
+    const float g = dy[r * ldy + c];
+    dx[r * lddx + c] = clamped ? g * inv : (g - y[r * ldyy + c] * dot) * inv;
+  }
+}
+
+}  // namespace
+}  // namespace sgb
+
+using namespace sgb;
+
+extern "C" int sgb_act_fwd(const float* x, int64_t ldx, int64_t M, int64_t N, int act, float* y, int64_t ldy, void* stream) {
+  SGB_REQUIRE(M >= 0 && N >= 0, SGB_ERR_ARG, "act_fwd: negative size");
+  if (M * N == 0) return SGB_OK;
+  SGB_REQUIRE(x && y && ldx >= N && ldy >= N, SGB_ERR_ARG, "act_fwd: bad argument");
+  act_fwd_kernel<<<static_cast<unsigned>(ceil_div(M * N, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, M, N, act, y, ldy);
+  return check_launch("act_fwd");
+}
+extern "C" int sgb_act_bwd(const float* dy, int64_t ldy, const float* x, int64_t ldx, int64_t M, int64_t N, int act,
+                           float* dx, int64_t lddx, void* stream) {
+  SGB_REQUIRE(M >= 0 && N >= 0, SGB_ERR_ARG, "act_bwd: negative size");
+  if (M * N == 0) return SGB_OK;
+  SGB_REQUIRE(x && dy && dx && ldx >= N && ldy >= N && lddx >= N, SGB_ERR_ARG, "act_bwd: bad argument");
+  act_bwd_kernel<<<static_cast<unsigned>(ceil_div(M * N, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, ldy, x, ldx, M, N, act, dx, lddx);
+  return check_launch("act_bwd");
+}
+
+extern "C" int sgb_embedding_fwd(const float* table, int64_t n_rows, int D, const void* ids, int idx_bytes, int64_t N,
+                                 float* out, int64_t ldo, float* out_act, int64_t lda, int act, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, SGB_ERR_ARG, "embedding_fwd: idx_bytes must be 4 or 8");
+  SGB_REQUIRE(N >= 0 && D >= 1 && n_rows >= 1, SGB_ERR_ARG, "embedding_fwd: bad size");
+  if (N == 0) return SGB_OK;
+  SGB_REQUIRE(table && ids && (out || out_act), SGB_ERR_ARG, "embedding_fwd: null tensor");
+  const unsigned blocks = static_cast<unsigned>(ceil_div(N * D, 256));
+  if (idx_bytes == 8)
+    embedding_fwd_kernel<int64_t><<<blocks, 256, 0, stream>>>(table, n_rows, D, static_cast<const int64_t*>(ids), N, out, ldo, out_act, lda, act);
+  else
+    embedding_fwd_kernel<int32_t><<<blocks, 256, 0, stream>>>(table, n_rows, D, static_cast<const int32_t*>(ids), N, out, ldo, out_act, lda, act);
+  return check_launch("embedding_fwd");
+}
+
+namespace {
+struct EmbWs { uint32_t *ids32, *sid, *perm; int32_t* rowptr; float* part; void* sort_ws; size_t sort_bytes, total; };
+EmbWs emb_carve(void* ws, int64_t N, int64_t n_rows, int D) {
+  EmbWs e{};
+  const size_t nb = align_up(static_cast<size_t>(N > 0 ? N : 1) * 4);
+  char* p = static_cast<char*>(ws);
+  e.ids32 = reinterpret_cast<uint32_t*>(p); p += nb;
+  e.sid = reinterpret_cast<uint32_t*>(p); p += nb;
+  e.perm = reinterpret_cast<uint32_t*>(p); p += nb;
+  e.rowptr = reinterpret_cast<int32_t*>(p); p += align_up(static_cast<size_t>(n_rows + 1) * 4);
+  const size_t chunks = static_cast<size_t>(ceil_div(N > 0 ? N : 1, kEmbChunk));
+  e.part = reinterpret_cast<float*>(p); p += align_up(chunks * 2 * D * sizeof(float));
+  e.sort_ws = p;
+  e.sort_bytes = sort_pairs_workspace_bytes(N);
+  e.total = static_cast<size_t>(p - static_cast<char*>(ws)) + e.sort_bytes;
+  return e;
+}
+}  // namespace
+
+extern "C" size_t sgb_embedding_bwd_workspace_bytes(int64_t N, int D, int64_t n_rows) {
+  return emb_carve(nullptr, N, n_rows, D).total;
+}
+
+extern "C" int sgb_embedding_bwd(const float* dy, int64_t ldy, const void* ids, int idx_bytes, int64_t N, int D,
+                                 int64_t n_rows, const float* table, int act, float* grad_table, void* ws,
+                                 size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, SGB_ERR_ARG, "embedding_bwd: idx_bytes must be 4 or 8");
+  SGB_REQUIRE(N >= 0 && N < (int64_t(1) << 31) && D >= 1 && D <= 512 && n_rows >= 1 && n_rows <= (1 << 20), SGB_ERR_RANGE,
+              "embedding_bwd: size out of range");
+  SGB_REQUIRE(grad_table && ws, SGB_ERR_ARG, "embedding_bwd: null tensor");
+  EmbWs e = emb_carve(ws, N, n_rows, D);
+  SGB_REQUIRE(ws_bytes >= e.total, SGB_ERR_WORKSPACE, "embedding_bwd: workspace too small");
+  if (N == 0) {
+    cudaMemsetAsync(grad_table, 0, static_cast<size_t>(n_rows) * D * sizeof(float), stream);
+    return check_launch("embedding_bwd(empty)");
+  }
+  SGB_REQUIRE(dy && ids, SGB_ERR_ARG, "embedding_bwd: null tensor");
+  const unsigned nblk = static_cast<unsigned>(ceil_div(N, 256));
+  if (idx_bytes == 8) ids_to_u32_kernel<int64_t><<<nblk, 256, 0, stream>>>(static_cast<const int64_t*>(ids), N, n_rows, e.ids32);
+  else ids_to_u32_kernel<int32_t><<<nblk, 256, 0, stream>>>(static_cast<const int32_t*>(ids), N, n_rows, e.ids32);
+  int rc = sort_pairs(e.ids32, nullptr, e.sid, e.perm, N, bits_for(n_rows), e.sort_ws, e.sort_bytes, stream);
+  if (rc != SGB_OK) return rc;
+  rc = rowptr_from_sorted(e.sid, N, e.rowptr, n_rows, stream);
+  if (rc != SGB_OK) return rc;
+  const int64_t chunks = ceil_div(N, kEmbChunk);
+  embedding_bwd_stage1_kernel<<<static_cast<unsigned>(ceil_div(chunks, 8)), 256, 0, stream>>>(
+      dy, ldy, e.sid, e.perm, e.rowptr, N, D, table, table ? act : SGB_ACT_NONE, grad_table, e.part);
+  embedding_bwd_stage2_kernel<<<static_cast<unsigned>(ceil_div(n_rows, 8)), 256, 0, stream>>>(e.rowptr, n_rows, D, e.part, grad_table);
+  return check_launch("embedding_bwd");
+}
+
+extern "C" size_t sgb_posfreq_workspace_bytes(int64_t n_batches) {
+  return align_up(static_cast<size_t>(n_batches > 0 ? n_batches : 1) * 4 * sizeof(int));
+}
+
+extern "C" int sgb_posfreq_fwd(const float* pos, int64_t N, const void* batch, int idx_bytes, int64_t n_batches,
+                               int dim, const float* freqs, float* feat, int64_t ldf, void* ws, size_t ws_bytes,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(N >= 0 && dim >= 2 && n_batches >= 1, SGB_ERR_ARG, "posfreq_fwd: bad size");
+  SGB_REQUIRE(!batch || idx_bytes == 4 || idx_bytes == 8, SGB_ERR_ARG, "posfreq_fwd: idx_bytes must be 4 or 8");
+  if (N == 0) return SGB_OK;
+  SGB_REQUIRE(pos && freqs && feat && ws && ldf >= dim, SGB_ERR_ARG, "posfreq_fwd: null tensor");
+  SGB_REQUIRE(ws_bytes >= sgb_posfreq_workspace_bytes(n_batches), SGB_ERR_WORKSPACE, "posfreq_fwd: workspace too small");
+  int* mm = static_cast<int*>(ws);
+  minmax_init_kernel<<<static_cast<unsigned>(ceil_div(n_batches * 4, 256)), 256, 0, stream>>>(mm, n_batches);
+  const unsigned nb = static_cast<unsigned>(ceil_div(N, 256));
+  const int64_t total = 2 * N * (dim / 2);
+  const unsigned fb = static_cast<unsigned>(ceil_div(total, 256));
+  if (batch && idx_bytes == 8) {
+    minmax_kernel<int64_t><<<nb, 256, 0, stream>>>(pos, N, static_cast<const int64_t*>(batch), n_batches, mm);
+    posfreq_kernel<int64_t><<<fb, 256, 0, stream>>>(pos, N, static_cast<const int64_t*>(batch), n_batches, mm, freqs, dim, feat, ldf);
+  } else {
+    const int32_t* b32 = static_cast<const int32_t*>(batch);
+    minmax_kernel<int32_t><<<nb, 256, 0, stream>>>(pos, N, b32, n_batches, mm);
+    posfreq_kernel<int32_t><<<fb, 256, 0, stream>>>(pos, N, b32, n_batches, mm, freqs, dim, feat, ldf);
+  }
+  return check_launch("posfreq_fwd");
+}
+
+extern "C" int sgb_l2norm_fwd(const float* x, int64_t ldx, int64_t M, int D, float eps, float* y, int64_t ldy,
+                              float* norm, void* stream) {
+  SGB_REQUIRE(M >= 0 && D >= 1, SGB_ERR_ARG, "l2norm_fwd: bad size");
+  if (M == 0) return SGB_OK;
+  SGB_REQUIRE(x && y, SGB_ERR_ARG, "l2norm_fwd: null tensor");
+  l2norm_fwd_kernel<<<static_cast<unsigned>(ceil_div(M, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, M, D, eps, y, ldy, norm);
+  return check_launch("l2norm_fwd");
+}
+extern "C" int sgb_l2norm_bwd(const float* dy, int64_t ldy, const float* y, int64_t ldyy, const float* norm, int64_t M,
+                              int D, float eps, float* dx, int64_t lddx, void* stream) {
+  SGB_REQUIRE(M >= 0 && D >= 1, SGB_ERR_ARG, "l2norm_bwd: bad size");
+  if (M == 0) return SGB_OK;
+  SGB_REQUIRE(dy && y && norm && dx, SGB_ERR_ARG, "l2norm_bwd: null tensor");
+  l2norm_bwd_kernel<<<static_cast<unsigned>(ceil_div(M, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, ldy, y, ldyy, norm, M, D, eps, dx, lddx);
+  return check_launch("l2norm_bwd");
+}

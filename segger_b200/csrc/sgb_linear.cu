@@ -1,0 +1,50 @@
+// C ABI of the dense projections: argument validation + back-end selection.
+#include "sgb_api_internal.cuh"
+#include "sgb_linear.cuh"
+
+using namespace sgb;
+
+static int check_dims(const char* fn, int64_t M, int64_t N, int64_t K) {
+  SGB_REQUIRE(M >= 0 && N >= 0 && K >= 0, SGB_ERR_ARG, "%s: negative dimension", fn);
+  SGB_REQUIRE(M < (int64_t(1) << 31) && N < (int64_t(1) << 24) && K < (int64_t(1) << 24), SGB_ERR_RANGE,
+              "%s: dimension out of range (M=%lld N=%lld K=%lld)", fn, (long long)M, (long long)N, (long long)K);
+  return SGB_OK;
+}
+
+extern "C" int sgb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b, int64_t M,
+                              int64_t N, int64_t K, float* y, int64_t ldy, int act, float* y_act, int64_t ldya,
+                              void* stream) {
+  int rc = check_dims("linear_fwd", M, N, K);
+  if (rc != SGB_OK) return rc;
+  if (M == 0 || N == 0) return SGB_OK;
+  SGB_REQUIRE(y && (K == 0 || (x && w)), SGB_ERR_ARG, "linear_fwd: null tensor");
+  SGB_REQUIRE(ldx >= K && ldw >= K && ldy >= N && (!y_act || ldya >= N), SGB_ERR_ARG, "linear_fwd: leading dimension too small");
+  SGB_REQUIRE(act >= SGB_ACT_NONE && act <= SGB_ACT_SILU, SGB_ERR_ARG, "linear_fwd: unknown activation %d", act);
+  return simt_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, act, y_act, ldya, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sgb_linear_dgrad(const float* dy, int64_t ldy, const float* w, int64_t ldw, int64_t M, int64_t N,
+                                int64_t K, float* dx, int64_t ldx, int accumulate, int act, const float* act_pre,
+                                int64_t ld_pre, void* stream) {
+  int rc = check_dims("linear_dgrad", M, N, K);
+  if (rc != SGB_OK) return rc;
+  if (M == 0 || K == 0) return SGB_OK;
+  SGB_REQUIRE(dx && (N == 0 || (dy && w)), SGB_ERR_ARG, "linear_dgrad: null tensor");
+  SGB_REQUIRE(ldy >= N && ldw >= K && ldx >= K && (!act_pre || ld_pre >= K), SGB_ERR_ARG, "linear_dgrad: leading dimension too small");
+  return simt_linear_dgrad(dy, ldy, w, ldw, M, N, K, dx, ldx, accumulate, act, act_pre, ld_pre, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t sgb_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  return simt_linear_wgrad_workspace_bytes(M, N, K);
+}
+
+extern "C" int sgb_linear_wgrad(const float* dy, int64_t ldy, const float* x, int64_t ldx, int64_t M, int64_t N,
+                                int64_t K, float* dw, int64_t lddw, float* db, int accumulate, void* ws,
+                                size_t ws_bytes, void* stream) {
+  int rc = check_dims("linear_wgrad", M, N, K);
+  if (rc != SGB_OK) return rc;
+  if (N == 0) return SGB_OK;
+  SGB_REQUIRE((K == 0 || dw) && (M == 0 || (dy && (K == 0 || x))), SGB_ERR_ARG, "linear_wgrad: null tensor");
+  SGB_REQUIRE(ldy >= N && ldx >= K && lddw >= K, SGB_ERR_ARG, "linear_wgrad: leading dimension too small");
+  return simt_linear_wgrad(dy, ldy, x, ldx, M, N, K, dw, lddw, db, accumulate, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,241 @@
+"""B200-native drop-in for ``segger.models.ist_encoder``
+(/root/reference/src/segger/models/ist_encoder.py): ``Positional2dEmbedder``, ``SkipGAT`` and
+``ISTEncoder`` with identical constructor signatures, sub-module names and state-dict keys
+(``sinusoidal_embedding`` is folded into ``Positional2dEmbedder.features``, one fused kernel).
+All arithmetic runs in libsegger_b200 kernels; the modules below only hold parameters and
+schedule launches.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+from torch.nn import Embedding, Module, ModuleList, Sequential, SiLU
+from torch.nn import Linear as NNLinear
+
+from . import ops
+from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, require_cuda
+from .nn import GATv2Conv, HeteroConv, HeteroDictLinear, Linear, ModuleDict
+
+logger = logging.getLogger(__name__)
+
+TT = ("tx", "neighbors", "tx")
+TB = ("tx", "belongs", "bd")
+BT = ("bd", "contains", "tx")
+
+
+def _num_batches(batch: Optional[Tensor]) -> int:
+    if batch is None or batch.numel() == 0:
+        return 1
+    return int(batch.max()) + 1   # one host sync, as in the reference (ist_encoder.py:67-68)
+
+
+class Positional2dEmbedder(Module):
+    """ist_encoder.py:33-79.  ``forward`` normalises positions per tile, builds the 2 x 256-d sinusoid
+    and applies the 2-layer SiLU MLP; returns [N, 2*dim] (x embedding | y embedding)."""
+
+    def __init__(self, hidden_size: int, frequency_embedding_size: int = 256):
+        super().__init__()
+        self.dim = hidden_size // 2
+        self.mlp = Sequential(
+            NNLinear(frequency_embedding_size, self.dim, bias=True),
+            SiLU(),
+            NNLinear(self.dim, self.dim, bias=True),
+        )
+        self.frequency_embedding_size = frequency_embedding_size
+        self._freqs: Dict[torch.device, Tensor] = {}
+
+    def freqs(self, device) -> Tensor:
+        f = self._freqs.get(device)
+        if f is None:
+            f = ops.sinusoid_freqs(self.frequency_embedding_size, 10000, device)
+            self._freqs[device] = f
+        return f
+
+    def features(self, pos: Tensor, batch: Optional[Tensor]) -> Tensor:
+        """[2, N, freq] sinusoid features of the normalised coordinates (no parameters involved)."""
+        return ops.posfreq(pos, batch, _num_batches(batch), self.frequency_embedding_size, self.freqs(pos.device))
+
+    def forward(self, pos: Tensor, batch: Optional[Tensor] = None) -> Tensor:
+        feat = self.features(pos, batch)                   # [2, N, 256]
+        N = pos.size(0)
+        h = ops.linear(feat.view(2 * N, -1), self.mlp[0].weight, self.mlp[0].bias, ACT_SILU)
+        h = ops.linear(h, self.mlp[2].weight, self.mlp[2].bias, ACT_NONE)   # [2N, dim]
+        return h.view(2, N, self.dim).permute(1, 0, 2).reshape(N, 2 * self.dim)
+
+
+class SkipGAT(Module):
+    """ist_encoder.py:82-211: HeteroConv over three GATv2Conv (dropout 0.2, aggr='sum').
+
+    As in the reference, only ``tx-neighbors-tx`` and ``tx-belongs-bd`` ever receive edges; the
+    ``bd-contains-tx`` conv is declared (its lazy parameters stay unmaterialised, SURVEY Appendix
+    B.1) and still runs -- through the generic path -- if a caller does supply such edges.
+    ``attention_weights`` is exposed for parity of the interface; unlike the reference (where the
+    hook stores junk, Appendix B.2) it is computed on demand from the last forward.
+    """
+
+    def __init__(self, in_channels, out_channels: int, n_heads: int, add_self_loops_tx: bool = False) -> None:
+        super().__init__()
+        self.conv = HeteroConv(
+            convs={
+                TT: GATv2Conv(in_channels=in_channels, out_channels=out_channels, heads=n_heads,
+                              add_self_loops=add_self_loops_tx, dropout=0.2),
+                TB: GATv2Conv(in_channels=in_channels, out_channels=out_channels, heads=n_heads,
+                              add_self_loops=False, dropout=0.2),
+                BT: GATv2Conv(in_channels=in_channels, out_channels=out_channels, heads=n_heads,
+                              add_self_loops=False, dropout=0.2),
+            },
+            aggr="sum",
+        )
+        self._attn_weights: Dict[Tuple[str, str, str], Tensor] = {}
+        self._last = None
+
+    # -- fused path ----------------------------------------------------------------------------
+    def _fusable(self, x_dict, edge_index_dict) -> bool:
+        if TT not in edge_index_dict or TB not in edge_index_dict or BT in edge_index_dict:
+            return False
+        if "tx" not in x_dict or "bd" not in x_dict:
+            return False
+        if self.conv.convs[TT].add_self_loops:
+            return False
+        return all(isinstance(x_dict[k], Tensor) and x_dict[k].is_cuda for k in ("tx", "bd"))
+
+    def forward_fused(self, x_dict: Dict[str, Tensor], edge_index_dict, apply_gelu: bool = False,
+                      csr: Optional[dict] = None) -> Dict[str, Tensor]:
+        tt, tb = self.conv.convs[TT], self.conv.convs[TB]
+        x_tx, x_bd = x_dict["tx"].to(torch.float32), x_dict["bd"].to(torch.float32)
+        tt.lin_l.materialize(x_tx.size(-1), x_tx)
+        tt.lin_r.materialize(x_tx.size(-1), x_tx)
+        tb.lin_l.materialize(x_tx.size(-1), x_tx)
+        tb.lin_r.materialize(x_bd.size(-1), x_bd)
+        need_t = torch.is_grad_enabled()
+        if csr is None:
+            csr = {}
+        N, M = x_tx.size(0), x_bd.size(0)
+        csr_tt = csr.get(TT) or ops.CSR_CACHE.get(edge_index_dict[TT], N, N, need_t)
+        csr_tb = csr.get(TB) or ops.CSR_CACHE.get(edge_index_dict[TB], N, M, need_t)
+        training = self.training and tt.dropout > 0.0
+        seed_tt = ops.new_seed() if training else 0
+        seed_tb = ops.new_seed() if training else 0
+        self._last = (x_dict, edge_index_dict)
+        h_tx, h_bd = ops.SkipGATLayerFn.apply(
+            x_tx, x_bd,
+            tt.lin_l.weight, tt.lin_l.bias, tt.lin_r.weight, tt.lin_r.bias, tt.att, tt.bias,
+            tb.lin_l.weight, tb.lin_l.bias, tb.lin_r.weight, tb.lin_r.bias, tb.att, tb.bias,
+            csr_tt, csr_tb, tt.heads, tt.out_channels, tt.negative_slope, tt.dropout, training,
+            seed_tt, seed_tb, apply_gelu)
+        return {"tx": h_tx, "bd": h_bd}
+
+    def forward(self, x_dict: Dict[str, Tensor], edge_index_dict: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        if self._fusable(x_dict, edge_index_dict):
+            return self.forward_fused(x_dict, edge_index_dict)
+        self._last = (x_dict, edge_index_dict)
+        # Reference builds {edge: False for edge in self.conv.convs} -- string keys that HeteroConv
+        # never matches, i.e. a no-op kwarg (Appendix B.2); we simply do not pass it.
+        return self.conv(x_dict, edge_index_dict)
+
+    @property
+    def attention_weights(self) -> Dict[Tuple[str, str, str], Tensor]:
+        if self._last is None:
+            raise AttributeError("Attention weights are empty. Please perform a forward pass.")
+        x_dict, edge_index_dict = self._last
+        with torch.no_grad():
+            was = self.training
+            self.eval()
+            try:
+                conv = self.conv.convs[TT]
+                _, (_, alpha) = conv(x_dict["tx"].detach(), edge_index_dict[TT], return_attention_weights=True)
+            finally:
+                self.train(was)
+        self._attn_weights[TT] = alpha
+        return self._attn_weights
+
+
+class ISTEncoder(torch.nn.Module):
+    """ist_encoder.py:214-333, same signature and sub-module names.
+
+    forward = input stage (Embedding / Linear + positional MLP + GELU) -> (n_mid_layers + 2) fused
+    hetero GATv2 layers with GELU epilogues -> per-type output projection -> L2 normalisation.
+    """
+
+    def __init__(self, n_genes: int, in_channels: int = 16, hidden_channels: int = 32, out_channels: int = 32,
+                 n_mid_layers: int = 3, n_heads: int = 3, normalize_embeddings: bool = True,
+                 use_positional_embeddings: bool = True):
+        super().__init__()
+        self.normalize_embeddings = normalize_embeddings
+        self.use_positional_embeddings = use_positional_embeddings
+        self.hparams = locals()
+        for k in ["self", "__class__"]:
+            self.hparams.pop(k)
+        self.lin_first = ModuleDict({
+            "tx": Embedding(n_genes, in_channels),
+            "bd": Linear(-1, in_channels),
+        })
+        self.pos_emb = Positional2dEmbedder(in_channels)
+        self.conv_layers = ModuleList()
+        self.conv_layers.append(SkipGAT((-1, -1), hidden_channels, n_heads))
+        for _ in range(n_mid_layers):
+            self.conv_layers.append(SkipGAT((-1, -1), hidden_channels, n_heads))
+        self.conv_layers.append(SkipGAT((-1, -1), out_channels, n_heads))
+        self.lin_last = HeteroDictLinear(-1, out_channels, types=("tx", "bd"))
+        logger.debug(f"ISTEncoder: n_genes={n_genes}, in={in_channels}, hidden={hidden_channels}, "
+                     f"out={out_channels}, layers={n_mid_layers + 2}")
+
+    def _input_stage(self, k: str, x: Tensor, pos: Optional[Tensor], batch: Optional[Tensor]) -> Tensor:
+        first = self.lin_first[k]
+        feat = w0 = b0 = w2 = b2 = None
+        if self.use_positional_embeddings:
+            feat = self.pos_emb.features(pos, batch)
+            w0, b0 = self.pos_emb.mlp[0].weight, self.pos_emb.mlp[0].bias
+            w2, b2 = self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias
+        if isinstance(first, Embedding):
+            return ops.InputStageFn.apply(x, first.weight, None, feat, w0, b0, w2, b2, True)
+        first.materialize(x.size(-1), x)
+        return ops.InputStageFn.apply(x, first.weight, first.bias, feat, w0, b0, w2, b2, False)
+
+    def forward(self, x_dict: Dict[str, Tensor], edge_index_dict: Dict[str, Tensor], pos_dict: Dict[str, Tensor],
+                batch_dict: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        for k, x in x_dict.items():
+            require_cuda(x)
+        # Input stage (ist_encoder.py:312-320)
+        h_dict = {
+            k: self._input_stage(k, x, pos_dict[k] if self.use_positional_embeddings else None,
+                                 batch_dict.get(k) if self.use_positional_embeddings and batch_dict is not None else None)
+            for k, x in x_dict.items()
+        }
+        # Graph convolutions with GATv2 + GELU (ist_encoder.py:323-325)
+        fused = len(self.conv_layers) > 0 and self.conv_layers[0]._fusable(h_dict, edge_index_dict)
+        if fused:
+            need_t = torch.is_grad_enabled()
+            N, M = h_dict["tx"].size(0), h_dict["bd"].size(0)
+            csr = {TT: ops.CSR_CACHE.get(edge_index_dict[TT], N, N, need_t),
+                   TB: ops.CSR_CACHE.get(edge_index_dict[TB], N, M, need_t)}
+            for conv_layer in self.conv_layers:
+                h_dict = conv_layer.forward_fused(h_dict, edge_index_dict, apply_gelu=True, csr=csr)
+        else:
+            for conv_layer in self.conv_layers:
+                h_dict = conv_layer(h_dict, edge_index_dict)
+                h_dict = {k: _GeluFn.apply(v) for k, v in h_dict.items()}
+        # Output projection + normalisation (ist_encoder.py:328-332)
+        out = {}
+        for k, h in h_dict.items():
+            if k not in self.lin_last.lins:
+                continue
+            lin = self.lin_last.lins[k]
+            lin.materialize(h.size(-1), h)
+            out[k] = ops.OutputStageFn.apply(h, lin.weight, lin.bias, self.normalize_embeddings)
+        return out
+
+
+class _GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.act_fwd(x, ACT_GELU)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.act_bwd(dy.contiguous(), x, ACT_GELU)

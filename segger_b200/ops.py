@@ -1,0 +1,592 @@
+"""Functional layer over the C ABI: torch tensors in, torch tensors out, autograd wired by hand.
+
+Everything here enqueues hand-written sm_100a kernels from libsegger_b200.so on the current torch
+stream.  torch provides device memory (caching allocator), streams and the autograd *graph*; no
+torch operator computes anything on the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, check, ptr, require_cuda, stream_ptr
+
+LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _ws(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _rowmajor(t: Tensor) -> Tensor:
+    """2-D fp32 tensor with unit inner stride (column slices of a wider buffer are fine)."""
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D tensor, got shape {tuple(t.shape)}")
+    if t.size(1) > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.size(0) > 1 and t.stride(0) < t.size(1):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: Tensor) -> int:
+    return t.stride(0) if t.size(0) > 1 else max(t.size(1), t.stride(0))
+
+
+def _vec(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# Graph layout
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class EdgeCSR:
+    """dst-sorted CSR (+ src-sorted transposed CSR) of one edge type; all int32 on device."""
+    rowptr: Tensor
+    col: Tensor
+    eid: Tensor
+    t_rowptr: Optional[Tensor]
+    t_dst: Optional[Tensor]
+    t_pos: Optional[Tensor]
+    n_src: int
+    n_dst: int
+    E: int
+    status: Tensor
+
+
+def build_csr(edge_index: Tensor, n_src: int, n_dst: int, transpose: bool = True) -> EdgeCSR:
+    """COO [2,E] (int32/int64, any strides) -> EdgeCSR.  Replaces PyG's per-call scatter indexing."""
+    require_cuda(edge_index)
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError(f"edge_index must be [2, E], got {tuple(edge_index.shape)}")
+    if edge_index.dtype not in (torch.int32, torch.int64):
+        raise TypeError(f"edge_index must be int32 or int64, got {edge_index.dtype}")
+    dev = edge_index.device
+    E = edge_index.size(1)
+    lib = _lib.load()
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr = torch.empty(n_dst + 1, **i32)
+    col = torch.empty(E, **i32)
+    eid = torch.empty(E, **i32)
+    t_rowptr = torch.empty(n_src + 1, **i32) if transpose else None
+    t_dst = torch.empty(E, **i32) if transpose else None
+    t_pos = torch.empty(E, **i32) if transpose else None
+    status = torch.zeros(1, **i32)
+    ws = _ws(lib.sgb_csr_workspace_bytes(E), dev)
+    check(lib.sgb_csr_build(ptr(edge_index), edge_index.element_size(), edge_index.stride(0),
+                            edge_index.stride(1), E, n_src, n_dst, ptr(rowptr), ptr(col), ptr(eid),
+                            ptr(t_rowptr), ptr(t_dst), ptr(t_pos), ptr(status), ptr(ws), ws.numel(),
+                            stream_ptr(dev)), "csr_build")
+    _count(12 if transpose else 6)
+    return EdgeCSR(rowptr, col, eid, t_rowptr, t_dst, t_pos, n_src, n_dst, E, status)
+
+
+class _CsrCache:
+    """Tiny LRU so that the layers of one forward (and repeated forwards over a static graph) share
+    one CSR build per edge type.  Keyed on storage identity + version; holds the tensor alive."""
+
+    def __init__(self, size: int = 8):
+        self.size = size
+        self.items = []
+
+    def get(self, edge_index: Tensor, n_src: int, n_dst: int, transpose: bool) -> EdgeCSR:
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index.stride(), edge_index.dtype,
+               edge_index._version, n_src, n_dst)
+        for i, (k, t, csr) in enumerate(self.items):
+            if k == key and (csr.t_rowptr is not None or not transpose):
+                self.items.append(self.items.pop(i))
+                return csr
+        csr = build_csr(edge_index, n_src, n_dst, transpose)
+        self.items.append((key, edge_index, csr))
+        if len(self.items) > self.size:
+            self.items.pop(0)
+        return csr
+
+    def clear(self):
+        self.items.clear()
+
+
+CSR_CACHE = _CsrCache()
+
+
+def new_seed() -> int:
+    """63-bit seed drawn from torch's default (CPU) generator: torch.manual_seed governs dropout."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+# ------------------------------------------------------------------------------------------------
+# raw kernel wrappers (no autograd)
+# ------------------------------------------------------------------------------------------------
+def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE,
+               y: Optional[Tensor] = None, y_act: Optional[Tensor] = None,
+               want_pre: bool = True) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """(y, act(y)) with y = x w^T + b.  y / y_act may be preallocated (strided) views."""
+    x, w = _rowmajor(x), _rowmajor(w)
+    M, K = x.shape
+    N = w.size(0)
+    if w.size(1) != K:
+        raise ValueError(f"linear: x is [*, {K}] but weight is {tuple(w.shape)}")
+    dev = x.device
+    if y is None:
+        y = torch.empty(M, N, dtype=torch.float32, device=dev)
+    if act != ACT_NONE and y_act is None:
+        y_act = torch.empty(M, N, dtype=torch.float32, device=dev)
+    b = _vec(b)
+    check(_lib.load().sgb_linear_fwd(ptr(x), _ld(x), ptr(w), _ld(w), ptr(b), M, N, K, ptr(y), _ld(y), act,
+                                     ptr(y_act), _ld(y_act) if y_act is not None else 0, stream_ptr(dev)),
+          "linear_fwd")
+    _count(1)
+    return y, y_act
+
+
+def linear_dgrad(dy: Tensor, w: Tensor, dx: Optional[Tensor] = None, accumulate: bool = False,
+                 act: int = ACT_NONE, act_pre: Optional[Tensor] = None) -> Tensor:
+    dy, w = _rowmajor(dy), _rowmajor(w)
+    M, N = dy.shape
+    K = w.size(1)
+    if dx is None:
+        dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
+    check(_lib.load().sgb_linear_dgrad(ptr(dy), _ld(dy), ptr(w), _ld(w), M, N, K, ptr(dx), _ld(dx),
+                                       int(accumulate), act, ptr(act_pre),
+                                       _ld(act_pre) if act_pre is not None else 0, stream_ptr(dy.device)),
+          "linear_dgrad")
+    _count(1)
+    return dx
+
+
+def linear_wgrad(dy: Tensor, x: Tensor, dw: Optional[Tensor] = None, db: Optional[Tensor] = None,
+                 want_db: bool = True, accumulate: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+    dy, x = _rowmajor(dy), _rowmajor(x)
+    M, N = dy.shape
+    K = x.size(1)
+    dev = dy.device
+    if dw is None:
+        dw = torch.empty(N, K, dtype=torch.float32, device=dev)
+    if db is None and want_db:
+        db = torch.empty(N, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    ws = _ws(lib.sgb_linear_wgrad_workspace_bytes(M, N, K), dev)
+    check(lib.sgb_linear_wgrad(ptr(dy), _ld(dy), ptr(x), _ld(x), M, N, K, ptr(dw), _ld(dw), ptr(db),
+                               int(accumulate), ptr(ws), ws.numel(), stream_ptr(dev)), "linear_wgrad")
+    _count(4 if db is not None else 2)
+    return dw, db
+
+
+def act_bwd(dy: Tensor, pre: Tensor, act: int, dx: Optional[Tensor] = None) -> Tensor:
+    dy, pre = _rowmajor(dy), _rowmajor(pre)
+    M, N = dy.shape
+    if dx is None:
+        dx = torch.empty(M, N, dtype=torch.float32, device=dy.device)
+    check(_lib.load().sgb_act_bwd(ptr(dy), _ld(dy), ptr(pre), _ld(pre), M, N, act, ptr(dx), _ld(dx),
+                                  stream_ptr(dy.device)), "act_bwd")
+    _count(1)
+    return dx
+
+
+def act_fwd(x: Tensor, act: int, y: Optional[Tensor] = None) -> Tensor:
+    x = _rowmajor(x)
+    M, N = x.shape
+    if y is None:
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    check(_lib.load().sgb_act_fwd(ptr(x), _ld(x), M, N, act, ptr(y), _ld(y), stream_ptr(x.device)), "act_fwd")
+    _count(1)
+    return y
+
+
+def gatv2_fwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], csr: EdgeCSR, H: int, C: int,
+              slope: float, p_drop: float, training: bool, seed: int, want_act: bool,
+              out: Optional[Tensor] = None, out_act: Optional[Tensor] = None):
+    """-> (out_pre, out_act|None, stat_max, stat_den)."""
+    x_l, x_r = _rowmajor(x_l), _rowmajor(x_r)
+    F = H * C
+    dev = x_r.device
+    n_dst = x_r.size(0)
+    if x_l.size(0) != csr.n_src or n_dst != csr.n_dst:
+        raise ValueError(f"gatv2: node counts ({x_l.size(0)}, {n_dst}) do not match the CSR "
+                         f"({csr.n_src}, {csr.n_dst})")
+    if x_l.size(1) != F or x_r.size(1) != F:
+        raise ValueError("gatv2: projected features must be [*, heads*out_channels]")
+    if out is None:
+        out = torch.empty(n_dst, F, dtype=torch.float32, device=dev)
+    if want_act and out_act is None:
+        out_act = torch.empty(n_dst, F, dtype=torch.float32, device=dev)
+    smax = torch.empty(n_dst, H, dtype=torch.float32, device=dev)
+    sden = torch.empty(n_dst, H, dtype=torch.float32, device=dev)
+    att, bias = _vec(att.reshape(-1)), _vec(bias)
+    check(_lib.load().sgb_gatv2_fwd(ptr(x_l), _ld(x_l), ptr(x_r), _ld(x_r), ptr(att), ptr(bias), ptr(csr.rowptr),
+                                    ptr(csr.col), ptr(csr.eid), n_dst, csr.E, H, C, slope, p_drop, seed,
+                                    int(training), ptr(out), _ld(out), ptr(out_act),
+                                    _ld(out_act) if out_act is not None else 0, ptr(smax), ptr(sden),
+                                    stream_ptr(dev)), "gatv2_fwd")
+    _count(1)
+    return out, out_act, smax, sden
+
+
+def gatv2_bwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], out_pre: Tensor, grad_out: Tensor,
+              gelu_fused: bool, csr: EdgeCSR, H: int, C: int, slope: float, p_drop: float, training: bool,
+              seed: int, smax: Tensor, sden: Tensor, grad_x_l: Optional[Tensor] = None,
+              grad_x_r: Optional[Tensor] = None):
+    """-> (grad_x_l, grad_x_r, grad_att [H*C], grad_bias [H*C])."""
+    if csr.t_rowptr is None:
+        raise RuntimeError("gatv2_bwd needs the transposed CSR (build_csr(..., transpose=True))")
+    x_l, x_r, out_pre, grad_out = _rowmajor(x_l), _rowmajor(x_r), _rowmajor(out_pre), _rowmajor(grad_out)
+    F = H * C
+    dev = x_r.device
+    n_src, n_dst = csr.n_src, csr.n_dst
+    if grad_x_l is None:
+        grad_x_l = torch.empty(n_src, F, dtype=torch.float32, device=dev)
+    if grad_x_r is None:
+        grad_x_r = torch.empty(n_dst, F, dtype=torch.float32, device=dev)
+    g_att = torch.empty(F, dtype=torch.float32, device=dev)
+    g_bias = torch.empty(F, dtype=torch.float32, device=dev) if bias is not None else None
+    g_buf = None
+    if gelu_fused:
+        g_buf = torch.empty(n_dst, _ld(grad_out), dtype=torch.float32, device=dev) if n_dst > 0 else grad_out
+    lib = _lib.load()
+    ws = _ws(lib.sgb_gatv2_bwd_workspace_bytes(n_dst, csr.E, H, C), dev)
+    att, bias = _vec(att.reshape(-1)), _vec(bias)
+    check(lib.sgb_gatv2_bwd(ptr(x_l), _ld(x_l), ptr(x_r), _ld(x_r), ptr(att), ptr(bias), ptr(out_pre), _ld(out_pre),
+                            ptr(grad_out), _ld(grad_out), int(gelu_fused), ptr(g_buf), ptr(csr.rowptr), ptr(csr.col),
+                            ptr(csr.eid), ptr(csr.t_rowptr), ptr(csr.t_dst), ptr(csr.t_pos), n_src, n_dst, csr.E,
+                            H, C, slope, p_drop, seed, int(training), ptr(smax), ptr(sden), ptr(grad_x_l),
+                            _ld(grad_x_l), ptr(grad_x_r), _ld(grad_x_r), ptr(g_att), ptr(g_bias), ptr(ws),
+                            ws.numel(), stream_ptr(dev)), "gatv2_bwd")
+    _count(3)
+    return grad_x_l, grad_x_r, g_att, g_bias
+
+
+def gatv2_alpha(x_l, x_r, att, csr: EdgeCSR, H, C, slope, smax, sden) -> Tensor:
+    x_l, x_r = _rowmajor(x_l), _rowmajor(x_r)
+    alpha = torch.zeros(csr.E, H, dtype=torch.float32, device=x_r.device)
+    att = _vec(att.reshape(-1))
+    check(_lib.load().sgb_gatv2_alpha(ptr(x_l), _ld(x_l), ptr(x_r), _ld(x_r), ptr(att), ptr(csr.rowptr), ptr(csr.col),
+                                      ptr(csr.eid), csr.n_dst, csr.E, H, C, slope, ptr(smax), ptr(sden), ptr(alpha),
+                                      stream_ptr(x_r.device)), "gatv2_alpha")
+    _count(1)
+    return alpha
+
+
+def dropout_keep_mask(seed: int, E: int, H: int, p: float, device) -> Tensor:
+    """[E,H] bool keep mask identical to the one the fused kernels regenerate (test hook)."""
+    mask = torch.empty(E, H, dtype=torch.uint8, device=device)
+    check(_lib.load().sgb_dropout_mask(seed, E, H, p, ptr(mask), stream_ptr(device)), "dropout_mask")
+    _count(1)
+    return mask.bool()
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd Functions
+# ------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) with a hand-written backward (dgrad + deterministic split-K wgrad)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        require_cuda(x, w, b)
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.size(-1))
+        y, y_act = linear_fwd(x2, w, b, act)
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.lead = lead
+        ctx.save_for_backward(x2, w, y if act != ACT_NONE else None)
+        out = y_act if act != ACT_NONE else y
+        return out.view(*lead, w.size(0))
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, w, y = ctx.saved_tensors
+        dy = dout.reshape(-1, w.size(0))
+        if ctx.act != ACT_NONE:
+            dy = act_bwd(dy, y, ctx.act)
+        dx = linear_dgrad(dy, w).view(*ctx.lead, w.size(1)) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = linear_wgrad(dy, x2, want_db=ctx.has_bias)
+        return dx, dw, db, None
+
+
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE) -> Tensor:
+    return LinearFn.apply(x, w, b, act)
+
+
+class GATv2AggregateFn(torch.autograd.Function):
+    """Attention + softmax + aggregation (+bias, optional fused GELU) of one GATv2Conv."""
+
+    @staticmethod
+    def forward(ctx, x_l, x_r, att, bias, csr, H, C, slope, p_drop, training, seed, apply_gelu):
+        require_cuda(x_l, x_r, att, bias)
+        out, out_act, smax, sden = gatv2_fwd(x_l, x_r, att, bias, csr, H, C, slope, p_drop, training, seed,
+                                             apply_gelu)
+        ctx.csr, ctx.cfg = csr, (H, C, slope, p_drop, training, seed, apply_gelu)
+        ctx.att_shape = att.shape
+        ctx.save_for_backward(x_l, x_r, att, bias, out, smax, sden)
+        return out_act if apply_gelu else out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x_l, x_r, att, bias, out, smax, sden = ctx.saved_tensors
+        H, C, slope, p_drop, training, seed, apply_gelu = ctx.cfg
+        gl, gr, ga, gb = gatv2_bwd(x_l, x_r, att, bias, out, dout.contiguous(), apply_gelu, ctx.csr, H, C, slope,
+                                   p_drop, training, seed, smax, sden)
+        return gl, gr, ga.view(ctx.att_shape), gb, None, None, None, None, None, None, None, None
+
+
+class SkipGATLayerFn(torch.autograd.Function):
+    """One hetero GATv2 layer of ISTEncoder fused end to end:
+
+        Y_tx = x_tx [W_l^tt | W_r^tt | W_l^tb]^T + b      (one concatenated projection GEMM)
+        Y_bd = x_bd W_r^tb^T + b
+        h_tx = act(agg_tt(Y_tx[:, :F], Y_tx[:, F:2F]) + bias_tt)
+        h_bd = act(agg_tb(Y_tx[:, 2F:], Y_bd) + bias_tb)
+
+    which is HeteroConv({tt: GATv2Conv, tb: GATv2Conv}) (+ the following F.gelu when apply_gelu)
+    of /root/reference/src/segger/models/ist_encoder.py:109-134,183-189,323-325.  The backward
+    writes all three tx-side feature gradients into one [N, 3F] buffer so dgrad/wgrad are again
+    single GEMMs.
+    """
+
+    @staticmethod
+    def forward(ctx, x_tx, x_bd, wl_tt, bl_tt, wr_tt, br_tt, att_tt, bias_tt, wl_tb, bl_tb, wr_tb, br_tb,
+                att_tb, bias_tb, csr_tt, csr_tb, H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu):
+        require_cuda(x_tx, x_bd)
+        F = H * C
+        N, M = x_tx.size(0), x_bd.size(0)
+        dev = x_tx.device
+        w_cat = torch.cat([wl_tt, wr_tt, wl_tb], 0)
+        b_cat = torch.cat([bl_tt, br_tt, bl_tb], 0)
+        y_tx, _ = linear_fwd(x_tx, w_cat, b_cat)
+        y_bd, _ = linear_fwd(x_bd, wr_tb, br_tb)
+        v_tx, h_tx, smax_tt, sden_tt = gatv2_fwd(y_tx[:, :F], y_tx[:, F:2 * F], att_tt, bias_tt, csr_tt, H, C,
+                                                 slope, p_drop, training, seed_tt, apply_gelu)
+        v_bd, h_bd, smax_tb, sden_tb = gatv2_fwd(y_tx[:, 2 * F:], y_bd, att_tb, bias_tb, csr_tb, H, C, slope,
+                                                 p_drop, training, seed_tb, apply_gelu)
+        ctx.csr = (csr_tt, csr_tb)
+        ctx.cfg = (H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu)
+        ctx.att_shape = att_tt.shape
+        ctx.save_for_backward(x_tx, x_bd, w_cat, wr_tb, y_tx, y_bd, v_tx, v_bd, att_tt, bias_tt, att_tb, bias_tb,
+                              smax_tt, sden_tt, smax_tb, sden_tb)
+        if apply_gelu:
+            return h_tx, h_bd
+        return v_tx, v_bd
+
+    @staticmethod
+    def backward(ctx, d_tx, d_bd):
+        (x_tx, x_bd, w_cat, wr_tb, y_tx, y_bd, v_tx, v_bd, att_tt, bias_tt, att_tb, bias_tb, smax_tt, sden_tt,
+         smax_tb, sden_tb) = ctx.saved_tensors
+        csr_tt, csr_tb = ctx.csr
+        H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu = ctx.cfg
+        F = H * C
+        N, M = x_tx.size(0), x_bd.size(0)
+        dev = x_tx.device
+        if d_tx is None:
+            d_tx = torch.zeros_like(v_tx)
+        if d_bd is None:
+            d_bd = torch.zeros_like(v_bd)
+        g_tx = torch.empty(N, 3 * F, dtype=torch.float32, device=dev)
+        g_bd = torch.empty(M, F, dtype=torch.float32, device=dev)
+        _, _, ga_tt, gb_tt = gatv2_bwd(y_tx[:, :F], y_tx[:, F:2 * F], att_tt, bias_tt, v_tx, d_tx.contiguous(),
+                                       apply_gelu, csr_tt, H, C, slope, p_drop, training, seed_tt, smax_tt, sden_tt,
+                                       grad_x_l=g_tx[:, :F], grad_x_r=g_tx[:, F:2 * F])
+        _, _, ga_tb, gb_tb = gatv2_bwd(y_tx[:, 2 * F:], y_bd, att_tb, bias_tb, v_bd, d_bd.contiguous(), apply_gelu,
+                                       csr_tb, H, C, slope, p_drop, training, seed_tb, smax_tb, sden_tb,
+                                       grad_x_l=g_tx[:, 2 * F:], grad_x_r=g_bd)
+        dx_tx = linear_dgrad(g_tx, w_cat) if ctx.needs_input_grad[0] else None
+        dx_bd = linear_dgrad(g_bd, wr_tb) if ctx.needs_input_grad[1] else None
+        dw_cat, db_cat = linear_wgrad(g_tx, x_tx)
+        dwr_tb, dbr_tb = linear_wgrad(g_bd, x_bd)
+        return (dx_tx, dx_bd,
+                dw_cat[:F], db_cat[:F], dw_cat[F:2 * F], db_cat[F:2 * F], ga_tt.view(ctx.att_shape), gb_tt,
+                dw_cat[2 * F:], db_cat[2 * F:], dwr_tb, dbr_tb, ga_tb.view(ctx.att_shape), gb_tb,
+                None, None, None, None, None, None, None, None, None, None)
+
+
+def sinusoid_freqs(dim: int, max_period: float, device) -> Tensor:
+    """Frequency table of sinusoidal_embedding, computed with the reference's own formula
+    (/root/reference/src/segger/models/ist_encoder.py:24-26) so the table is bit-identical."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+    return freqs.to(device)
+
+
+def posfreq(pos: Tensor, batch: Optional[Tensor], n_batches: int, dim: int, freqs: Tensor) -> Tensor:
+    """[2, N, dim] sinusoid features of the per-tile-normalised coordinates (x block, then y block)."""
+    require_cuda(pos, batch)
+    pos = pos.to(torch.float32).contiguous()
+    N = pos.size(0)
+    dev = pos.device
+    feat = torch.empty(2, N, dim, dtype=torch.float32, device=dev)
+    if batch is not None:
+        if batch.dtype not in (torch.int32, torch.int64):
+            batch = batch.long()
+        batch = batch.contiguous()
+    lib = _lib.load()
+    ws = _ws(lib.sgb_posfreq_workspace_bytes(n_batches), dev)
+    check(lib.sgb_posfreq_fwd(ptr(pos), N, ptr(batch), batch.element_size() if batch is not None else 0, n_batches,
+                              dim, ptr(freqs), ptr(feat), dim, ptr(ws), ws.numel(), stream_ptr(dev)), "posfreq_fwd")
+    _count(3)
+    return feat
+
+
+class InputStageFn(torch.autograd.Function):
+    """Input stage of ISTEncoder.forward for one node type
+    (/root/reference/src/segger/models/ist_encoder.py:312-320):
+
+        h = gelu( cat( first(x), pos_mlp(sinusoid(normalise(pos))) ) )
+
+    ``first`` is an Embedding gather (tx: integer gene ids) or a Linear (bd: float features).
+    GELU is applied per column block straight into the concatenated buffer.
+    """
+
+    @staticmethod
+    def forward(ctx, x, first_w, first_b, feat, w0, b0, w2, b2, is_embedding):
+        dev = first_w.device
+        N = x.size(0)
+        D = first_w.size(1) if is_embedding else first_w.size(0)
+        use_pos = feat is not None
+        dim = w2.size(0) if use_pos else 0
+        h = torch.empty(N, D + 2 * dim, dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        pre_first = None
+        if is_embedding:
+            ids = x if x.dtype in (torch.int32, torch.int64) else x.long()
+            ids = ids.contiguous()
+            tab = first_w.contiguous()
+            check(lib.sgb_embedding_fwd(ptr(tab), tab.size(0), D, ptr(ids), ids.element_size(), N, None, 0,
+                                        ptr(h), _ld(h), ACT_GELU, stream_ptr(dev)), "embedding_fwd")
+            _count(1)
+            saved_x = ids
+        else:
+            x2 = _rowmajor(x.to(torch.float32))
+            pre_first, _ = linear_fwd(x2, first_w, first_b, ACT_GELU, y_act=h[:, :D])
+            saved_x = x2
+        y0 = a0 = y2 = None
+        if use_pos:
+            f2 = feat.view(2 * N, feat.size(-1))
+            y0, a0 = linear_fwd(f2, w0, b0, ACT_SILU)                      # [2N, dim] pre / SiLU
+            y2 = torch.empty(2 * N, dim, dtype=torch.float32, device=dev)
+            for d in range(2):                                            # x block, y block
+                linear_fwd(a0[d * N:(d + 1) * N], w2, b2, ACT_GELU, y=y2[d * N:(d + 1) * N],
+                           y_act=h[:, D + d * dim: D + (d + 1) * dim])
+        ctx.is_embedding, ctx.use_pos, ctx.D, ctx.dim, ctx.N = is_embedding, use_pos, D, dim, N
+        ctx.has_first_b = first_b is not None
+        ctx.save_for_backward(saved_x, first_w, pre_first, feat, w0, y0, a0, w2, y2)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        saved_x, first_w, pre_first, feat, w0, y0, a0, w2, y2 = ctx.saved_tensors
+        N, D, dim = ctx.N, ctx.D, ctx.dim
+        dev = dh.device
+        dh = _rowmajor(dh)
+        lib = _lib.load()
+        d_first_w = d_first_b = dw0 = db0 = dw2 = db2 = None
+        if ctx.is_embedding:
+            if ctx.needs_input_grad[1]:
+                tab = first_w.contiguous()
+                d_first_w = torch.empty_like(tab)
+                ws = _ws(lib.sgb_embedding_bwd_workspace_bytes(N, D, tab.size(0)), dev)
+                check(lib.sgb_embedding_bwd(ptr(dh), _ld(dh), ptr(saved_x), saved_x.element_size(), N, D,
+                                            tab.size(0), ptr(tab), ACT_GELU, ptr(d_first_w), ptr(ws), ws.numel(),
+                                            stream_ptr(dev)), "embedding_bwd")
+                _count(10)
+        else:
+            dpre = act_bwd(dh[:, :D], pre_first, ACT_GELU)
+            d_first_w, d_first_b = linear_wgrad(dpre, saved_x, want_db=ctx.has_first_b)
+        if ctx.use_pos:
+            dy2 = torch.empty(2 * N, dim, dtype=torch.float32, device=dev)
+            for d in range(2):
+                act_bwd(dh[:, D + d * dim: D + (d + 1) * dim], y2[d * N:(d + 1) * N], ACT_GELU,
+                        dx=dy2[d * N:(d + 1) * N])
+            dw2, db2 = linear_wgrad(dy2, a0)
+            dy0 = linear_dgrad(dy2, w2, act=ACT_SILU, act_pre=y0)
+            dw0, db0 = linear_wgrad(dy0, feat.view(2 * N, feat.size(-1)))
+        return None, d_first_w, d_first_b, None, dw0, db0, dw2, db2, None
+
+
+class OutputStageFn(torch.autograd.Function):
+    """lin_last + F.normalize for one node type (ist_encoder.py:328-332)."""
+
+    @staticmethod
+    def forward(ctx, h, w, b, normalize):
+        require_cuda(h, w, b)
+        y, _ = linear_fwd(h, w, b)
+        ctx.normalize = normalize
+        if not normalize:
+            ctx.save_for_backward(h, w, None, None)
+            return y
+        M, D = y.shape
+        e = torch.empty_like(y)
+        nrm = torch.empty(M, dtype=torch.float32, device=y.device)
+        check(_lib.load().sgb_l2norm_fwd(ptr(y), _ld(y), M, D, 1e-12, ptr(e), _ld(e), ptr(nrm), stream_ptr(y.device)),
+              "l2norm_fwd")
+        _count(1)
+        ctx.save_for_backward(h, w, e, nrm)
+        return e
+
+    @staticmethod
+    def backward(ctx, de):
+        h, w, e, nrm = ctx.saved_tensors
+        de = _rowmajor(de)
+        if ctx.normalize:
+            M, D = e.shape
+            dy = torch.empty_like(e)
+            check(_lib.load().sgb_l2norm_bwd(ptr(de), _ld(de), ptr(e), _ld(e), ptr(nrm), M, D, 1e-12, ptr(dy), _ld(dy),
+                                             stream_ptr(e.device)), "l2norm_bwd")
+            _count(1)
+        else:
+            dy = de
+        dh = linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
+        dw, db = linear_wgrad(dy, h)
+        return dh, dw, db, None
+
+
+# ------------------------------------------------------------------------------------------------
+# scoring
+# ------------------------------------------------------------------------------------------------
+def score_argmax(emb_tx: Tensor, emb_bd: Tensor, edge_index: Tensor, bd_index: Optional[Tensor],
+                 min_similarity: Optional[float] = None, eps: float = 1e-8):
+    """Fused cosine-similarity / scatter-max / cell lookup over candidate edges [2,E] (tx -> bd).
+
+    Returns (max_sim fp32 [N_tx], max_idx int64 [N_tx] (E where a transcript has no candidate),
+    seg_idx int64 [N_tx] (-1 where unassigned)) -- models/lightning_model.py:275-293.
+    """
+    require_cuda(emb_tx, emb_bd, edge_index, bd_index)
+    emb_tx, emb_bd = _rowmajor(emb_tx), _rowmajor(emb_bd)
+    n_tx, D = emb_tx.shape
+    dev = emb_tx.device
+    E = edge_index.size(1)
+    # candidate CSR over transcripts: the "destination" of the sort is the transcript row
+    csr = build_csr(edge_index.flip(0), emb_bd.size(0), n_tx, transpose=False)
+    max_sim = torch.empty(n_tx, dtype=torch.float32, device=dev)
+    arg = torch.empty(n_tx, dtype=torch.int64, device=dev)
+    seg = torch.empty(n_tx, dtype=torch.int64, device=dev)
+    if bd_index is not None:
+        if bd_index.dtype not in (torch.int32, torch.int64):
+            bd_index = bd_index.long()
+        bd_index = bd_index.contiguous()
+    ms = float("nan") if min_similarity is None else float(min_similarity)
+    check(_lib.load().sgb_score_argmax(ptr(emb_tx), _ld(emb_tx), ptr(emb_bd), _ld(emb_bd), D, ptr(csr.rowptr),
+                                       ptr(csr.col), ptr(csr.eid), n_tx, E, eps, ptr(bd_index),
+                                       bd_index.element_size() if bd_index is not None else 0, ms, ptr(max_sim),
+                                       ptr(arg), ptr(seg), stream_ptr(dev)), "score_argmax")
+    _count(1)
+    return max_sim, arg, seg

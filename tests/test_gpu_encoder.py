@@ -1,0 +1,193 @@
+"""GPU parity tests, module level: the drop-in ISTEncoder / SkipGAT / LitISTEncoder.predict_step /
+kdtree_neighbors against the CPU oracle on identical synthetic inputs and identical weights."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import neighbors_ref
+from oracle.ist_encoder_ref import TB, TT, predict_scores_ref
+from segger_b200 import ops
+from segger_b200.hetero import HeteroBatch
+from segger_b200.lightning_model import LitISTEncoder
+from segger_b200.neighbors import kdtree_neighbors, knn_table, knn_to_edge_index
+from tests.util import PRED, make_models, rel_err, synth_batch, to_dev
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+CONFIGS = [  # (in, hidden, out, n_mid, heads)
+    (128, 64, 64, 0, 2),     # BASELINE cfg-1/2 model ("2-layer hetero GATv2 hidden=64 heads=2")
+    (128, 64, 64, 2, 2),     # `segger segment` default (4 SkipGAT layers)
+    (16, 32, 32, 1, 3),      # ISTEncoder's own defaults -> generic (F=96) kernels
+    (64, 128, 128, 1, 4),    # cfg-4 shape (F=512)
+]
+
+
+def _loss(out, g):
+    return sum((out[k] * g[k]).sum() for k in ("tx", "bd"))
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_istencoder_forward_backward_vs_oracle(cfg):
+    in_c, hid, out_c, n_mid, heads = cfg
+    ts, x, edges, pos, bat = synth_batch(6000, 60, seed=1)
+    ref, prod = make_models(ts.n_genes, ts.bd_x.shape[1], in_c, hid, out_c, n_mid, heads, seed=3)
+    ref.eval(); prod.eval()
+    out_r = ref(x, edges, pos, bat)
+    gen = torch.Generator().manual_seed(0)
+    g = {k: torch.randn(v.shape, generator=gen) for k, v in out_r.items()}
+    _loss(out_r, g).backward()
+    out_p = prod(to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
+    _loss(out_p, to_dev(g)).backward()
+    for k in ("tx", "bd"):
+        assert out_p[k].shape == out_r[k].shape
+        assert rel_err(out_p[k], out_r[k]) < TOL, k
+    ref_grads = {n: p.grad for n, p in ref.named_parameters()}
+    checked = 0
+    for n, p in prod.named_parameters():
+        if "bd___contains___tx" in n:
+            continue
+        assert p.grad is not None, n
+        assert rel_err(p.grad, ref_grads[n]) < TOL, n
+        checked += 1
+    assert checked == len(ref_grads)
+
+
+def test_istencoder_train_mode_dropout_statistics_and_determinism():
+    ts, x, edges, pos, bat = synth_batch(4000, 40, seed=2)
+    _, prod = make_models(ts.n_genes, ts.bd_x.shape[1], 128, 64, 64, 0, 2, seed=1)
+    prod.train()
+    args = (to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
+    torch.manual_seed(5); a = prod(*args)["tx"].detach()
+    torch.manual_seed(5); b = prod(*args)["tx"].detach()
+    torch.manual_seed(6); c = prod(*args)["tx"].detach()
+    assert torch.equal(a, b)            # same torch seed -> same dropout realisation, bit-identical
+    assert not torch.equal(a, c)
+    prod.eval()
+    e = prod(*args)["tx"].detach()
+    assert float((a - e).abs().max()) > 0
+
+
+def test_skipgat_standalone_generic_and_fused_agree():
+    from segger_b200.ist_encoder import SkipGAT
+    torch.manual_seed(0)
+    ts, x, edges, pos, bat = synth_batch(3000, 30, seed=4)
+    layer = SkipGAT((-1, -1), 64, 2).cuda().eval()
+    xd = {"tx": torch.randn(3000, 96).cuda(), "bd": torch.randn(30, 96).cuda()}
+    ed = to_dev({TT: edges[TT], TB: edges[TB]})
+    fused = layer(xd, ed)
+    generic = layer.conv(xd, ed)
+    for k in ("tx", "bd"):
+        assert rel_err(fused[k], generic[k]) < 1e-6
+    # a caller that does supply bd-contains-tx edges gets the third conv through the generic path
+    ed[("bd", "contains", "tx")] = ed[TB].flip(0)
+    out = layer(xd, ed)
+    assert out["tx"].shape == (3000, 128)
+    aw = layer.attention_weights[TT]
+    assert aw.shape == (ed[TT].size(1), 2)
+    s = torch.zeros(3000, 2, device="cuda").index_add_(0, ed[TT][1], aw)
+    deg = torch.bincount(ed[TT][1], minlength=3000)
+    assert float((s[deg > 0] - 1).abs().max()) < 1e-5
+
+
+def test_predict_step_assignment_agreement():
+    ts, x, edges, pos, bat = synth_batch(20000, 200, seed=5, train_edges=False)
+    torch.manual_seed(0)
+    lit = LitISTEncoder(ts.n_genes, in_channels=128, n_mid_layers=0)
+    ref, _ = make_models(ts.n_genes, ts.bd_x.shape[1], 128, 64, 64, 0, 2, seed=3, device="cpu")
+    lit.model.load_state_dict(ref.state_dict(), strict=False)
+    lit = lit.cuda().eval(); ref.eval()
+    b = HeteroBatch()
+    for k in ("tx", "bd"):
+        b[k]["x"], b[k]["pos"], b[k]["batch"] = x[k], pos[k], bat[k]
+    b["tx"]["index"] = torch.from_numpy(ts.tx_index)
+    b["bd"]["index"] = torch.from_numpy(ts.bd_index) + 7
+    mask = torch.rand(20000, generator=torch.Generator().manual_seed(1)) < 0.8
+    b["tx"]["predict_mask"] = mask
+    for et in (TT, TB, PRED):
+        b[et]["edge_index"] = edges[et]
+    with torch.no_grad():
+        src_idx, seg_idx, max_sim, gen_idx = lit.predict_step(b.cuda(), 0)
+        emb = ref(x, edges, pos, bat)
+    seg_r, sim_r, _ = predict_scores_ref(emb["tx"], emb["bd"], edges[PRED], b["bd"]["index"])
+    assert not src_idx.is_cuda and src_idx.dtype == torch.int64 and seg_idx.dtype == torch.int64
+    assert torch.equal(src_idx, b["tx"]["index"][mask]) and torch.equal(gen_idx, x["tx"][mask])
+    agree = float((seg_idx == seg_r[mask]).float().mean())
+    assert agree >= 0.9999, agree
+    assert rel_err(max_sim, sim_r[mask]) < TOL
+    assert int((seg_idx >= 0).sum()) > 10000
+
+
+# ---------------------------------------------------------------------------------------------- kNN
+def _check_knn(points, k, r, query=None):
+    table, count = knn_table(points, k, r, query=query)
+    canon, n_tie, n_bf, raw = neighbors_ref.canonical_knn_table(points, k, r, query=query)
+    got = table.cpu().numpy()
+    assert got.shape == canon.shape
+    assert np.array_equal(got, canon), f"{(got != canon).any(1).sum()} rows differ"
+    assert np.array_equal(count.cpu().numpy(), (canon != points.shape[0]).sum(1))
+    return n_tie, raw, got
+
+
+@pytest.mark.parametrize("n,k,r,dtype", [(2000, 5, 5.0, np.float32), (50000, 5, 5.0, np.float32),
+                                         (30000, 20, 5.0, np.float32), (20000, 3, 2.5, np.float64),
+                                         (5000, 1 + 1, 50.0, np.float32), (10, 5, 5.0, np.float32)])
+def test_knn_table_bit_exact_vs_scipy(n, k, r, dtype):
+    rng = np.random.default_rng(n + k)
+    side = (n / 0.5) ** 0.5
+    pts = rng.uniform(0, side, (n, 2)).astype(dtype)
+    n_tie, raw, got = _check_knn(pts, k, r)
+    if n_tie == 0:
+        assert np.array_equal(got, raw)     # tie-free: identical to scipy's own row order
+
+
+def test_knn_ties_duplicates_and_lattice():
+    g = np.arange(40, dtype=np.float32)
+    lattice = np.stack(np.meshgrid(g, g), -1).reshape(-1, 2)            # massive exact ties
+    n_tie, _, _ = _check_knn(lattice, 5, 1.5)
+    assert n_tie > 0
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0, 30, (1500, 2)).astype(np.float32)
+    pts[100:110] = pts[100]                                             # coincident points
+    _check_knn(pts, 5, 5.0)
+    # strict radius: a neighbour at exactly max_dist is excluded (Appendix A.5)
+    ex = np.array([[0, 0], [5, 0], [0, 3], [100, 100]], dtype=np.float32)
+    t, _ = knn_table(ex, 3, 5.0)
+    assert t.cpu().tolist() == [[0, 2, 4], [1, 4, 4], [2, 0, 4], [3, 4, 4]]
+
+
+def test_knn_separate_query_set_and_clustered():
+    rng = np.random.default_rng(5)
+    centers = rng.uniform(0, 500, (50, 2))
+    pts = (centers[rng.integers(0, 50, 20000)] + rng.normal(0, 4, (20000, 2))).astype(np.float32)
+    _check_knn(pts, 5, 5.0)
+    qry = rng.uniform(-20, 520, (3000, 2)).astype(np.float32)           # some queries outside the bbox
+    _check_knn(pts, 4, 5.0, query=qry)
+
+
+def test_kdtree_neighbors_edge_list_matches_reference_call():
+    ts, x, edges, pos, bat = synth_batch(30000, 300, seed=7, train_edges=False)
+    ei, none = kdtree_neighbors(ts.tx_pos, 5, 5.0)
+    assert none is None and ei.dtype == torch.int64 and not ei.is_cuda
+    ref, _ = neighbors_ref.kdtree_neighbors(ts.tx_pos, 5, 5.0)
+    assert ei.shape == ref.shape
+    # same edge multiset; identical order wherever scipy's rows are tie-free
+    key = lambda e: np.unique(e[0].numpy() * (1 << 32) + e[1].numpy())
+    canon, n_tie, _, _ = neighbors_ref.canonical_knn_table(ts.tx_pos, 5, 5.0)
+    ce, _ = neighbors_ref.knn_to_edge_index(torch.from_numpy(canon), padding_value=30000)
+    assert torch.equal(ei, ce)
+    if n_tie == 0:
+        assert torch.equal(ei, ref)
+    else:
+        assert len(np.setxor1d(key(ei), key(ref))) <= 2 * n_tie
+    # self loop first for every transcript (A.5), query-major order
+    assert torch.equal(ei[0], torch.sort(ei[0], stable=True).values)
+
+
+def test_knn_to_edge_index_generic_padding():
+    t = torch.tensor([[1, 9, 2], [9, 9, 9], [0, 1, 9], [2, 9, 0]])
+    ei, ip = knn_to_edge_index(t.cuda(), padding_value=9)
+    er, ir = neighbors_ref.knn_to_edge_index(t, padding_value=9)
+    assert torch.equal(ei.cpu(), er) and torch.equal(ip.cpu(), ir)
+    ei2, _ = knn_to_edge_index(torch.full((4, 3), 4).cuda())          # default padding = N
+    assert ei2.shape == (2, 0)

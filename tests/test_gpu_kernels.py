@@ -1,0 +1,240 @@
+"""GPU parity tests, kernel level: every check goes through the C ABI (ctypes) and compares with the
+CPU oracle on identical seeded inputs.  Tolerance for fp32 work: 1e-4 relative to the tensor's scale
+(BASELINE.json north_star); integer/index work is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyg_ref
+from segger_b200 import ops
+from segger_b200._lib import ACT_GELU, ACT_NONE, ACT_SILU
+from tests.util import random_graph, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- CSR
+@pytest.mark.parametrize("E,n_src,n_dst,dtype", [
+    (0, 5, 7, torch.int64), (1, 1, 1, torch.int64), (37, 10, 12, torch.int32),
+    (5000, 300, 200, torch.int64), (70000, 70000, 1000, torch.int32), (300000, 5000, 100000, torch.int64)])
+def test_csr_build_bit_exact(E, n_src, n_dst, dtype):
+    ei = random_graph(n_src, n_dst, E, seed=E + 1, dtype=dtype) if E else torch.zeros(2, 0, dtype=dtype)
+    csr = ops.build_csr(ei.cuda(), n_src, n_dst, transpose=True)
+    src, dst = ei[0].long(), ei[1].long()
+    order = torch.argsort(dst, stable=True)
+    assert torch.equal(csr.eid.cpu().long(), order)
+    assert torch.equal(csr.col.cpu().long(), src[order])
+    rp = torch.zeros(n_dst + 1, dtype=torch.long)
+    rp[1:] = torch.bincount(dst, minlength=n_dst).cumsum(0)
+    assert torch.equal(csr.rowptr.cpu().long(), rp)
+    torder = torch.argsort(src, stable=True)
+    trp = torch.zeros(n_src + 1, dtype=torch.long)
+    trp[1:] = torch.bincount(src, minlength=n_src).cumsum(0)
+    assert torch.equal(csr.t_rowptr.cpu().long(), trp)
+    assert torch.equal(csr.t_dst.cpu().long(), dst[torder])
+    inv = torch.empty(E, dtype=torch.long)
+    inv[order] = torch.arange(E)
+    assert torch.equal(csr.t_pos.cpu().long(), inv[torder])
+    assert int(csr.status.item()) == 0
+
+
+def test_csr_strided_view_and_range_flag():
+    ei = random_graph(50, 60, 400, seed=3)
+    eit = ei.t().contiguous().cuda().t()          # [2,E] view with strides (1, 2)
+    assert not eit.is_contiguous()
+    a = ops.build_csr(eit, 50, 60)
+    b = ops.build_csr(ei.cuda(), 50, 60)
+    for f in ("rowptr", "col", "eid", "t_rowptr", "t_dst", "t_pos"):
+        assert torch.equal(getattr(a, f), getattr(b, f))
+    bad = ei.clone(); bad[1, 5] = 999
+    assert int(ops.build_csr(bad.cuda(), 50, 60).status.item()) == 1
+
+
+# ---------------------------------------------------------------------------------------------- GATv2
+def _gat_case(n_src, n_dst, E, H, C, seed, bipartite=True):
+    g = torch.Generator().manual_seed(seed)
+    F = H * C
+    x_l = torch.randn(n_src, F, generator=g)
+    x_r = torch.randn(n_dst, F, generator=g) if bipartite else torch.randn(n_src, F, generator=g)
+    att = torch.randn(1, H, C, generator=g) * 0.3
+    bias = torch.randn(F, generator=g) * 0.1
+    ei = random_graph(n_src, x_r.size(0), E, seed=seed) if E else torch.zeros(2, 0, dtype=torch.long)
+    return x_l, x_r, att, bias, ei
+
+
+SHAPES = [  # (H, C): vector path combos + generic path
+    (2, 64), (1, 128), (4, 32), (2, 128), (4, 64), (8, 32), (1, 256), (3, 128), (4, 128), (8, 64), (2, 256),
+    (1, 512), (3, 32), (1, 16), (2, 50), (5, 7), (1, 200)]
+
+
+@pytest.mark.parametrize("H,C", SHAPES)
+def test_gatv2_fwd_bwd_vs_oracle(H, C):
+    n_src, n_dst, E = 257, 131, 1900
+    x_l, x_r, att, bias, ei = _gat_case(n_src, n_dst, E, H, C, seed=H * 1000 + C)
+    xl_r, xr_r, att_r, b_r = (t.clone().requires_grad_() for t in (x_l, x_r, att, bias))
+    ref = pyg_ref.gatv2_aggregate(xl_r.view(n_src, H, C), xr_r.view(n_dst, H, C), ei, att_r, b_r)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(7))
+    (ref * w).sum().backward()
+
+    csr = ops.build_csr(ei.cuda(), n_src, n_dst)
+    xl_g, xr_g, att_g, b_g = (t.clone().cuda().requires_grad_() for t in (x_l, x_r, att, bias))
+    out = ops.GATv2AggregateFn.apply(xl_g, xr_g, att_g, b_g, csr, H, C, 0.2, 0.0, False, 0, False)
+    (out * w.cuda()).sum().backward()
+    assert rel_err(out, ref) < TOL
+    assert rel_err(xl_g.grad, xl_r.grad) < TOL
+    assert rel_err(xr_g.grad, xr_r.grad) < TOL
+    assert rel_err(att_g.grad, att_r.grad) < TOL
+    assert rel_err(b_g.grad, b_r.grad) < TOL
+    # isolated destination rows: out == bias exactly
+    deg = torch.bincount(ei[1], minlength=n_dst)
+    assert torch.equal(out.detach().cpu()[deg == 0], bias.expand(int((deg == 0).sum()), -1))
+
+
+def test_gatv2_fused_gelu_and_strided_slices():
+    H, C, N, E = 2, 64, 500, 3000
+    F = H * C
+    x_l, _, att, bias, ei = _gat_case(N, N, E, H, C, seed=5, bipartite=False)
+    g = torch.Generator().manual_seed(9)
+    y = torch.randn(N, 3 * F, generator=g)                       # concatenated projection buffer
+    yr = y.clone().requires_grad_()
+    ref = torch.nn.functional.gelu(pyg_ref.gatv2_aggregate(
+        yr[:, :F].reshape(N, H, C), yr[:, F:2 * F].reshape(N, H, C), ei, att, bias))
+    w = torch.randn(N, F, generator=g)
+    (ref * w).sum().backward()
+    csr = ops.build_csr(ei.cuda(), N, N)
+    yg = y.cuda()
+    out, h, smax, sden = ops.gatv2_fwd(yg[:, :F], yg[:, F:2 * F], att.cuda(), bias.cuda(), csr, H, C, 0.2, 0.0,
+                                       False, 0, True)
+    assert rel_err(h, ref) < TOL
+    G = torch.zeros(N, 3 * F, device="cuda")
+    ops.gatv2_bwd(yg[:, :F], yg[:, F:2 * F], att.cuda(), bias.cuda(), out, w.cuda(), True, csr, H, C, 0.2, 0.0,
+                  False, 0, smax, sden, grad_x_l=G[:, :F], grad_x_r=G[:, F:2 * F])
+    assert rel_err(G[:, :2 * F], yr.grad[:, :2 * F]) < TOL
+    assert float(G[:, 2 * F:].abs().max()) == 0.0
+
+
+def test_gatv2_edge_cases_empty_and_single():
+    H, C = 2, 64
+    F = H * C
+    # E = 0: output is the bias, gradients are zero
+    x_l, x_r = torch.randn(5, F), torch.randn(4, F)
+    att, bias = torch.randn(1, H, C), torch.randn(F)
+    csr = ops.build_csr(torch.zeros(2, 0, dtype=torch.long).cuda(), 5, 4)
+    xl_g, xr_g = x_l.cuda().requires_grad_(), x_r.cuda().requires_grad_()
+    out = ops.GATv2AggregateFn.apply(xl_g, xr_g, att.cuda(), bias.cuda(), csr, H, C, 0.2, 0.0, False, 0, False)
+    assert torch.equal(out.detach().cpu(), bias.expand(4, -1))
+    out.sum().backward()
+    assert float(xl_g.grad.abs().max()) == 0.0 and float(xr_g.grad.abs().max()) == 0.0
+    # a hub: one destination with a long row (exercises the chunk loop), self loops, int32 indices
+    n = 300
+    ei = torch.stack([torch.arange(n), torch.zeros(n, dtype=torch.long)]).int()
+    x = torch.randn(n, F)
+    ref = pyg_ref.gatv2_aggregate(x.view(n, H, C), x.view(n, H, C), ei.long(), att, bias)
+    csr = ops.build_csr(ei.cuda(), n, n)
+    got, _, _, _ = ops.gatv2_fwd(x.cuda(), x.cuda(), att.cuda(), bias.cuda(), csr, H, C, 0.2, 0.0, False, 0, False)
+    assert rel_err(got, ref) < TOL
+
+
+@pytest.mark.parametrize("H,C", [(2, 64), (3, 32)])
+def test_gatv2_dropout_replays_injected_mask(H, C):
+    n_src, n_dst, E, p = 200, 150, 2500, 0.2
+    x_l, x_r, att, bias, ei = _gat_case(n_src, n_dst, E, H, C, seed=11)
+    seed = 123456789
+    keep = ops.dropout_keep_mask(seed, E, H, p, "cuda").cpu()
+    assert abs(float(keep.float().mean()) - (1 - p)) < 0.02          # drop rate
+    xl_r, xr_r = x_l.clone().requires_grad_(), x_r.clone().requires_grad_()
+    ref = pyg_ref.gatv2_aggregate(xl_r.view(n_src, H, C), xr_r.view(n_dst, H, C), ei, att, bias,
+                                  dropout_p=p, training=True, keep_mask=keep)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(3))
+    (ref * w).sum().backward()
+    csr = ops.build_csr(ei.cuda(), n_src, n_dst)
+    xl_g, xr_g = x_l.cuda().requires_grad_(), x_r.cuda().requires_grad_()
+    out = ops.GATv2AggregateFn.apply(xl_g, xr_g, att.cuda(), bias.cuda(), csr, H, C, 0.2, p, True, seed, False)
+    (out * w.cuda()).sum().backward()
+    assert rel_err(out, ref) < TOL
+    assert rel_err(xl_g.grad, xl_r.grad) < TOL
+    assert rel_err(xr_g.grad, xr_r.grad) < TOL
+
+
+def test_gatv2_deterministic_and_permutation_invariant():
+    H, C, N, E = 2, 64, 400, 5000
+    x_l, x_r, att, bias, ei = _gat_case(N, N, E, H, C, seed=21, bipartite=False)
+    args = (x_l.cuda(), x_r.cuda(), att.cuda(), bias.cuda())
+    csr = ops.build_csr(ei.cuda(), N, N)
+    a = ops.gatv2_fwd(*args, csr, H, C, 0.2, 0.0, False, 0, False)[0]
+    b = ops.gatv2_fwd(*args, csr, H, C, 0.2, 0.0, False, 0, False)[0]
+    assert torch.equal(a, b)                                          # bit-reproducible
+    perm = torch.randperm(E, generator=torch.Generator().manual_seed(1))
+    c = ops.gatv2_fwd(*args, ops.build_csr(ei[:, perm].cuda(), N, N), H, C, 0.2, 0.0, False, 0, False)[0]
+    assert rel_err(c, a) < 1e-5                                       # only summation order changes
+    alpha = ops.gatv2_alpha(args[0], args[1], args[2], csr, H, C, 0.2, *ops.gatv2_fwd(
+        *args, csr, H, C, 0.2, 0.0, False, 0, False)[2:])
+    _, alpha_ref = pyg_ref.gatv2_aggregate(x_l.view(N, H, C), x_r.view(N, H, C), ei, att, bias, return_alpha=True)
+    assert rel_err(alpha, alpha_ref) < TOL
+
+
+# ---------------------------------------------------------------------------------------------- linear
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (7, 5, 3), (300, 384, 256), (1000, 64, 128), (129, 130, 131),
+                                   (4096, 8, 256), (50, 128, 50)])
+@pytest.mark.parametrize("act", [ACT_NONE, ACT_GELU, ACT_SILU])
+def test_linear_fwd_bwd_vs_torch(M, N, K, act):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    xr, wr, br = (t.clone().requires_grad_() for t in (x, w, b))
+    y = torch.nn.functional.linear(xr, wr, br)
+    y = {ACT_NONE: y, ACT_GELU: torch.nn.functional.gelu(y), ACT_SILU: torch.nn.functional.silu(y)}[act]
+    gy = torch.randn(M, N, generator=g)
+    (y * gy).sum().backward()
+    xg, wg, bg = (t.clone().cuda().requires_grad_() for t in (x, w, b))
+    yg = ops.linear(xg, wg, bg, act)
+    (yg * gy.cuda()).sum().backward()
+    assert rel_err(yg, y) < TOL
+    assert rel_err(xg.grad, xr.grad) < TOL
+    assert rel_err(wg.grad, wr.grad) < TOL
+    assert rel_err(bg.grad, br.grad) < TOL
+
+
+def test_linear_wgrad_large_m_splitk_deterministic():
+    M, N, K = 200_000, 384, 128
+    g = torch.Generator().manual_seed(1)
+    dy, x = torch.randn(M, N, generator=g), torch.randn(M, K, generator=g)
+    dw, db = ops.linear_wgrad(dy.cuda(), x.cuda())
+    dw2, db2 = ops.linear_wgrad(dy.cuda(), x.cuda())
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    ref = dy.double().t() @ x.double()
+    assert rel_err(dw, ref) < TOL
+    assert rel_err(db, dy.double().sum(0)) < TOL
+
+
+# ---------------------------------------------------------------------------------------------- scoring
+@pytest.mark.parametrize("D", [64, 32, 128, 256, 20])
+def test_score_argmax_vs_oracle(D):
+    from oracle.ist_encoder_ref import predict_scores_ref
+    g = torch.Generator().manual_seed(D)
+    n_tx, n_bd, E = 3000, 200, 5000
+    tx = torch.nn.functional.normalize(torch.randn(n_tx, D, generator=g), dim=-1)
+    bd = torch.nn.functional.normalize(torch.randn(n_bd, D, generator=g), dim=-1)
+    src = torch.randint(0, n_tx - 500, (E,), generator=g)           # last 500 tx have no candidate
+    dst = torch.randint(0, n_bd, (E,), generator=g)
+    src[src == 7] = 8
+    src[10:14] = 7; dst[10:14] = 3                                   # exact ties -> lowest edge id
+    ei = torch.stack([src, dst]).int()
+    bd_index = torch.randperm(n_bd, generator=g).int() + 1000
+    for ms in (None, 0.05):
+        seg_r, sim_r, idx_r = predict_scores_ref(tx, bd, ei, bd_index, ms)
+        sim, idx, seg = ops.score_argmax(tx.cuda(), bd.cuda(), ei.cuda(), bd_index.cuda(), ms)
+        assert rel_err(sim, sim_r) < TOL
+        agree = (idx.cpu() == idx_r).float().mean()
+        assert agree >= 0.9999, agree
+        assert (seg.cpu() == seg_r).float().mean() >= 0.9999
+        assert int(idx[7]) == 10
+        assert torch.equal(idx.cpu()[-500:], torch.full((500,), E)) and torch.equal(seg.cpu()[-500:], torch.full((500,), -1))
+        assert float(sim[-500:].abs().max()) == 0.0
+
+
+def test_score_argmax_no_edges():
+    sim, idx, seg = ops.score_argmax(torch.randn(10, 64).cuda(), torch.randn(3, 64).cuda(),
+                                     torch.zeros(2, 0, dtype=torch.int32).cuda(), torch.arange(3).int().cuda())
+    assert float(sim.abs().max()) == 0.0 and torch.equal(idx.cpu(), torch.zeros(10, dtype=torch.long))
+    assert torch.equal(seg.cpu(), torch.full((10,), -1))
