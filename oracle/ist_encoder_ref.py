@@ -71,7 +71,8 @@ class Positional2dEmbedderRef(torch.nn.Module):
         shape = pos.shape
         emb = sinusoidal_embedding(pos.flatten(), self.frequency_embedding_size, max_period=10000)
         pos_freq = emb.reshape(shape + (self.frequency_embedding_size,))
-        return self.mlp(pos_freq).flatten(-2)
+        # (.to() is a no-op in fp32; it lets the fp64 copy of the oracle run for conditioning checks)
+        return self.mlp(pos_freq.to(self.mlp[0].weight.dtype)).flatten(-2)
 
 
 class SkipGATRef(torch.nn.Module):

@@ -27,6 +27,20 @@ def _loss(out, g):
     return sum((out[k] * g[k]).sum() for k in ("tx", "bd"))
 
 
+def _fp64_truth(ref, x, edges, pos, bat, g):
+    """fp64 copy of the oracle: the conditioning yardstick.  Some gradients (e.g. lin_r of a deep
+    layer, whose true value is a small difference of large terms) are only reproducible to ~1e-2
+    in fp32 *by the reference itself*; for those the bar is "no worse than 2x the fp32 oracle's own
+    distance from the fp64 result" instead of the flat 1e-4."""
+    import copy
+    r64 = copy.deepcopy(ref).double()
+    r64.zero_grad()
+    x64 = {"tx": x["tx"], "bd": x["bd"].double()}
+    out = r64(x64, edges, {k: v.double() for k, v in pos.items()}, bat)
+    _loss(out, {k: v.double() for k, v in g.items()}).backward()
+    return out, {n: p.grad for n, p in r64.named_parameters()}
+
+
 @pytest.mark.parametrize("cfg", CONFIGS)
 def test_istencoder_forward_backward_vs_oracle(cfg):
     in_c, hid, out_c, n_mid, heads = cfg
@@ -37,6 +51,7 @@ def test_istencoder_forward_backward_vs_oracle(cfg):
     gen = torch.Generator().manual_seed(0)
     g = {k: torch.randn(v.shape, generator=gen) for k, v in out_r.items()}
     _loss(out_r, g).backward()
+    out_64, grads_64 = _fp64_truth(ref, x, edges, pos, bat, g)
     out_p = prod(to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
     _loss(out_p, to_dev(g)).backward()
     for k in ("tx", "bd"):
@@ -48,7 +63,10 @@ def test_istencoder_forward_backward_vs_oracle(cfg):
         if "bd___contains___tx" in n:
             continue
         assert p.grad is not None, n
-        assert rel_err(p.grad, ref_grads[n]) < TOL, n
+        noise = rel_err(ref_grads[n], grads_64[n])          # fp32 oracle's own conditioning error
+        assert rel_err(p.grad, grads_64[n]) < max(TOL, 2 * noise), (n, noise)
+        if noise < TOL / 4:
+            assert rel_err(p.grad, ref_grads[n]) < TOL, n     # well-conditioned: flat 1e-4 vs the fp32 oracle
         checked += 1
     assert checked == len(ref_grads)
 

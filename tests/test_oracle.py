@@ -1,0 +1,169 @@
+"""CPU tests of the oracle itself (no GPU).  The GATv2 restatement is unpinned by the reference
+(no tests / golden vectors exist, PyG is not installable here), so it is held to self-consistency
+properties: fp64 gradcheck, equivalence with a dense masked-attention formulation, softmax row
+sums, permutation equivariance, and the committed golden vectors.  The kNN oracle is the
+reference's own scipy call and is cross-checked by brute force."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import neighbors_ref, pyg_ref
+from oracle.ist_encoder_ref import (ISTEncoderRef, Positional2dEmbedderRef, predict_scores_ref, scatter_max_ref,
+                                    sinusoidal_embedding)
+from tests.util import random_graph
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _case(n_src, n_dst, E, H, C, seed, dtype=torch.float64):
+    g = torch.Generator().manual_seed(seed)
+    x_l = torch.randn(n_src, H, C, generator=g, dtype=dtype)
+    x_r = torch.randn(n_dst, H, C, generator=g, dtype=dtype)
+    att = torch.randn(1, H, C, generator=g, dtype=dtype)
+    bias = torch.randn(H * C, generator=g, dtype=dtype)
+    return x_l, x_r, att, bias, random_graph(n_src, n_dst, E, seed)
+
+
+def test_gatv2_gradcheck_fp64():
+    x_l, x_r, att, bias, ei = _case(6, 5, 14, 2, 3, seed=0)
+    for t in (x_l, x_r, att, bias):
+        t.requires_grad_()
+    assert torch.autograd.gradcheck(lambda a, b, c, d: pyg_ref.gatv2_aggregate(a, b, ei, c, d), (x_l, x_r, att, bias))
+
+
+def test_gatv2_equals_dense_masked_attention():
+    n_src, n_dst, H, C = 9, 7, 2, 4
+    x_l, x_r, att, bias, _ = _case(n_src, n_dst, 1, H, C, seed=1)
+    g = torch.Generator().manual_seed(2)
+    adj = torch.rand(n_dst, n_src, generator=g) < 0.4
+    adj[3] = False                                      # isolated destination
+    dst, src = adj.nonzero(as_tuple=True)
+    out = pyg_ref.gatv2_aggregate(x_l, x_r, torch.stack([src, dst]), att, bias)
+    e = torch.nn.functional.leaky_relu(x_l[None] + x_r[:, None], 0.2)       # [n_dst, n_src, H, C]
+    a = (e * att).sum(-1).masked_fill(~adj[..., None], float("-inf"))
+    alpha = torch.softmax(a, dim=1).nan_to_num(0.0)
+    dense = torch.einsum("ijh,jhc->ihc", alpha, x_l).reshape(n_dst, H * C) + bias
+    assert torch.allclose(out, dense, atol=1e-12)
+    assert torch.equal(out[3], bias)                    # isolated row = bias
+
+
+def test_softmax_rows_sum_to_one_and_permutation_equivariance():
+    x_l, x_r, att, bias, ei = _case(30, 20, 200, 3, 5, seed=3)
+    out, alpha = pyg_ref.gatv2_aggregate(x_l, x_r, ei, att, bias, return_alpha=True)
+    s = torch.zeros(20, 3, dtype=torch.float64).index_add_(0, ei[1], alpha)
+    deg = torch.bincount(ei[1], minlength=20)
+    assert torch.allclose(s[deg > 0], torch.ones_like(s[deg > 0]))
+    assert torch.all(s[deg == 0] == 0)
+    perm = torch.randperm(200, generator=torch.Generator().manual_seed(0))
+    out2 = pyg_ref.gatv2_aggregate(x_l, x_r, ei[:, perm], att, bias)
+    assert torch.allclose(out, out2, atol=1e-12)
+
+
+def test_dropout_mask_injection_matches_manual():
+    x_l, x_r, att, bias, ei = _case(12, 10, 60, 2, 4, seed=4)
+    keep = torch.rand(60, 2, generator=torch.Generator().manual_seed(1)) > 0.2
+    out = pyg_ref.gatv2_aggregate(x_l, x_r, ei, att, None, dropout_p=0.2, training=True, keep_mask=keep)
+    _, alpha = pyg_ref.gatv2_aggregate(x_l, x_r, ei, att, None, return_alpha=True)
+    w = alpha * keep / 0.8
+    manual = torch.zeros(10, 2, 4, dtype=torch.float64).index_add_(0, ei[1], x_l[ei[0]] * w[..., None]).reshape(10, 8)
+    assert torch.allclose(out, manual, atol=1e-12)
+
+
+def test_scatter_max_semantics():
+    src = torch.tensor([0.5, 0.9, 0.9, -1.0, 0.1])
+    index = torch.tensor([2, 0, 0, 3, 2])
+    out, arg = scatter_max_ref(src, index, 5)
+    assert out.tolist() == pytest.approx([0.9, 0.0, 0.5, -1.0, 0.0])
+    assert arg.tolist() == [1, 5, 0, 3, 5]               # ties -> first; empty -> (0, E)
+    out, arg = scatter_max_ref(torch.zeros(0), torch.zeros(0, dtype=torch.long), 3)
+    assert out.tolist() == [0, 0, 0] and arg.tolist() == [0, 0, 0]
+
+
+def test_predict_scores_ref_unassigned_and_threshold():
+    tx = torch.nn.functional.normalize(torch.randn(6, 8, generator=torch.Generator().manual_seed(0)), dim=-1)
+    bd = torch.nn.functional.normalize(torch.randn(3, 8, generator=torch.Generator().manual_seed(1)), dim=-1)
+    ei = torch.tensor([[0, 0, 2, 5], [0, 1, 2, 1]], dtype=torch.int32)
+    seg, sim, idx = predict_scores_ref(tx, bd, ei, torch.tensor([10, 11, 12], dtype=torch.int32))
+    assert seg[1] == -1 and seg[3] == -1 and seg[4] == -1 and idx[1] == 4
+    assert seg[2] == 12 and seg[5] == 11
+    seg2, _, _ = predict_scores_ref(tx, bd, ei, torch.tensor([10, 11, 12]), min_similarity=2.0)
+    assert torch.all(seg2 == -1)
+
+
+def test_positional_embedder_matches_reference_loop_semantics():
+    torch.manual_seed(0)
+    pe = Positional2dEmbedderRef(16)
+    pos = torch.rand(50, 2) * 100
+    batch = torch.randint(0, 3, (50,))
+    out = pe(pos, batch)
+    assert out.shape == (50, 16)
+    # a tile's embedding depends only on that tile's own points
+    m = batch == 1
+    out1 = pe(pos[m], torch.zeros(int(m.sum()), dtype=torch.long))
+    assert torch.allclose(out[m], out1, atol=1e-6)
+    emb = sinusoidal_embedding(torch.tensor([0.0, 1.0]), 256, max_period=10000)
+    assert emb.shape == (2, 256) and torch.all(emb[0, :128] == 1) and torch.all(emb[0, 128:] == 0)
+
+
+def test_istencoder_ref_shapes_and_state_dict_keys():
+    m = ISTEncoderRef(50, 12, in_channels=16, hidden_channels=8, out_channels=8, n_mid_layers=1, n_heads=2)
+    keys = set(m.state_dict().keys())
+    for k in ("lin_first.tx.weight", "lin_first.bd.bias", "pos_emb.mlp.0.weight", "pos_emb.mlp.2.bias",
+              "conv_layers.0.conv.convs.<tx___neighbors___tx>.lin_l.weight",
+              "conv_layers.2.conv.convs.<tx___belongs___bd>.att", "lin_last.lins.bd.weight"):
+        assert k in keys, k
+    assert m.conv_layers[0].conv.convs["<tx___neighbors___tx>"].lin_l.weight.shape == (16, 32)
+    assert m.conv_layers[1].conv.convs["<tx___neighbors___tx>"].lin_l.weight.shape == (16, 16)
+
+
+# ------------------------------------------------------------------------------------------- kNN
+def test_knn_oracle_vs_bruteforce_and_scipy_properties():
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0, 60, (1500, 2)).astype(np.float32)
+    canon, n_tie, n_bf, raw = neighbors_ref.canonical_knn_table(pts, 5, 5.0)
+    brute = neighbors_ref.brute_force_knn_table(pts, 5, 5.0)
+    assert np.array_equal(canon, brute)
+    assert np.array_equal(canon[:, 0], np.arange(1500))            # self is neighbour 0 (Appendix A.5)
+    d, i = neighbors_ref.kdtree_table(np.array([[0, 0], [5, 0], [0, 3]], dtype=np.float32), 3, 5.0)
+    assert i.tolist() == [[0, 2, 3], [1, 3, 3], [2, 0, 3]]           # d == max_dist is excluded, pad = n
+    ei, _ = neighbors_ref.kdtree_neighbors(pts, 5, 5.0, chunk_size=400)
+    ei2, _ = neighbors_ref.kdtree_neighbors(pts, 5, 5.0)
+    assert torch.equal(ei, ei2)                                    # chunking does not change the result
+
+
+def test_knn_canonical_handles_ties():
+    g = np.arange(12, dtype=np.float32)
+    lattice = np.stack(np.meshgrid(g, g), -1).reshape(-1, 2)
+    canon, n_tie, n_bf, _ = neighbors_ref.canonical_knn_table(lattice, 5, 1.5)
+    assert n_tie > 0 and n_bf > 0
+    assert np.array_equal(canon, neighbors_ref.brute_force_knn_table(lattice, 5, 1.5))
+
+
+def test_knn_to_edge_index_restatement():
+    t = torch.tensor([[0, 2, 4], [1, 4, 4], [4, 4, 4], [3, 0, 1]])
+    ei, ip = neighbors_ref.knn_to_edge_index(t)
+    assert ei.tolist() == [[0, 0, 1, 3, 3, 3], [0, 2, 1, 3, 0, 1]]
+    assert ip.tolist() == [0, 2, 3, 3, 6]
+
+
+# ------------------------------------------------------------------------------------------- golden
+def test_oracle_reproduces_committed_golden_vectors():
+    """tests/golden/*.pt were produced by tests/golden/make_golden.py from this oracle (the reference
+    itself cannot run here); they freeze the oracle so that later edits cannot silently change it."""
+    path = os.path.join(GOLD, "gatv2_small.pt")
+    g = torch.load(path)
+    out = pyg_ref.gatv2_aggregate(g["x_l"], g["x_r"], g["edge_index"], g["att"], g["bias"])
+    assert torch.allclose(out, g["out"], atol=1e-6)
+    enc = torch.load(os.path.join(GOLD, "encoder_small.pt"))
+    m = ISTEncoderRef(**enc["hparams"])
+    m.load_state_dict(enc["state_dict"])
+    m.eval()
+    o = m(enc["x"], enc["edges"], enc["pos"], enc["batch"])
+    for k in ("tx", "bd"):
+        assert torch.allclose(o[k], enc["out"][k], atol=1e-5)
+    kn = np.load(os.path.join(GOLD, "knn_small.npz"))
+    _, idx = neighbors_ref.kdtree_table(kn["points"], int(kn["k"]), float(kn["max_dist"]))
+    assert np.array_equal(idx, kn["scipy_idx"])
