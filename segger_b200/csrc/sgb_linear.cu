@@ -13,14 +13,16 @@ static int check_dims(const char* fn, int64_t M, int64_t N, int64_t K) {
 
 extern "C" int sgb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b, int64_t M,
                               int64_t N, int64_t K, float* y, int64_t ldy, int act, float* y_act, int64_t ldya,
-                              void* stream) {
+                              int exact, void* stream) {
   int rc = check_dims("linear_fwd", M, N, K);
   if (rc != SGB_OK) return rc;
   if (M == 0 || N == 0) return SGB_OK;
   SGB_REQUIRE(y && (K == 0 || (x && w)), SGB_ERR_ARG, "linear_fwd: null tensor");
   SGB_REQUIRE(ldx >= K && ldw >= K && ldy >= N && (!y_act || ldya >= N), SGB_ERR_ARG, "linear_fwd: leading dimension too small");
   SGB_REQUIRE(act >= SGB_ACT_NONE && act <= SGB_ACT_SILU, SGB_ERR_ARG, "linear_fwd: unknown activation %d", act);
-  return simt_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, act, y_act, ldya, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!exact && tc_linear_fwd_ok(x, ldx, w, ldw, M, N, K)) return tc_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, act, y_act, ldya, st);
+  return simt_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, act, y_act, ldya, st);
 }
 
 extern "C" int sgb_linear_dgrad(const float* dy, int64_t ldy, const float* w, int64_t ldw, int64_t M, int64_t N,
@@ -31,11 +33,20 @@ extern "C" int sgb_linear_dgrad(const float* dy, int64_t ldy, const float* w, in
   if (M == 0 || K == 0) return SGB_OK;
   SGB_REQUIRE(dx && (N == 0 || (dy && w)), SGB_ERR_ARG, "linear_dgrad: null tensor");
   SGB_REQUIRE(ldy >= N && ldw >= K && ldx >= K && (!act_pre || ld_pre >= K), SGB_ERR_ARG, "linear_dgrad: leading dimension too small");
-  return simt_linear_dgrad(dy, ldy, w, ldw, M, N, K, dx, ldx, accumulate, act, act_pre, ld_pre, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tc_linear_dgrad_ok(dy, ldy, w, ldw, M, N, K))
+    return tc_linear_dgrad(dy, ldy, w, ldw, M, N, K, dx, ldx, accumulate, act, act_pre, ld_pre, st);
+  return simt_linear_dgrad(dy, ldy, w, ldw, M, N, K, dx, ldx, accumulate, act, act_pre, ld_pre, st);
+}
+
+static size_t wgrad_gemm_ws(int64_t M, int64_t N, int64_t K) {
+  const size_t a = simt_linear_wgrad_workspace_bytes(M, N, K);
+  const size_t b = tc_enabled() ? tc_linear_wgrad_workspace_bytes(M, N, K) : 0;
+  return a > b ? a : b;
 }
 
 extern "C" size_t sgb_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-  return simt_linear_wgrad_workspace_bytes(M, N, K);
+  return wgrad_gemm_ws(M, N, K) + linear_colsum_workspace_bytes(M, N);
 }
 
 extern "C" int sgb_linear_wgrad(const float* dy, int64_t ldy, const float* x, int64_t ldx, int64_t M, int64_t N,
@@ -46,5 +57,13 @@ extern "C" int sgb_linear_wgrad(const float* dy, int64_t ldy, const float* x, in
   if (N == 0) return SGB_OK;
   SGB_REQUIRE((K == 0 || dw) && (M == 0 || (dy && (K == 0 || x))), SGB_ERR_ARG, "linear_wgrad: null tensor");
   SGB_REQUIRE(ldy >= N && ldx >= K && lddw >= K, SGB_ERR_ARG, "linear_wgrad: leading dimension too small");
-  return simt_linear_wgrad(dy, ldy, x, ldx, M, N, K, dw, lddw, db, accumulate, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  SGB_REQUIRE(ws && ws_bytes >= sgb_linear_wgrad_workspace_bytes(M, N, K), SGB_ERR_WORKSPACE, "linear_wgrad: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (K > 0) {
+    if (tc_linear_wgrad_ok(dy, ldy, x, ldx, M, N, K)) rc = tc_linear_wgrad(dy, ldy, x, ldx, M, N, K, dw, lddw, accumulate, ws, st);
+    else rc = simt_linear_wgrad(dy, ldy, x, ldx, M, N, K, dw, lddw, accumulate, ws, st);
+    if (rc != SGB_OK) return rc;
+  }
+  if (db) rc = linear_colsum(dy, ldy, M, N, db, accumulate, static_cast<char*>(ws) + wgrad_gemm_ws(M, N, K), st);
+  return rc;
 }

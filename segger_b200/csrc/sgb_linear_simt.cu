@@ -329,45 +329,46 @@ static int64_t colsum_chunks(int64_t M) {
   return c;
 }
 
+size_t linear_colsum_workspace_bytes(int64_t M, int64_t N) {
+  return align_up(static_cast<size_t>(colsum_chunks(M)) * (N > 0 ? N : 1) * sizeof(float));
+}
+
+// db[n] (+)= sum_m dy[m, n]; two deterministic stages
+int linear_colsum(const float* dy, int64_t ldy, int64_t M, int64_t N, float* db, int accumulate, void* ws,
+                  cudaStream_t stream) {
+  float* cs = static_cast<float*>(ws);
+  const int64_t chunks = colsum_chunks(M);
+  const int64_t rpb = ceil_div(M > 0 ? M : 1, chunks);
+  dim3 grid(static_cast<unsigned>(ceil_div(N, 64)), static_cast<unsigned>(chunks));
+  colsum_stage1_kernel<<<grid, 256, 0, stream>>>(dy, ldy, M, N, rpb, cs);
+  colsum_stage2_kernel<<<static_cast<unsigned>(ceil_div(N, 128)), 128, 0, stream>>>(cs, chunks, N, db, accumulate);
+  return check_launch("colsum");
+}
+
 size_t simt_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-  const size_t part = static_cast<size_t>(wgrad_splits(M, N, K)) * N * K * sizeof(float);
-  const size_t cs = static_cast<size_t>(colsum_chunks(M)) * N * sizeof(float);
-  return align_up(part) + align_up(cs);
+  return align_up(static_cast<size_t>(wgrad_splits(M, N, K)) * N * (K > 0 ? K : 1) * sizeof(float));
 }
 
 int simt_linear_wgrad(const float* dy, int64_t ldy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K,
-                      float* dw, int64_t lddw, float* db, int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                      float* dw, int64_t lddw, int accumulate, void* ws, cudaStream_t stream) {
   // dw[N,K] = dy^T[N,M] * x[M,K]: reduction over M
-  SGB_REQUIRE(ws && ws_bytes >= simt_linear_wgrad_workspace_bytes(M, N, K), SGB_ERR_WORKSPACE, "linear_wgrad: workspace too small");
+  if (K == 0) return SGB_OK;
   const int splits = wgrad_splits(M, N, K);
   float* part = static_cast<float*>(ws);
-  float* cs = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up(static_cast<size_t>(splits) * N * K * sizeof(float)));
   GemmParams p{};
   p.A = dy; p.lda = ldy; p.B = x; p.ldb = ldx; p.M = N; p.N = K; p.K = M;
   p.k_chunk = ceil_div(ceil_div(M > 0 ? M : 1, splits), BK) * BK;
   p.vec_a = vec_ok(dy, ldy, N); p.vec_b = vec_ok(x, ldx, K);
-  int rc;
   if (splits == 1) {
     p.C = dw; p.ldc = lddw; p.accumulate = accumulate;
-    rc = launch<false, false>(p, 1, stream);
-  } else {
-    p.C = part; p.ldc = K;
-    rc = launch<false, false>(p, splits, stream);
-    if (rc != SGB_OK) return rc;
-    const int64_t MN = N * K;
-    splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div(MN, 256)), 256, 0, stream>>>(part, splits, MN, K, dw, lddw, accumulate);
-    rc = check_launch("splitk_reduce");
+    return launch<false, false>(p, 1, stream);
   }
+  p.C = part; p.ldc = K;
+  int rc = launch<false, false>(p, splits, stream);
   if (rc != SGB_OK) return rc;
-  if (db) {
-    const int64_t chunks = colsum_chunks(M);
-    const int64_t rpb = ceil_div(M > 0 ? M : 1, chunks);
-    dim3 grid(static_cast<unsigned>(ceil_div(N, 64)), static_cast<unsigned>(chunks));
-    colsum_stage1_kernel<<<grid, 256, 0, stream>>>(dy, ldy, M, N, rpb, cs);
-    colsum_stage2_kernel<<<static_cast<unsigned>(ceil_div(N, 128)), 128, 0, stream>>>(cs, chunks, N, db, accumulate);
-    rc = check_launch("colsum");
-  }
-  return rc;
+  const int64_t MN = N * K;
+  splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div(MN, 256)), 256, 0, stream>>>(part, splits, MN, K, dw, lddw, accumulate);
+  return check_launch("splitk_reduce");
 }
 
 }  // namespace sgb

@@ -125,7 +125,7 @@ class SkipGAT(Module):
             tt.lin_l.weight, tt.lin_l.bias, tt.lin_r.weight, tt.lin_r.bias, tt.att, tt.bias,
             tb.lin_l.weight, tb.lin_l.bias, tb.lin_r.weight, tb.lin_r.bias, tb.att, tb.bias,
             csr_tt, csr_tb, tt.heads, tt.out_channels, tt.negative_slope, tt.dropout, training,
-            seed_tt, seed_tb, apply_gelu)
+            seed_tt, seed_tb, apply_gelu, torch.is_grad_enabled())
         return {"tx": h_tx, "bd": h_bd}
 
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict: Dict[str, Tensor]) -> Dict[str, Tensor]:
@@ -191,9 +191,10 @@ class ISTEncoder(torch.nn.Module):
             w0, b0 = self.pos_emb.mlp[0].weight, self.pos_emb.mlp[0].bias
             w2, b2 = self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias
         if isinstance(first, Embedding):
-            return ops.InputStageFn.apply(x, first.weight, None, feat, w0, b0, w2, b2, True)
+            return ops.InputStageFn.apply(x, first.weight, None, feat, w0, b0, w2, b2, True, torch.is_grad_enabled())
         first.materialize(x.size(-1), x)
-        return ops.InputStageFn.apply(x, first.weight, first.bias, feat, w0, b0, w2, b2, False)
+        return ops.InputStageFn.apply(x, first.weight, first.bias, feat, w0, b0, w2, b2, False,
+                                      torch.is_grad_enabled())
 
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict: Dict[str, Tensor], pos_dict: Dict[str, Tensor],
                 batch_dict: Dict[str, Tensor]) -> Dict[str, Tensor]:

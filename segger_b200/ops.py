@@ -137,8 +137,15 @@ def new_seed() -> int:
 # ------------------------------------------------------------------------------------------------
 def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE,
                y: Optional[Tensor] = None, y_act: Optional[Tensor] = None,
-               want_pre: bool = True) -> Tuple[Optional[Tensor], Optional[Tensor]]:
-    """(y, act(y)) with y = x w^T + b.  y / y_act may be preallocated (strided) views."""
+               want_pre: bool = True, exact: Optional[bool] = None) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """(y, act(y)) with y = x w^T + b.  y / y_act may be preallocated (strided) views.
+
+    ``exact``: force the round-to-nearest fp32 SIMT GEMM instead of the tcgen05 split-TF32 one.
+    Default: exact while autograd is recording (the result will be differentiated through the
+    attention layers, whose backward amplifies the tensor core's biased accumulation error --
+    DESIGN.md "GEMM precision"), tensor cores under ``torch.no_grad()`` (inference)."""
+    if exact is None:
+        exact = torch.is_grad_enabled()
     x, w = _rowmajor(x), _rowmajor(w)
     M, K = x.shape
     N = w.size(0)
@@ -151,7 +158,8 @@ def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE,
         y_act = torch.empty(M, N, dtype=torch.float32, device=dev)
     b = _vec(b)
     check(_lib.load().sgb_linear_fwd(ptr(x), _ld(x), ptr(w), _ld(w), ptr(b), M, N, K, ptr(y), _ld(y), act,
-                                     ptr(y_act), _ld(y_act) if y_act is not None else 0, stream_ptr(dev)),
+                                     ptr(y_act), _ld(y_act) if y_act is not None else 0, int(bool(exact)),
+                                     stream_ptr(dev)),
           "linear_fwd")
     _count(1)
     return y, y_act
@@ -299,11 +307,11 @@ class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b) with a hand-written backward (dgrad + deterministic split-K wgrad)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act):
+    def forward(ctx, x, w, b, act, exact):
         require_cuda(x, w, b)
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.size(-1))
-        y, y_act = linear_fwd(x2, w, b, act)
+        y, y_act = linear_fwd(x2, w, b, act, exact=exact)
         ctx.act = act
         ctx.has_bias = b is not None
         ctx.lead = lead
@@ -321,11 +329,14 @@ class LinearFn(torch.autograd.Function):
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = linear_wgrad(dy, x2, want_db=ctx.has_bias)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def linear(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE) -> Tensor:
-    return LinearFn.apply(x, w, b, act)
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE, exact: Optional[bool] = None) -> Tensor:
+    # grad mode is decided HERE: inside autograd.Function.forward it always reads False
+    if exact is None:
+        exact = torch.is_grad_enabled()
+    return LinearFn.apply(x, w, b, act, exact)
 
 
 class GATv2AggregateFn(torch.autograd.Function):
@@ -366,15 +377,15 @@ class SkipGATLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_tx, x_bd, wl_tt, bl_tt, wr_tt, br_tt, att_tt, bias_tt, wl_tb, bl_tb, wr_tb, br_tb,
-                att_tb, bias_tb, csr_tt, csr_tb, H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu):
+                att_tb, bias_tb, csr_tt, csr_tb, H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu, exact):
         require_cuda(x_tx, x_bd)
         F = H * C
         N, M = x_tx.size(0), x_bd.size(0)
         dev = x_tx.device
         w_cat = torch.cat([wl_tt, wr_tt, wl_tb], 0)
         b_cat = torch.cat([bl_tt, br_tt, bl_tb], 0)
-        y_tx, _ = linear_fwd(x_tx, w_cat, b_cat)
-        y_bd, _ = linear_fwd(x_bd, wr_tb, br_tb)
+        y_tx, _ = linear_fwd(x_tx, w_cat, b_cat, exact=exact)
+        y_bd, _ = linear_fwd(x_bd, wr_tb, br_tb, exact=exact)
         v_tx, h_tx, smax_tt, sden_tt = gatv2_fwd(y_tx[:, :F], y_tx[:, F:2 * F], att_tt, bias_tt, csr_tt, H, C,
                                                  slope, p_drop, training, seed_tt, apply_gelu)
         v_bd, h_bd, smax_tb, sden_tb = gatv2_fwd(y_tx[:, 2 * F:], y_bd, att_tb, bias_tb, csr_tb, H, C, slope,
@@ -416,7 +427,7 @@ class SkipGATLayerFn(torch.autograd.Function):
         return (dx_tx, dx_bd,
                 dw_cat[:F], db_cat[:F], dw_cat[F:2 * F], db_cat[F:2 * F], ga_tt.view(ctx.att_shape), gb_tt,
                 dw_cat[2 * F:], db_cat[2 * F:], dwr_tb, dbr_tb, ga_tb.view(ctx.att_shape), gb_tb,
-                None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None)
 
 
 def sinusoid_freqs(dim: int, max_period: float, device) -> Tensor:
@@ -457,7 +468,7 @@ class InputStageFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, first_w, first_b, feat, w0, b0, w2, b2, is_embedding):
+    def forward(ctx, x, first_w, first_b, feat, w0, b0, w2, b2, is_embedding, exact):
         dev = first_w.device
         N = x.size(0)
         D = first_w.size(1) if is_embedding else first_w.size(0)
@@ -476,16 +487,16 @@ class InputStageFn(torch.autograd.Function):
             saved_x = ids
         else:
             x2 = _rowmajor(x.to(torch.float32))
-            pre_first, _ = linear_fwd(x2, first_w, first_b, ACT_GELU, y_act=h[:, :D])
+            pre_first, _ = linear_fwd(x2, first_w, first_b, ACT_GELU, y_act=h[:, :D], exact=exact)
             saved_x = x2
         y0 = a0 = y2 = None
         if use_pos:
             f2 = feat.view(2 * N, feat.size(-1))
-            y0, a0 = linear_fwd(f2, w0, b0, ACT_SILU)                      # [2N, dim] pre / SiLU
+            y0, a0 = linear_fwd(f2, w0, b0, ACT_SILU, exact=exact)         # [2N, dim] pre / SiLU
             y2 = torch.empty(2 * N, dim, dtype=torch.float32, device=dev)
             for d in range(2):                                            # x block, y block
                 linear_fwd(a0[d * N:(d + 1) * N], w2, b2, ACT_GELU, y=y2[d * N:(d + 1) * N],
-                           y_act=h[:, D + d * dim: D + (d + 1) * dim])
+                           y_act=h[:, D + d * dim: D + (d + 1) * dim], exact=exact)
         ctx.is_embedding, ctx.use_pos, ctx.D, ctx.dim, ctx.N = is_embedding, use_pos, D, dim, N
         ctx.has_first_b = first_b is not None
         ctx.save_for_backward(saved_x, first_w, pre_first, feat, w0, y0, a0, w2, y2)
@@ -519,7 +530,7 @@ class InputStageFn(torch.autograd.Function):
             dw2, db2 = linear_wgrad(dy2, a0)
             dy0 = linear_dgrad(dy2, w2, act=ACT_SILU, act_pre=y0)
             dw0, db0 = linear_wgrad(dy0, feat.view(2 * N, feat.size(-1)))
-        return None, d_first_w, d_first_b, None, dw0, db0, dw2, db2, None
+        return None, d_first_w, d_first_b, None, dw0, db0, dw2, db2, None, None
 
 
 class OutputStageFn(torch.autograd.Function):
@@ -528,7 +539,7 @@ class OutputStageFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, w, b, normalize):
         require_cuda(h, w, b)
-        y, _ = linear_fwd(h, w, b)
+        y, _ = linear_fwd(h, w, b, exact=False)   # nothing downstream amplifies its error
         ctx.normalize = normalize
         if not normalize:
             ctx.save_for_backward(h, w, None, None)
