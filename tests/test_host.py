@@ -1,0 +1,155 @@
+"""CPU tests of the host side (no GPU): C-ABI library exports, header/ctypes agreement, drop-in module
+structure (state-dict keys, lazy parameters, tuple-key ModuleDict), containers, and the fail-loud
+behaviour of the product path without a CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from segger_b200 import _lib
+from segger_b200.hetero import HeteroBatch, from_synth
+from segger_b200.ist_encoder import BT, TB, TT, ISTEncoder, Positional2dEmbedder, SkipGAT
+from segger_b200.nn import GATv2Conv, HeteroConv, HeteroDictLinear, Linear, ModuleDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "segger_b200.h")).read()
+    return re.findall(r"SGB_API\s+[\w\s\*]+?\b(sgb_\w+)\s*\(", src)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = _header_functions()
+    assert len(names) >= 30
+    raw = ctypes.CDLL(str(_lib.lib_path()))
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/segger_b200.h but not exported"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS), set(names) ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.sgb_version() == 100
+
+
+def test_ctypes_prototypes_match_header_arity():
+    src = open(os.path.join(ROOT, "include", "segger_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    for name, (_, args) in _lib._PROTOS.items():
+        m = re.search(r"\b%s\s*\((.*?)\)\s*;" % name, src, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert n == len(args), f"{name}: header has {n} parameters, ctypes binding {len(args)}"
+
+
+def test_abi_argument_validation_without_gpu(lib):
+    # pure host-side argument checks return error codes (no CUDA call is reached)
+    assert lib.sgb_csr_build(None, 3, 0, 1, 0, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert b"idx_bytes" in lib.sgb_last_error()
+    assert lib.sgb_csr_build(None, 8, 0, 1, 1 << 31, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -3
+    assert lib.sgb_dropout_mask(0, 10, 2, 1.5, None, None) == -1
+    assert lib.sgb_csr_workspace_bytes(1000) > 5 * 4000
+    assert lib.sgb_gatv2_bwd_workspace_bytes(100, 1000, 2, 64) >= 2 * 1000 * 2 * 4
+
+
+def test_product_path_fails_loudly_on_cpu_tensors():
+    from segger_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.build_csr(torch.zeros(2, 3, dtype=torch.long), 4, 4)
+    m = ISTEncoder(10, in_channels=16, hidden_channels=8, out_channels=8, n_mid_layers=0, n_heads=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m({"tx": torch.zeros(3, dtype=torch.int32), "bd": torch.zeros(2, 4)}, {}, {}, {})
+
+
+def test_missing_library_raises(monkeypatch, tmp_path):
+    monkeypatch.setenv("SEGGER_B200_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(RuntimeError, match="no CPU or eager fallback"):
+        _lib.load()
+
+
+def test_moduledict_tuple_keys_mangled_like_pyg():
+    md = ModuleDict({TT: torch.nn.Identity(), "tx": torch.nn.Identity(), "type": torch.nn.Identity()})
+    assert list(torch.nn.ModuleDict.keys(md)) == ["<tx___neighbors___tx>", "tx", "<type>"]
+    assert TT in md and "tx" in md and ("a", "b", "c") not in md
+    assert md.keys() == [TT, "tx", "type"]
+    # __iter__ yields the INTERNAL string keys -> the reference's attention kwarg is a no-op (Appendix B.2)
+    assert [k for k in md] == ["<tx___neighbors___tx>", "tx", "<type>"]
+    assert all(not isinstance(k, tuple) for k in md)
+
+
+def test_istencoder_state_dict_keys_and_hparams():
+    m = ISTEncoder(n_genes=50, in_channels=128, hidden_channels=64, out_channels=64, n_mid_layers=2, n_heads=2)
+    assert m.hparams == dict(n_genes=50, in_channels=128, hidden_channels=64, out_channels=64, n_mid_layers=2,
+                             n_heads=2, normalize_embeddings=True, use_positional_embeddings=True)
+    keys = list(m.state_dict().keys())
+    expect = ["lin_first.tx.weight", "lin_first.bd.weight", "lin_first.bd.bias", "pos_emb.mlp.0.weight",
+              "pos_emb.mlp.0.bias", "pos_emb.mlp.2.weight", "pos_emb.mlp.2.bias"]
+    for layer in range(4):
+        for et in ("<tx___neighbors___tx>", "<tx___belongs___bd>", "<bd___contains___tx>"):
+            for leaf in ("att", "bias", "lin_l.weight", "lin_l.bias", "lin_r.weight", "lin_r.bias"):
+                expect.append(f"conv_layers.{layer}.conv.convs.{et}.{leaf}")
+    expect += ["lin_last.lins.tx.weight", "lin_last.lins.tx.bias", "lin_last.lins.bd.weight", "lin_last.lins.bd.bias"]
+    assert sorted(keys) == sorted(expect)
+    assert len(m.conv_layers) == 4 and m.pos_emb.dim == 64 and m.lin_first["tx"].weight.shape == (50, 128)
+    tt = m.conv_layers[0].conv.convs[TT]
+    assert tt.att.shape == (1, 2, 64) and tt.bias.shape == (128,) and tt.dropout == 0.2 and not tt.add_self_loops
+    assert tt.negative_slope == 0.2 and not tt.initialized
+
+
+def test_lazy_parameters_round_trip_through_state_dict():
+    from torch.nn.parameter import UninitializedParameter
+    a = ISTEncoder(20, in_channels=16, hidden_channels=8, out_channels=8, n_mid_layers=0, n_heads=2)
+    sd = a.state_dict()
+    assert isinstance(sd["lin_first.bd.weight"], UninitializedParameter)
+    b = ISTEncoder(20, in_channels=16, hidden_channels=8, out_channels=8, n_mid_layers=0, n_heads=2)
+    b.load_state_dict(sd)                                    # lazy -> lazy, strict
+    assert isinstance(b.lin_first["bd"].weight, UninitializedParameter)
+    # a materialised checkpoint (e.g. trained with PyG) loads into a fresh lazy model
+    from oracle.ist_encoder_ref import ISTEncoderRef
+    ref = ISTEncoderRef(20, 12, 16, 8, 8, 0, 2)
+    missing, unexpected = b.load_state_dict(ref.state_dict(), strict=False)
+    assert not unexpected and all("bd___contains___tx" in k for k in missing)
+    assert b.lin_first["bd"].weight.shape == (16, 12) and b.lin_first["bd"].in_channels == 12
+    assert torch.equal(b.conv_layers[1].conv.convs[TB].lin_r.weight, ref.conv_layers[1].conv.convs["<tx___belongs___bd>"].lin_r.weight)
+    assert not b.conv_layers[0].conv.convs[BT].initialized  # the dead conv stays unmaterialised (Appendix B.1)
+    c = ISTEncoder(20, in_channels=16, hidden_channels=8, out_channels=8, n_mid_layers=0, n_heads=2)
+    c.load_state_dict(b.state_dict())                        # mixed lazy / materialised, strict
+    assert torch.equal(c.lin_last.lins["tx"].weight, b.lin_last.lins["tx"].weight)
+
+
+def test_unsupported_gatv2_options_raise():
+    for kw in (dict(concat=False), dict(edge_dim=4), dict(share_weights=True), dict(residual=True)):
+        with pytest.raises(NotImplementedError):
+            GATv2Conv((-1, -1), 8, heads=2, **kw)
+    with pytest.raises(ValueError):
+        HeteroConv({TT: torch.nn.Identity()}, aggr="median")
+    h = HeteroDictLinear(-1, 8, types=("tx", "bd"))
+    assert list(h.state_dict().keys()) == ["lins.tx.weight", "lins.tx.bias", "lins.bd.weight", "lins.bd.bias"]
+    assert Linear(4, 3, bias=False).bias is None
+
+
+def test_hetero_batch_protocol_and_synth_layout():
+    from segger_b200.synth import drop_cross_tile_edges, synth
+    ts = synth(4000, 40, seed=3, nodes_per_tile=1000)
+    assert ts.tx_pos.dtype == np.float32 and ts.tx_gene.dtype == np.int32 and ts.edge_pred.dtype == np.int32
+    assert ts.n_tiles == 4 and np.all(np.diff(ts.tx_tile) >= 0)              # tile-major node order
+    assert ts.edge_tb.shape[1] == 40 * 40 and np.all(ts.tx_compartment[ts.edge_tb[0]] == 2)
+    assert np.all(ts.tx_cell[ts.edge_tb[0]] == ts.edge_tb[1])
+    d = np.linalg.norm(ts.tx_pos[ts.edge_pred[0]] - ts.bd_pos[ts.edge_pred[1]], axis=1)
+    assert d.max() < 6.5 * 1.05 and np.bincount(ts.edge_pred[0], minlength=4000).max() <= 3
+    ei = np.stack([np.arange(3999), np.arange(1, 4000)])
+    kept = drop_cross_tile_edges(ei, ts.tx_tile, ts.tx_tile)
+    assert kept.shape[1] == 3999 - 3
+    b = from_synth(ts, torch.from_numpy(ei))
+    assert set(b.x_dict) == {"tx", "bd"} and set(b.edge_index_dict) == {TT, TB, ("tx", "neighbors", "bd")}
+    assert b["tx"].num_nodes == 4000 and b["bd"].num_nodes == 40 and b[TT].edge_index.shape == (2, 3999)
+    assert b.nbytes() > 0 and set(b.batch_dict) == {"tx", "bd"}
+
+
+def test_synth_is_deterministic():
+    from segger_b200.synth import synth
+    a, b = synth(3000, 30, seed=5), synth(3000, 30, seed=5)
+    assert np.array_equal(a.tx_pos, b.tx_pos) and np.array_equal(a.edge_pred, b.edge_pred)
+    assert not np.array_equal(a.tx_pos, synth(3000, 30, seed=6).tx_pos)
