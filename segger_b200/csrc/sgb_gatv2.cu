@@ -17,6 +17,8 @@
 //    per head (delta, alpha') from the dst pass for the src-sorted (transposed) pass.
 //  * arbitrary (H, C) fall back to a warp-per-(row, head) scalar kernel with the same structure.
 #include "sgb_api_internal.cuh"
+#include "sgb_gatv2.cuh"
+#include <cstdlib>
 
 namespace sgb {
 namespace {
@@ -62,48 +64,6 @@ struct HeadMap {
 };
 
 template <int VEC> struct Chunk { static constexpr int value = VEC == 1 ? 8 : (VEC == 2 ? 4 : 2); };
-
-__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
-  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
-}
-__device__ __forceinline__ float lrelu(float z, float slope) { return z > 0.f ? z : slope * z; }
-__device__ __forceinline__ float4 lrelu4(const float4 z, float slope) {
-  return make_float4(lrelu(z.x, slope), lrelu(z.y, slope), lrelu(z.z, slope), lrelu(z.w, slope));
-}
-__device__ __forceinline__ float4 add4(const float4 a, const float4 b) {
-  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-}
-__device__ __forceinline__ void fma4(float4& acc, float w, const float4 x) {
-  acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y); acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
-}
-__device__ __forceinline__ void scale4(float4& a, float s) { a.x *= s; a.y *= s; a.z *= s; a.w *= s; }
-
-struct GatParams {
-  const float *x_l, *x_r, *att, *bias;
-  int64_t ld_l, ld_r;
-  const int32_t *rowptr, *col, *eid;
-  int64_t n_dst, n_src;
-  int H, C;
-  float slope;
-  int training;
-  uint32_t drop_thr;
-  float keep_scale;
-  uint64_t seed;
-  // forward outputs / backward saved inputs
-  float *out, *out_act;
-  int64_t ld_out, ld_act;
-  float *stat_max, *stat_den;
-  // backward
-  const float* grad_out;
-  int64_t ld_g;
-  int gelu_fused;
-  float* g_buf;
-  float *e_delta, *e_alpha;  // [E,H] per-edge scalars in dst-CSR order
-  float *grad_x_l, *grad_x_r;
-  int64_t ld_gl, ld_gr;
-  float* partial;            // per-CTA (vector path) / per-warp (generic path) partial sums
-  const int32_t *t_rowptr, *t_dst, *t_pos;
-};
 
 // ================================================================================================
 // Forward, vector path
@@ -691,6 +651,12 @@ Shape classify(int H, int C, bool aligned) {
 
 bool ld_ok(int64_t ld) { return ld % 4 == 0; }
 
+// SEGGER_B200_GAT=legacy forces the first-generation row-per-warp kernels (debug / A-B profiling)
+bool legacy_path() {
+  const char* e = getenv("SEGGER_B200_GAT");   // read per call so a profiling script can A/B in one process
+  return e && e[0] == 'l';
+}
+
 int gen_bwd_blocks(int H) {  // CTA count for the persistent generic dst pass: warps_total % H == 0
   int nb = sm_count() * 2;
   nb = (nb + H - 1) / H * H;
@@ -739,6 +705,7 @@ extern "C" int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, i
   p.slope = negative_slope; p.training = train ? 1 : 0; p.drop_thr = drop_threshold(p_drop);
   p.keep_scale = 1.0f / (1.0f - p_drop); p.seed = seed;
   p.out = out; p.out_act = out_act; p.ld_out = ld_out; p.ld_act = ld_act; p.stat_max = stat_max; p.stat_den = stat_den;
+  if (aligned && !legacy_path() && quad_fwd_launch(p, stream)) return check_launch("gatv2_fwd(quad)");
   if (sh.path == Path::kVec) {
     const unsigned blocks = static_cast<unsigned>(ceil_div(n_dst, 8));
 #define X(V, Cv) if (sh.vec == V && sh.cv == Cv) gatv2_fwd_vec_kernel<V, Cv><<<blocks, 256, 0, stream>>>(p);
@@ -778,12 +745,17 @@ static size_t bwd_partial_floats(int64_t n_dst, int H, int C) {
   const int F = H * C;
   const size_t vec = static_cast<size_t>(vec_bwd_blocks(n_dst)) * 2 * F;
   const size_t gen = static_cast<size_t>(gen_bwd_blocks(H)) * 8 * 2 * C;
-  return vec > gen ? vec : gen;
+  const size_t quad = quad_bwd_partial_floats(H, C);
+  const size_t m = vec > gen ? vec : gen;
+  return m > quad ? m : quad;
+}
+// bytes of ONE of the two per-edge scalar arrays; two of them also hold the quad path's [E][rec_stride] records
+static size_t bwd_edge_bytes(int64_t E, int H) {
+  return align_up(static_cast<size_t>(E > 0 ? E : 1) * (rec_stride(H) / 2) * sizeof(float));
 }
 
 extern "C" size_t sgb_gatv2_bwd_workspace_bytes(int64_t n_dst, int64_t E, int H, int C) {
-  const size_t edge = align_up(static_cast<size_t>(E > 0 ? E : 1) * H * sizeof(float));
-  return 2 * edge + align_up(bwd_partial_floats(n_dst, H, C) * sizeof(float));
+  return 2 * bwd_edge_bytes(E, H) + align_up(bwd_partial_floats(n_dst, H, C) * sizeof(float));
 }
 
 extern "C" int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, int64_t ld_r, const float* att,
@@ -812,7 +784,7 @@ extern "C" int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, i
   const Shape sh = classify(H, C, aligned);
   SGB_REQUIRE(sh.path != Path::kNone, SGB_ERR_ARG, "gatv2_bwd: unsupported shape H=%d C=%d (aligned=%d)", H, C, (int)aligned);
 
-  const size_t edge = align_up(static_cast<size_t>(E > 0 ? E : 1) * H * sizeof(float));
+  const size_t edge = bwd_edge_bytes(E, H);
   char* w = static_cast<char*>(ws);
   GatParams p{};
   p.x_l = x_l; p.x_r = x_r; p.att = att; p.bias = bias; p.ld_l = ld_l; p.ld_r = ld_r;
@@ -827,6 +799,8 @@ extern "C" int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, i
   p.grad_x_l = grad_x_l; p.grad_x_r = grad_x_r; p.ld_gl = ld_gl; p.ld_gr = ld_gr;
   p.t_rowptr = src_rowptr; p.t_dst = src_dst; p.t_pos = src_pos;
 
+  if (n_dst > 0 && aligned && !legacy_path() && quad_bwd_launch(p, grad_att, grad_bias, stream))
+    return check_launch("gatv2_bwd(quad)");
   if (n_dst == 0) {
     cudaMemsetAsync(grad_att, 0, sizeof(float) * F, stream);
     if (grad_bias) cudaMemsetAsync(grad_bias, 0, sizeof(float) * F, stream);

@@ -1,0 +1,765 @@
+// Fused GATv2 kernels, sub-warp-per-row ("quad") path with a cp.async shared-memory gather pipeline.
+//
+// Same math as sgb_gatv2.cu (replaces the PyG GATv2Conv message passing
+// configured at /root/reference/src/segger/models/ist_encoder.py:111-131), restructured for the
+// instruction-issue and latency limits the first kernels hit on B200 (profiles/r1_summary.md):
+//
+//  * LPR lanes own one row (LPR = 8 for F = 128: a warp advances G = 4 destination rows in lock
+//    step), each lane holds V float4 of the row (float4 index t*LPR + s).  All per-edge scalar work
+//    (logit reduction, exp, dropout hash, softmax bookkeeping, loop control) is paid once per
+//    warp instruction for G edges, and the head reduction is log2(LPR) shuffles instead of 4-5.
+//  * every lane stages exactly the float4s it will consume itself through a D-deep ring in shared
+//    memory with cp.async (LDGSTS, 16 B, L2-only): the gathers of step K+D-1 are in flight while
+//    step K is computed, across row boundaries, with no register cost and no cross-lane
+//    synchronisation (a lane only reads back its own copies, so cp.async.wait_group suffices).
+//    Destination-side rows (x_r, grad_out, out) travel through the same ring as "header" steps.
+//  * the column index for step K+D is loaded one iteration before its copy is issued, so no
+//    dependent global load sits on the issue path.
+//  * LeakyReLU logits use lrelu(z) = c1*z + c2*|z| (c1 = (1+slope)/2, c2 = (1-slope)/2): two FMAs
+//    per element with |z| as a free operand modifier.
+//  * online softmax with a lazily updated maximum: the running accumulator is only rescaled when a
+//    logit exceeds the reference maximum by more than kTau (warp-uniform rare branch).  The saved
+//    (stat_max, stat_den) pair is self-consistent, which is all the backward needs.
+//  * row-owner reductions everywhere (dst pass: grad_x_r, src pass: grad_x_l), fixed summation order
+//    -> bit-reproducible, no atomics.  The dst pass leaves one 16-byte record (delta, alpha') per
+//    edge for the src pass; nothing of width C is ever written per edge.
+#include "sgb_gatv2.cuh"
+
+namespace sgb {
+namespace {
+
+constexpr int kQW = 4;                  // warps per CTA
+constexpr int kQThreads = kQW * 32;
+constexpr float kTau = 12.0f;           // lazy-max slack: exp(logit - m) <= e^12
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float4 sub4(const float4 a, const float4 b) {
+  return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+}
+__device__ __forceinline__ float4 mul4(const float4 a, const float4 b) {
+  return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+__device__ __forceinline__ float dotabs4(const float4 a, const float4 z) {
+  return a.x * fabsf(z.x) + a.y * fabsf(z.y) + a.z * fabsf(z.z) + a.w * fabsf(z.w);
+}
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float x) {
+#pragma unroll
+  for (int o = LPR / 2; o >= 1; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+  return x;
+}
+
+// rows of this lane group in quad q: CSR range [beg, beg+deg), mx = max degree over the warp's groups
+template <int LPR>
+__device__ __forceinline__ void quad_info(int rp_b, int rp_e, int q, int g, int& beg, int& deg, int& mx) {
+  constexpr int G = 32 / LPR;
+  const int idx = q * G + g;
+  beg = __shfl_sync(kFull, rp_b, idx);
+  deg = __shfl_sync(kFull, rp_e, idx) - beg;
+  mx = (G == 1) ? deg : __reduce_max_sync(kFull, deg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gather pipeline: a warp-private ring of D steps x SLOTS x (32 lanes x 16 B).
+// The kernel supplies  gen(step descriptor)  through the Src policy:
+//   header steps (NH per quad) then one step per edge position k < max degree of the quad.
+// ------------------------------------------------------------------------------------------------
+template <int LPR, int D, int SLOTS, int NH>
+struct Pipe {
+  static constexpr int G = 32 / LPR;
+  uint32_t ring;        // shared-space byte address of this lane's column of the ring
+  int pslot = 0, cslot = 0;
+  // producer cursor
+  int pq = 0, pk = 0, p_beg = 0, p_deg = 0, p_n = 0;
+  int nq = 0;
+  int rp_b = 0, rp_e = 0;
+  int g = 0;
+
+  __device__ __forceinline__ void start(int nq_, int rp_b_, int rp_e_, int g_) {
+    nq = nq_; rp_b = rp_b_; rp_e = rp_e_; g = g_;
+    pq = 0; pk = 0;
+    pslot = 0; cslot = 0;   // a previous chunk leaves only empty groups behind: restart the ring in phase
+    if (nq > 0) {
+      int mx;
+      quad_info<LPR>(rp_b, rp_e, 0, g, p_beg, p_deg, mx);
+      p_n = mx + NH;
+    }
+  }
+  // advance the producer cursor by one step (after the caller described the current one)
+  __device__ __forceinline__ void advance() {
+    if (++pk == p_n) {
+      pk = 0;
+      ++pq;
+      if (pq < nq) {
+        int mx;
+        quad_info<LPR>(rp_b, rp_e, pq, g, p_beg, p_deg, mx);
+        p_n = mx + NH;
+      }
+    }
+  }
+  __device__ __forceinline__ uint32_t issue_addr(int slot_in_step) const {
+    return ring + static_cast<uint32_t>((pslot * SLOTS + slot_in_step) * 512);
+  }
+  __device__ __forceinline__ void committed() {
+    cp_commit();
+    pslot = (pslot + 1 == D) ? 0 : pslot + 1;
+  }
+  __device__ __forceinline__ uint32_t read_addr(int slot_in_step) const {
+    return ring + static_cast<uint32_t>((cslot * SLOTS + slot_in_step) * 512);
+  }
+  __device__ __forceinline__ void consumed() { cslot = (cslot + 1 == D) ? 0 : cslot + 1; }
+};
+
+__device__ __forceinline__ float4 lds4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t saddr, const float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ================================================================================================
+// Forward
+// ================================================================================================
+template <int V, int LPR, int H, int D>
+__global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
+  constexpr int G = 32 / LPR, VPH = V / H;
+  static_assert(V % H == 0, "a lane must hold whole heads");
+  extern __shared__ float4 q_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = lane % LPR, g = lane / LPR;
+  using P = Pipe<LPR, D, V, 1>;
+  P pipe;
+  pipe.ring = static_cast<uint32_t>(__cvta_generic_to_shared(q_smem + warp * (D * V * 32) + lane));
+#pragma unroll
+  for (int i = 0; i < D * V; ++i) sts4(pipe.ring + i * 512, make_float4(0.f, 0.f, 0.f, 0.f));
+
+  float4 a[V];
+#pragma unroll
+  for (int t = 0; t < V; ++t) a[t] = ldg4(p.att + (t * LPR + s) * 4);
+  const float c1 = 0.5f * (1.0f + p.slope), c2 = 0.5f * (1.0f - p.slope);
+  const bool training = p.training != 0;
+
+  for (int64_t chunk = static_cast<int64_t>(blockIdx.x) * kQW + warp; chunk < nchunks;
+       chunk += static_cast<int64_t>(gridDim.x) * kQW) {
+    const int64_t wrow0 = chunk * rpw;
+    const int nrows = static_cast<int>(min(static_cast<int64_t>(rpw), p.n_dst - wrow0));
+    const int nq = (nrows + G - 1) / G;
+    const int rp_b = __ldg(p.rowptr + min(wrow0 + lane, p.n_dst));
+    const int rp_e = __ldg(p.rowptr + min(wrow0 + lane + 1, p.n_dst));
+    pipe.start(nq, rp_b, rp_e, g);
+
+    const float* nsrc = nullptr;
+    bool nact = false;
+    auto gen = [&]() {
+      nact = false;
+      if (pipe.pq < pipe.nq) {
+        if (pipe.pk == 0) {
+          const int64_t row = wrow0 + pipe.pq * G + g;
+          nact = row < p.n_dst;
+          nsrc = p.x_r + row * p.ld_r;
+        } else {
+          const int k = pipe.pk - 1;
+          if (k < pipe.p_deg) {
+            nact = true;
+            nsrc = p.x_l + static_cast<int64_t>(__ldg(p.col + pipe.p_beg + k)) * p.ld_l;
+          }
+        }
+        pipe.advance();
+      }
+    };
+    auto issue = [&]() {
+      if (nact) {
+#pragma unroll
+        for (int t = 0; t < V; ++t) cp_async16(pipe.issue_addr(t), nsrc + (t * LPR + s) * 4);
+      }
+      pipe.committed();
+    };
+    gen();
+#pragma unroll
+    for (int i = 0; i < D - 1; ++i) { issue(); gen(); }
+
+    for (int q = 0; q < nq; ++q) {
+      int c_beg, c_deg, c_mx;
+      quad_info<LPR>(rp_b, rp_e, q, g, c_beg, c_deg, c_mx);
+      const int64_t row = wrow0 + q * G + g;
+      const bool rvalid = row < p.n_dst;
+
+      issue(); gen(); cp_wait<D - 1>();
+      float4 r[V], acc[V];
+#pragma unroll
+      for (int t = 0; t < V; ++t) {
+        r[t] = lds4(pipe.read_addr(t));
+        acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      pipe.consumed();
+      float m[H], ss[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) { m[h] = 0.f; ss[h] = 0.f; }
+      int eid_next = (training && c_deg > 0) ? __ldg(p.eid + c_beg) : 0;
+
+      for (int k = 0; k < c_mx; ++k) {
+        issue(); gen(); cp_wait<D - 1>();
+        const bool act = k < c_deg;
+        float4 x[V];
+#pragma unroll
+        for (int t = 0; t < V; ++t) x[t] = lds4(pipe.read_addr(t));
+        pipe.consumed();
+        float lg[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+          for (int u = 0; u < VPH; ++u) {
+            const int t = h * VPH + u;
+            const float4 z = add4(x[t], r[t]);
+            p1 += dot4(a[t], z);
+            p2 += dotabs4(a[t], z);
+          }
+          lg[h] = group_sum<LPR>(fmaf(c1, p1, c2 * p2));
+        }
+        const int e = eid_next;
+        if (training && k + 1 < c_deg) eid_next = __ldg(p.eid + c_beg + k + 1);
+
+        if (k == 0) {
+#pragma unroll
+          for (int h = 0; h < H; ++h) m[h] = act ? lg[h] : 0.f;
+        } else {
+          bool need = false;
+#pragma unroll
+          for (int h = 0; h < H; ++h) need |= act && (lg[h] > m[h] + kTau);
+          if (__any_sync(kFull, need)) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+              const bool nh = act && (lg[h] > m[h] + kTau);
+              const float mn = nh ? lg[h] : m[h];
+              const float sc = __expf(m[h] - mn);
+              ss[h] *= sc;
+#pragma unroll
+              for (int u = 0; u < VPH; ++u) scale4(acc[h * VPH + u], sc);
+              m[h] = mn;
+            }
+          }
+        }
+        uint32_t eh = 0;
+        if (training) eh = rng_edge(p.seed, static_cast<uint32_t>(e));
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float pe = act ? __expf(lg[h] - m[h]) : 0.f;
+          ss[h] += pe;
+          float w = pe;
+          if (training) w = rng_head(eh, p.seed, h) >= p.drop_thr ? pe * p.keep_scale : 0.f;
+#pragma unroll
+          for (int u = 0; u < VPH; ++u) fma4(acc[h * VPH + u], w, x[h * VPH + u]);
+        }
+      }
+
+      float inv[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float den = ss[h] + 1e-16f;
+        inv[h] = 1.0f / den;
+        if (s == 0 && rvalid) {
+          p.stat_max[row * H + h] = m[h];
+          p.stat_den[row * H + h] = den;
+        }
+      }
+      if (rvalid) {
+#pragma unroll
+        for (int t = 0; t < V; ++t) {
+          const int off = (t * LPR + s) * 4;
+          float4 o = acc[t];
+          scale4(o, inv[t / VPH]);
+          if (p.bias) o = add4(o, ldg4(p.bias + off));
+          st4(p.out + row * p.ld_out + off, o);
+          if (p.out_act)
+            st4(p.out_act + row * p.ld_act + off,
+                make_float4(gelu_erf(o.x), gelu_erf(o.y), gelu_erf(o.z), gelu_erf(o.w)));
+        }
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// Backward, dst-CSR pass: grad_x_r, per-edge records (delta, alpha'), partial grad_att / grad_bias
+// ================================================================================================
+template <int V, int LPR, int H, int D>
+__global__ void __launch_bounds__(kQThreads) gatv2_bwd_dst_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
+  constexpr int G = 32 / LPR, VPH = V / H, F4 = V * LPR;
+  constexpr int SH = (2 * H + 3) / 4 * 4;
+  extern __shared__ float4 q_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = lane % LPR, g = lane / LPR;
+  using P = Pipe<LPR, D, V, 3>;
+  P pipe;
+  // per warp: ring D*V*512 B, then V*512 B of grad_bias accumulators (lane-private)
+  float4* wbase = q_smem + warp * ((D + 1) * V * 32);
+  pipe.ring = static_cast<uint32_t>(__cvta_generic_to_shared(wbase + lane));
+  const uint32_t gb_addr = pipe.ring + D * V * 512;
+#pragma unroll
+  for (int i = 0; i < (D + 1) * V; ++i) sts4(pipe.ring + i * 512, make_float4(0.f, 0.f, 0.f, 0.f));
+
+  float4 a[V], gatt[V];
+#pragma unroll
+  for (int t = 0; t < V; ++t) {
+    a[t] = ldg4(p.att + (t * LPR + s) * 4);
+    gatt[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float c1 = 0.5f * (1.0f + p.slope), c2 = 0.5f * (1.0f - p.slope);
+  const float slope = p.slope;
+  const bool training = p.training != 0;
+
+  for (int64_t chunk = static_cast<int64_t>(blockIdx.x) * kQW + warp; chunk < nchunks;
+       chunk += static_cast<int64_t>(gridDim.x) * kQW) {
+    const int64_t wrow0 = chunk * rpw;
+    const int nrows = static_cast<int>(min(static_cast<int64_t>(rpw), p.n_dst - wrow0));
+    const int nq = (nrows + G - 1) / G;
+    const int rp_b = __ldg(p.rowptr + min(wrow0 + lane, p.n_dst));
+    const int rp_e = __ldg(p.rowptr + min(wrow0 + lane + 1, p.n_dst));
+    pipe.start(nq, rp_b, rp_e, g);
+
+    const float* nsrc = nullptr;
+    bool nact = false;
+    auto gen = [&]() {
+      nact = false;
+      if (pipe.pq < pipe.nq) {
+        if (pipe.pk < 3) {
+          const int64_t row = wrow0 + pipe.pq * G + g;
+          nact = row < p.n_dst;
+          nsrc = pipe.pk == 0 ? p.x_r + row * p.ld_r : (pipe.pk == 1 ? p.grad_out + row * p.ld_g : p.out + row * p.ld_out);
+        } else {
+          const int k = pipe.pk - 3;
+          if (k < pipe.p_deg) {
+            nact = true;
+            nsrc = p.x_l + static_cast<int64_t>(__ldg(p.col + pipe.p_beg + k)) * p.ld_l;
+          }
+        }
+        pipe.advance();
+      }
+    };
+    auto issue = [&]() {
+      if (nact) {
+#pragma unroll
+        for (int t = 0; t < V; ++t) cp_async16(pipe.issue_addr(t), nsrc + (t * LPR + s) * 4);
+      }
+      pipe.committed();
+    };
+    gen();
+#pragma unroll
+    for (int i = 0; i < D - 1; ++i) { issue(); gen(); }
+
+    for (int q = 0; q < nq; ++q) {
+      int c_beg, c_deg, c_mx;
+      quad_info<LPR>(rp_b, rp_e, q, g, c_beg, c_deg, c_mx);
+      const int64_t row = wrow0 + q * G + g;
+      const bool rvalid = row < p.n_dst;
+      float m[H], inv[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        m[h] = rvalid ? __ldg(p.stat_max + row * H + h) : 0.f;
+        inv[h] = rvalid ? __ldg(p.stat_den + row * H + h) : 1.f;
+      }
+      int eid_next = (training && c_deg > 0) ? __ldg(p.eid + c_beg) : 0;
+
+      float4 r[V], g4[V], gr[V];
+      issue(); gen(); cp_wait<D - 1>();
+#pragma unroll
+      for (int t = 0; t < V; ++t) r[t] = lds4(pipe.read_addr(t));
+      pipe.consumed();
+      issue(); gen(); cp_wait<D - 1>();
+#pragma unroll
+      for (int t = 0; t < V; ++t) g4[t] = lds4(pipe.read_addr(t));
+      pipe.consumed();
+      issue(); gen(); cp_wait<D - 1>();
+      float cdot[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) cdot[h] = 0.f;
+#pragma unroll
+      for (int t = 0; t < V; ++t) {
+        const int off = (t * LPR + s) * 4;
+        const float4 o4 = lds4(pipe.read_addr(t));
+        if (!rvalid) g4[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.gelu_fused) {
+          g4[t].x *= gelu_erf_grad(o4.x); g4[t].y *= gelu_erf_grad(o4.y);
+          g4[t].z *= gelu_erf_grad(o4.z); g4[t].w *= gelu_erf_grad(o4.w);
+          if (rvalid) st4(p.g_buf + row * p.ld_g + off, g4[t]);
+        }
+        const float4 b4 = p.bias ? ldg4(p.bias + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        cdot[t / VPH] += dot4(g4[t], sub4(o4, b4));
+        const uint32_t ga = gb_addr + t * 512;
+        sts4(ga, add4(lds4(ga), g4[t]));
+        gr[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      pipe.consumed();
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        cdot[h] = group_sum<LPR>(cdot[h]);
+        inv[h] = 1.0f / inv[h];
+      }
+
+      for (int k = 0; k < c_mx; ++k) {
+        issue(); gen(); cp_wait<D - 1>();
+        const bool act = k < c_deg;
+        float4 z[V];
+        float lg[H], dd[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          float p1 = 0.f, p2 = 0.f, pd = 0.f;
+#pragma unroll
+          for (int u = 0; u < VPH; ++u) {
+            const int t = h * VPH + u;
+            const float4 x = lds4(pipe.read_addr(t));
+            pd += dot4(g4[t], x);
+            z[t] = add4(x, r[t]);
+            p1 += dot4(a[t], z[t]);
+            p2 += dotabs4(a[t], z[t]);
+          }
+          lg[h] = group_sum<LPR>(fmaf(c1, p1, c2 * p2));
+          dd[h] = group_sum<LPR>(pd);
+        }
+        pipe.consumed();
+        const int e = eid_next;
+        if (training && k + 1 < c_deg) eid_next = __ldg(p.eid + c_beg + k + 1);
+        uint32_t eh = 0;
+        if (training) eh = rng_edge(p.seed, static_cast<uint32_t>(e));
+        float delta[H], alk[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float alpha = act ? __expf(lg[h] - m[h]) * inv[h] : 0.f;
+          float ks = 1.0f;
+          if (training) ks = rng_head(eh, p.seed, h) >= p.drop_thr ? p.keep_scale : 0.f;
+          delta[h] = alpha * (dd[h] * ks - cdot[h]);
+          alk[h] = alpha * ks;
+        }
+        if (act && s < SH / 4) {
+          // record: [delta_0..delta_{H-1}, alpha'_0..alpha'_{H-1}, pad]
+          float rec[SH];
+#pragma unroll
+          for (int i = 0; i < SH; ++i) rec[i] = i < H ? delta[i] : (i < 2 * H ? alk[i - H] : 0.f);
+          float4 out4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < SH / 4; ++i)
+            if (s == i) out4 = make_float4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
+          st4(p.e_delta + (static_cast<int64_t>(c_beg + k) * SH + s * 4), out4);
+        }
+#pragma unroll
+        for (int t = 0; t < V; ++t) {
+          const float d = delta[t / VPH];
+          const float4 zz = z[t];
+          const float4 sel = make_float4(zz.x > 0.f ? 1.f : slope, zz.y > 0.f ? 1.f : slope,
+                                         zz.z > 0.f ? 1.f : slope, zz.w > 0.f ? 1.f : slope);
+          const float4 da = make_float4(d * a[t].x, d * a[t].y, d * a[t].z, d * a[t].w);
+          gr[t].x = fmaf(da.x, sel.x, gr[t].x); gr[t].y = fmaf(da.y, sel.y, gr[t].y);
+          gr[t].z = fmaf(da.z, sel.z, gr[t].z); gr[t].w = fmaf(da.w, sel.w, gr[t].w);
+          fma4(gatt[t], d, mul4(zz, sel));
+        }
+      }
+      if (rvalid) {
+#pragma unroll
+        for (int t = 0; t < V; ++t) st4(p.grad_x_r + row * p.ld_gr + (t * LPR + s) * 4, gr[t]);
+      }
+    }
+  }
+
+  // ---- CTA-level ordered reduction -> partial[blockIdx][2][F] ------------------------------------
+  float4 gb[V];
+#pragma unroll
+  for (int t = 0; t < V; ++t) {
+    gb[t] = lds4(gb_addr + t * 512);
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {   // sum over the G lane groups (same columns, different rows)
+      gatt[t].x += __shfl_xor_sync(kFull, gatt[t].x, o); gatt[t].y += __shfl_xor_sync(kFull, gatt[t].y, o);
+      gatt[t].z += __shfl_xor_sync(kFull, gatt[t].z, o); gatt[t].w += __shfl_xor_sync(kFull, gatt[t].w, o);
+      gb[t].x += __shfl_xor_sync(kFull, gb[t].x, o); gb[t].y += __shfl_xor_sync(kFull, gb[t].y, o);
+      gb[t].z += __shfl_xor_sync(kFull, gb[t].z, o); gb[t].w += __shfl_xor_sync(kFull, gb[t].w, o);
+    }
+  }
+  __syncthreads();   // every warp is done with its ring; reuse the start of shared memory
+  float4* red = q_smem;   // [2][kQW][F4]
+  if (g == 0) {
+#pragma unroll
+    for (int t = 0; t < V; ++t) {
+      red[(0 * kQW + warp) * F4 + t * LPR + s] = gatt[t];
+      red[(1 * kQW + warp) * F4 + t * LPR + s] = gb[t];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * F4; i += kQThreads) {
+    const int which = i / F4, f = i % F4;
+    float4 tsum = red[(which * kQW + 0) * F4 + f];
+#pragma unroll
+    for (int w = 1; w < kQW; ++w) tsum = add4(tsum, red[(which * kQW + w) * F4 + f]);
+    st4(p.partial + (static_cast<int64_t>(blockIdx.x) * 2 + which) * (F4 * 4) + f * 4, tsum);
+  }
+}
+
+// fixed-order column sums of partial[nb][cols] -> grad_att | grad_bias.  block = (32, 8)
+__global__ void quad_colsum_kernel(const float* __restrict__ partial, int nb, int cols, int F,
+                                   float* __restrict__ grad_att, float* __restrict__ grad_bias) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < cols)
+    for (int b = threadIdx.y; b < nb; b += 8) acc += partial[static_cast<int64_t>(b) * cols + c];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = red[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) t += red[y][threadIdx.x];
+    if (c < F) grad_att[c] = t;
+    else if (grad_bias) grad_bias[c - F] = t;
+  }
+}
+
+// ================================================================================================
+// Backward, src-CSR (transposed) pass: grad_x_l
+// ================================================================================================
+template <int V, int LPR, int H, int D>
+__global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
+  constexpr int G = 32 / LPR, VPH = V / H;
+  constexpr int SH = (2 * H + 3) / 4 * 4;
+  constexpr int SLOTS = 2 * V + 1;
+  extern __shared__ float4 q_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = lane % LPR, g = lane / LPR;
+  using P = Pipe<LPR, D, SLOTS, 1>;
+  P pipe;
+  pipe.ring = static_cast<uint32_t>(__cvta_generic_to_shared(q_smem + warp * (D * SLOTS * 32) + lane));
+#pragma unroll
+  for (int i = 0; i < D * SLOTS; ++i) sts4(pipe.ring + i * 512, make_float4(0.f, 0.f, 0.f, 0.f));
+  // the scalar record of this lane's group sits at lane (g*LPR + i) of slot 2V, i < SH/4
+  const uint32_t rec_off = static_cast<uint32_t>(2 * V * 512) - static_cast<uint32_t>(s * 16);
+
+  float4 a[V];
+#pragma unroll
+  for (int t = 0; t < V; ++t) a[t] = ldg4(p.att + (t * LPR + s) * 4);
+  const float slope = p.slope;
+  const float* gsrc = p.gelu_fused ? p.g_buf : p.grad_out;
+
+  for (int64_t chunk = static_cast<int64_t>(blockIdx.x) * kQW + warp; chunk < nchunks;
+       chunk += static_cast<int64_t>(gridDim.x) * kQW) {
+    const int64_t wrow0 = chunk * rpw;
+    const int nrows = static_cast<int>(min(static_cast<int64_t>(rpw), p.n_src - wrow0));
+    const int nq = (nrows + G - 1) / G;
+    const int rp_b = __ldg(p.t_rowptr + min(wrow0 + lane, p.n_src));
+    const int rp_e = __ldg(p.t_rowptr + min(wrow0 + lane + 1, p.n_src));
+    pipe.start(nq, rp_b, rp_e, g);
+
+    const float *nsrc = nullptr, *nsrc2 = nullptr, *nrec = nullptr;
+    bool nact = false, nedge = false;
+    auto gen = [&]() {
+      nact = false;
+      nedge = false;
+      if (pipe.pq < pipe.nq) {
+        if (pipe.pk == 0) {
+          const int64_t row = wrow0 + pipe.pq * G + g;
+          nact = row < p.n_src;
+          nsrc = p.x_l + row * p.ld_l;
+        } else {
+          const int k = pipe.pk - 1;
+          if (k < pipe.p_deg) {
+            nact = true;
+            nedge = true;
+            const int64_t i = __ldg(p.t_dst + pipe.p_beg + k);
+            const int64_t pos = __ldg(p.t_pos + pipe.p_beg + k);
+            nsrc = p.x_r + i * p.ld_r;
+            nsrc2 = gsrc + i * p.ld_g;
+            nrec = p.e_delta + pos * SH;
+          }
+        }
+        pipe.advance();
+      }
+    };
+    auto issue = [&]() {
+      if (nact) {
+#pragma unroll
+        for (int t = 0; t < V; ++t) cp_async16(pipe.issue_addr(t), nsrc + (t * LPR + s) * 4);
+        if (nedge) {
+#pragma unroll
+          for (int t = 0; t < V; ++t) cp_async16(pipe.issue_addr(V + t), nsrc2 + (t * LPR + s) * 4);
+          if (s < SH / 4) cp_async16(pipe.issue_addr(2 * V), nrec + s * 4);
+        }
+      }
+      pipe.committed();
+    };
+    gen();
+#pragma unroll
+    for (int i = 0; i < D - 1; ++i) { issue(); gen(); }
+
+    for (int q = 0; q < nq; ++q) {
+      int c_beg, c_deg, c_mx;
+      quad_info<LPR>(rp_b, rp_e, q, g, c_beg, c_deg, c_mx);
+      const int64_t row = wrow0 + q * G + g;
+      const bool rvalid = row < p.n_src;
+
+      issue(); gen(); cp_wait<D - 1>();
+      float4 l[V], acc[V];
+#pragma unroll
+      for (int t = 0; t < V; ++t) {
+        l[t] = lds4(pipe.read_addr(t));
+        acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      pipe.consumed();
+
+      for (int k = 0; k < c_mx; ++k) {
+        issue(); gen(); cp_wait<D - 1>();
+        __syncwarp();   // the (delta, alpha') record was staged by other lanes of the group
+        const bool act = k < c_deg;
+        float rec[SH];
+#pragma unroll
+        for (int i = 0; i < SH / 4; ++i) {
+          const float4 v = lds4(pipe.read_addr(0) + rec_off + i * 16);
+          rec[4 * i] = v.x; rec[4 * i + 1] = v.y; rec[4 * i + 2] = v.z; rec[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int t = 0; t < V; ++t) {
+          const float4 xr = lds4(pipe.read_addr(t));
+          const float4 gg = lds4(pipe.read_addr(V + t));
+          const float d = act ? rec[t / VPH] : 0.f;
+          const float al = act ? rec[H + t / VPH] : 0.f;
+          const float4 z = add4(l[t], xr);
+          const float4 sel = make_float4(z.x > 0.f ? 1.f : slope, z.y > 0.f ? 1.f : slope,
+                                         z.z > 0.f ? 1.f : slope, z.w > 0.f ? 1.f : slope);
+          acc[t].x = fmaf(d * a[t].x, sel.x, acc[t].x); acc[t].y = fmaf(d * a[t].y, sel.y, acc[t].y);
+          acc[t].z = fmaf(d * a[t].z, sel.z, acc[t].z); acc[t].w = fmaf(d * a[t].w, sel.w, acc[t].w);
+          fma4(acc[t], al, gg);
+        }
+        pipe.consumed();
+        __syncwarp();   // all lanes are done with this step's record before its slot is refilled
+      }
+      if (rvalid) {
+#pragma unroll
+        for (int t = 0; t < V; ++t) st4(p.grad_x_l + row * p.ld_gl + (t * LPR + s) * 4, acc[t]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+#define SGB_QUAD_COMBOS(X) \
+  X(4, 8, 1) X(4, 8, 2) X(4, 8, 4) X(3, 8, 3) X(3, 8, 1) X(2, 8, 1) X(2, 8, 2) X(2, 32, 1) X(2, 32, 2) X(4, 32, 1) X(4, 32, 2) X(4, 32, 4)
+
+struct QShape {
+  int v, lpr;
+};
+
+// F = 16*V*LPR/4 ... a lane holds V float4, LPR lanes per row: F = 4*V*LPR; heads must not split a
+// float4 slice: C % (4*LPR) == 0.
+bool quad_shape(int H, int C, QShape& qs) {
+  const int F = H * C;
+  const int lprs[2] = {8, 32};
+  for (int i = 0; i < 2; ++i) {
+    const int lpr = lprs[i];
+    if (F % (4 * lpr) != 0 || C % (4 * lpr) != 0) continue;
+    const int v = F / (4 * lpr);
+    if (v > 4 || v % H != 0) continue;
+#define X(V, L, Hh) if (v == V && lpr == L && H == Hh) { qs = {V, L}; return true; }
+    SGB_QUAD_COMBOS(X)
+#undef X
+  }
+  return false;
+}
+
+int pick_rpw(int64_t n_rows, int G) {
+  // rows per warp: enough warps to fill the machine several times over, at most 32 rows (rowptr lives in lanes)
+  const int64_t target_warps = static_cast<int64_t>(sm_count()) * 16 * 6;
+  int64_t rpw = n_rows / target_warps;
+  rpw = rpw / G * G;
+  if (rpw < G) rpw = G;
+  if (rpw > 32) rpw = 32;
+  return static_cast<int>(rpw);
+}
+
+constexpr int kDFwd = 4, kDDst = 4, kDSrc = 3;
+
+template <typename K>
+bool set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)) == cudaSuccess;
+}
+
+}  // namespace
+
+bool quad_fwd_launch(const GatParams& p, cudaStream_t stream) {
+  QShape qs;
+  if (!quad_shape(p.H, p.C, qs)) return false;
+  const int G = 32 / qs.lpr;
+  const int rpw = pick_rpw(p.n_dst, G);
+  const int64_t nchunks = ceil_div(p.n_dst, rpw);
+  const unsigned blocks = static_cast<unsigned>(ceil_div(nchunks, kQW));
+#define X(V, L, Hh)                                                                                   \
+  if (qs.v == V && qs.lpr == L && p.H == Hh) {                                                        \
+    const size_t smem = static_cast<size_t>(kQW) * kDFwd * V * 512;                                   \
+    auto kern = gatv2_fwd_quad_kernel<V, L, Hh, kDFwd>;                                               \
+    if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                      \
+    kern<<<blocks, kQThreads, smem, stream>>>(p, rpw, nchunks);                                       \
+    return true;                                                                                      \
+  }
+  SGB_QUAD_COMBOS(X)
+#undef X
+  return false;
+}
+
+static int quad_dst_blocks(int64_t n_dst, int rpw) {
+  const int64_t nchunks = ceil_div(n_dst > 0 ? n_dst : 1, rpw);
+  const int64_t want = ceil_div(nchunks, kQW);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+  return static_cast<int>(want < cap ? want : cap);
+}
+
+size_t quad_bwd_partial_floats(int H, int C) {
+  QShape qs;
+  if (!quad_shape(H, C, qs)) return 0;
+  return static_cast<size_t>(sm_count()) * 4 * 2 * H * C;
+}
+
+bool quad_bwd_launch(const GatParams& p, float* grad_att, float* grad_bias, cudaStream_t stream) {
+  QShape qs;
+  if (!quad_shape(p.H, p.C, qs)) return false;
+  const int G = 32 / qs.lpr;
+  const int F = p.H * p.C;
+  if (p.n_dst > 0) {
+    const int rpw = pick_rpw(p.n_dst, G);
+    const int64_t nchunks = ceil_div(p.n_dst, rpw);
+    const int nb = quad_dst_blocks(p.n_dst, rpw);
+#define X(V, L, Hh)                                                                                   \
+  if (qs.v == V && qs.lpr == L && p.H == Hh) {                                                        \
+    const size_t smem = static_cast<size_t>(kQW) * (kDDst + 1) * V * 512;                             \
+    auto kern = gatv2_bwd_dst_quad_kernel<V, L, Hh, kDDst>;                                           \
+    if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                      \
+    kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks);                                           \
+  }
+    SGB_QUAD_COMBOS(X)
+#undef X
+    quad_colsum_kernel<<<static_cast<unsigned>(ceil_div(2 * F, 32)), dim3(32, 8), 0, stream>>>(p.partial, nb, 2 * F, F,
+                                                                                               grad_att, grad_bias);
+  }
+  if (p.n_src > 0) {
+    const int rpw = pick_rpw(p.n_src, G);
+    const int64_t nchunks = ceil_div(p.n_src, rpw);
+    const unsigned blocks = static_cast<unsigned>(ceil_div(nchunks, kQW));
+#define X(V, L, Hh)                                                                                   \
+  if (qs.v == V && qs.lpr == L && p.H == Hh) {                                                        \
+    const size_t smem = static_cast<size_t>(kQW) * kDSrc * (2 * V + 1) * 512;                         \
+    auto kern = gatv2_bwd_src_quad_kernel<V, L, Hh, kDSrc>;                                           \
+    if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                      \
+    kern<<<blocks, kQThreads, smem, stream>>>(p, rpw, nchunks);                                       \
+  }
+    SGB_QUAD_COMBOS(X)
+#undef X
+  }
+  return true;
+}
+
+}  // namespace sgb

@@ -114,6 +114,27 @@ def test_gatv2_fused_gelu_and_strided_slices():
     assert float(G[:, 2 * F:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("H,C", [(2, 64), (4, 128)])
+def test_gatv2_large_graph_multi_chunk(H, C):
+    """Enough rows that every warp of the persistent dst pass owns several row chunks."""
+    n_src, n_dst, E = 30_011, 40_003, 160_000
+    x_l, x_r, att, bias, ei = _gat_case(n_src, n_dst, E, H, C, seed=77)
+    xl_r, xr_r, att_r, b_r = (t.clone().requires_grad_() for t in (x_l, x_r, att, bias))
+    ref = torch.nn.functional.gelu(
+        pyg_ref.gatv2_aggregate(xl_r.view(n_src, H, C), xr_r.view(n_dst, H, C), ei, att_r, b_r))
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(7))
+    (ref * w).sum().backward()
+    csr = ops.build_csr(ei.cuda(), n_src, n_dst)
+    xl_g, xr_g, att_g, b_g = (t.clone().cuda().requires_grad_() for t in (x_l, x_r, att, bias))
+    out = ops.GATv2AggregateFn.apply(xl_g, xr_g, att_g, b_g, csr, H, C, 0.2, 0.0, False, 0, True)
+    (out * w.cuda()).sum().backward()
+    assert rel_err(out, ref) < TOL
+    assert rel_err(xl_g.grad, xl_r.grad) < TOL
+    assert rel_err(xr_g.grad, xr_r.grad) < TOL
+    assert rel_err(att_g.grad, att_r.grad) < TOL
+    assert rel_err(b_g.grad, b_r.grad) < TOL
+
+
 def test_gatv2_edge_cases_empty_and_single():
     H, C = 2, 64
     F = H * C
