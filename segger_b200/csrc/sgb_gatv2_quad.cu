@@ -15,8 +15,7 @@
 //    Destination-side rows (x_r, grad_out, out) travel through the same ring as "header" steps.
 //  * the column index for step K+D is loaded one iteration before its copy is issued, so no
 //    dependent global load sits on the issue path.
-//  * LeakyReLU logits use lrelu(z) = c1*z + c2*|z| (c1 = (1+slope)/2, c2 = (1-slope)/2): two FMAs
-//    per element with |z| as a free operand modifier.
+//  * LeakyReLU is max(z, slope*z) (FMUL + FMNMX per element, rounded like the reference's leaky_relu).
 //  * online softmax with a lazily updated maximum: the running accumulator is only rescaled when a
 //    logit exceeds the reference maximum by more than kTau (warp-uniform rare branch).  The saved
 //    (stat_max, stat_den) pair is self-consistent, which is all the backward needs.
@@ -45,8 +44,11 @@ __device__ __forceinline__ float4 sub4(const float4 a, const float4 b) {
 __device__ __forceinline__ float4 mul4(const float4 a, const float4 b) {
   return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
 }
-__device__ __forceinline__ float dotabs4(const float4 a, const float4 z) {
-  return a.x * fabsf(z.x) + a.y * fabsf(z.y) + a.z * fabsf(z.z) + a.w * fabsf(z.w);
+// LeakyReLU for 0 <= slope <= 1 as max(z, slope*z): FMUL + FMNMX, the product rounded per element like
+// the reference's leaky_relu (a split  c1*sum(a z) + c2*sum(a |z|)  saves one instruction per element but
+// measured no faster end to end, so the reference's own rounding is kept).
+__device__ __forceinline__ float4 lrelu_max4(const float4 z, float slope) {
+  return make_float4(fmaxf(z.x, slope * z.x), fmaxf(z.y, slope * z.y), fmaxf(z.z, slope * z.z), fmaxf(z.w, slope * z.w));
 }
 
 template <int LPR>
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
   float4 a[V];
 #pragma unroll
   for (int t = 0; t < V; ++t) a[t] = ldg4(p.att + (t * LPR + s) * 4);
-  const float c1 = 0.5f * (1.0f + p.slope), c2 = 0.5f * (1.0f - p.slope);
+  const float slope = p.slope;
   const bool training = p.training != 0;
 
   for (int64_t chunk = static_cast<int64_t>(blockIdx.x) * kQW + warp; chunk < nchunks;
@@ -216,15 +218,13 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
         float lg[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          float p1 = 0.f, p2 = 0.f;
+          float p1 = 0.f;
 #pragma unroll
           for (int u = 0; u < VPH; ++u) {
             const int t = h * VPH + u;
-            const float4 z = add4(x[t], r[t]);
-            p1 += dot4(a[t], z);
-            p2 += dotabs4(a[t], z);
+            p1 += dot4(a[t], lrelu_max4(add4(x[t], r[t]), slope));
           }
-          lg[h] = group_sum<LPR>(fmaf(c1, p1, c2 * p2));
+          lg[h] = group_sum<LPR>(p1);
         }
         const int e = eid_next;
         if (training && k + 1 < c_deg) eid_next = __ldg(p.eid + c_beg + k + 1);
@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_dst_quad_kernel(const Gat
     a[t] = ldg4(p.att + (t * LPR + s) * 4);
     gatt[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const float c1 = 0.5f * (1.0f + p.slope), c2 = 0.5f * (1.0f - p.slope);
   const float slope = p.slope;
   const bool training = p.training != 0;
 
@@ -409,21 +408,20 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_dst_quad_kernel(const Gat
       for (int k = 0; k < c_mx; ++k) {
         issue(); gen(); cp_wait<D - 1>();
         const bool act = k < c_deg;
-        float4 z[V];
+        float4 z[V];   // holds u = lrelu(z): sign(u) == sign(z), so lrelu'(z) is recovered from u
         float lg[H], dd[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          float p1 = 0.f, p2 = 0.f, pd = 0.f;
+          float p1 = 0.f, pd = 0.f;
 #pragma unroll
           for (int u = 0; u < VPH; ++u) {
             const int t = h * VPH + u;
             const float4 x = lds4(pipe.read_addr(t));
             pd += dot4(g4[t], x);
-            z[t] = add4(x, r[t]);
+            z[t] = lrelu_max4(add4(x, r[t]), slope);
             p1 += dot4(a[t], z[t]);
-            p2 += dotabs4(a[t], z[t]);
           }
-          lg[h] = group_sum<LPR>(fmaf(c1, p1, c2 * p2));
+          lg[h] = group_sum<LPR>(p1);
           dd[h] = group_sum<LPR>(pd);
         }
         pipe.consumed();
@@ -460,7 +458,7 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_dst_quad_kernel(const Gat
           const float4 da = make_float4(d * a[t].x, d * a[t].y, d * a[t].z, d * a[t].w);
           gr[t].x = fmaf(da.x, sel.x, gr[t].x); gr[t].y = fmaf(da.y, sel.y, gr[t].y);
           gr[t].z = fmaf(da.z, sel.z, gr[t].z); gr[t].w = fmaf(da.w, sel.w, gr[t].w);
-          fma4(gatt[t], d, mul4(zz, sel));
+          fma4(gatt[t], d, zz);
         }
       }
       if (rvalid) {
@@ -691,9 +689,12 @@ bool set_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+// max(z, slope*z) and the sign test on lrelu(z) in the backward need 0 <= slope <= 1
+static bool quad_slope_ok(float slope) { return slope >= 0.f && slope <= 1.f; }
+
 bool quad_fwd_launch(const GatParams& p, cudaStream_t stream) {
   QShape qs;
-  if (!quad_shape(p.H, p.C, qs)) return false;
+  if (!quad_slope_ok(p.slope) || !quad_shape(p.H, p.C, qs)) return false;
   const int G = 32 / qs.lpr;
   const int rpw = pick_rpw(p.n_dst, G);
   const int64_t nchunks = ceil_div(p.n_dst, rpw);
@@ -726,7 +727,7 @@ size_t quad_bwd_partial_floats(int H, int C) {
 
 bool quad_bwd_launch(const GatParams& p, float* grad_att, float* grad_bias, cudaStream_t stream) {
   QShape qs;
-  if (!quad_shape(p.H, p.C, qs)) return false;
+  if (!quad_slope_ok(p.slope) || !quad_shape(p.H, p.C, qs)) return false;
   const int G = 32 / qs.lpr;
   const int F = p.H * p.C;
   if (p.n_dst > 0) {

@@ -41,6 +41,29 @@ def _fp64_truth(ref, x, edges, pos, bat, g):
     return out, {n: p.grad for n, p in r64.named_parameters()}
 
 
+def _ulp_perturbed_noise(ref, x, edges, pos, bat, g, grads_64, trials=3):
+    """Second conditioning yardstick: the fp32 oracle re-run with every weight moved by ~half an
+    ulp (relative 2^-24 * N(0,1), fixed seed).  LeakyReLU has a kink: when some z = x_l[j] + x_r[i]
+    lies within an ulp of 0, ANY fp32 implementation may put it on the other side than the fp64
+    run, which moves one output channel of the affected lin_l/lin_r gradient (and, diluted, every
+    gradient upstream of it) by far more than 1e-4 -- measured: one flipped element = 2e-3 of
+    lin_r.weight of the last tx-tx conv (scripts/debug_mix2.py).  Such a gradient is not pinned by
+    the fp32 reference itself, so the bar for it is what ulp-level perturbation does to the oracle."""
+    import copy
+    gen = torch.Generator().manual_seed(1234)
+    worst = {}
+    for _ in range(trials):
+        r = copy.deepcopy(ref)
+        r.zero_grad()
+        with torch.no_grad():
+            for p in r.parameters():
+                p.mul_(1 + 2.0 ** -24 * torch.randn(p.shape, generator=gen))
+        _loss(r(x, edges, pos, bat), g).backward()
+        for n, p in r.named_parameters():
+            worst[n] = max(worst.get(n, 0.0), rel_err(p.grad, grads_64[n]))
+    return worst
+
+
 @pytest.mark.parametrize("cfg", CONFIGS)
 def test_istencoder_forward_backward_vs_oracle(cfg):
     in_c, hid, out_c, n_mid, heads = cfg
@@ -58,12 +81,13 @@ def test_istencoder_forward_backward_vs_oracle(cfg):
         assert out_p[k].shape == out_r[k].shape
         assert rel_err(out_p[k], out_r[k]) < TOL, k
     ref_grads = {n: p.grad for n, p in ref.named_parameters()}
+    ulp_noise = _ulp_perturbed_noise(ref, x, edges, pos, bat, g, grads_64)
     checked = 0
     for n, p in prod.named_parameters():
         if "bd___contains___tx" in n:
             continue
         assert p.grad is not None, n
-        noise = rel_err(ref_grads[n], grads_64[n])          # fp32 oracle's own conditioning error
+        noise = max(rel_err(ref_grads[n], grads_64[n]), ulp_noise[n])   # fp32 oracle's own conditioning error
         assert rel_err(p.grad, grads_64[n]) < max(TOL, 2 * noise), (n, noise)
         if noise < TOL / 4:
             assert rel_err(p.grad, ref_grads[n]) < TOL, n     # well-conditioned: flat 1e-4 vs the fp32 oracle
