@@ -114,20 +114,26 @@ SGB_API int sgb_dropout_mask(uint64_t seed, int64_t E, int H, float p_drop, uint
  * Dense projections y = x W^T + b (PyG Linear / HeteroDictLinear / GATv2Conv.lin_l, lin_r /
  * torch.nn.Linear of the positional MLP; models/ist_encoder.py:43-47,261,282-286 and the
  * GATv2Conv constructors at :111-131).  x [M,K] ldx, w [N,K] ldw, y [M,N] ldy, fp32 in/out.
- * Error-compensated split-TF32 on tcgen05 (accumulators in TMEM) when the tile is a real dense GEMM,
- * fp32 SIMT otherwise.  The tensor core accumulates in fp32 with round-toward-zero, a ~K*2^-27
- * *biased* relative error that the attention backward amplifies (d_e - c_i cancellation), so
- * callers that will differentiate through a following GATv2 layer pass exact != 0 to force the
- * round-to-nearest fp32 SIMT path ("GEMM precision").  y_act (optional) receives act(y).
+ * Error-compensated split-TF32 on tcgen05 when the tile is a real dense GEMM, fp32 SIMT otherwise.
+ * The tensor core accumulates in fp32 with round-toward-zero, a biased error that the attention
+ * backward amplifies (d_e - c_i cancellation), so the reduction is cut into chunks whose TMEM
+ * partials are added in registers with round-to-nearest ("GEMM precision"):
+ *   exact = 0  3 products, 32-deep chunks (gradients, inference)
+ *   exact = 1  4 products (fp32-exact operand products), 32-deep chunks: for projections that a
+ *              following GATv2 layer will be differentiated through
+ *   exact = 2  force the fp32 SIMT kernel
+ * y_act (optional) receives act(y).  ws: sgb_linear_workspace_bytes(N, K) bytes of device scratch
+ * (the split + swizzled copy of the weights); fwd and dgrad of the same weights need the same size.
  * ---------------------------------------------------------------------------------------- */
+SGB_API size_t sgb_linear_workspace_bytes(int64_t N, int64_t K);
 SGB_API int sgb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b /*or NULL*/,
                    int64_t M, int64_t N, int64_t K, float* y, int64_t ldy, int act,
-                   float* y_act /*or NULL*/, int64_t ldya, int exact, void* stream);
+                   float* y_act /*or NULL*/, int64_t ldya, int exact, void* ws, size_t ws_bytes, void* stream);
 /* dx = dy W (+ dx if accumulate) ; if act_pre != NULL: dx *= act'(act_pre) (GELU/SiLU backward
  * fused as epilogue).  dy [M,N], w [N,K], dx [M,K]. */
 SGB_API int sgb_linear_dgrad(const float* dy, int64_t ldy, const float* w, int64_t ldw, int64_t M, int64_t N,
                      int64_t K, float* dx, int64_t ldx, int accumulate, int act,
-                     const float* act_pre /*or NULL*/, int64_t ld_pre, void* stream);
+                     const float* act_pre /*or NULL*/, int64_t ld_pre, void* ws, size_t ws_bytes, void* stream);
 /* dw = dy^T x (+ dw if accumulate), db = column sums of dy (+ db if accumulate); deterministic split-K. */
 SGB_API size_t sgb_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
 SGB_API int sgb_linear_wgrad(const float* dy, int64_t ldy, const float* x, int64_t ldx, int64_t M, int64_t N,

@@ -43,10 +43,11 @@ _PROTOS = {
                               c_f32, c_u64, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp,
                               c_sz, c_vp]),
     "sgb_dropout_mask": (c_int, [c_u64, c_i64, c_int, c_f32, c_vp, c_vp]),
+    "sgb_linear_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "sgb_linear_fwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_vp,
-                               c_i64, c_int, c_vp]),
+                               c_i64, c_int, c_vp, c_sz, c_vp]),
     "sgb_linear_dgrad": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int,
-                                 c_vp, c_i64, c_vp]),
+                                 c_vp, c_i64, c_vp, c_sz, c_vp]),
     "sgb_linear_wgrad_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "sgb_linear_wgrad": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_vp,
                                  c_sz, c_vp]),

@@ -23,7 +23,7 @@ constexpr unsigned kFull = 0xffffffffu;
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline __host__ __device__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // number of SMs of the current device (cached per process)
 int sm_count();

@@ -11,9 +11,16 @@ static int check_dims(const char* fn, int64_t M, int64_t N, int64_t K) {
   return SGB_OK;
 }
 
+// workspace of sgb_linear_fwd (weights [N,K]) and sgb_linear_dgrad (same weights: pass the same N, K)
+extern "C" size_t sgb_linear_workspace_bytes(int64_t N, int64_t K) {
+  if (N <= 0 || K <= 0 || !tc_enabled()) return 0;
+  const size_t a = tc_linear_workspace_bytes(N, K), b = tc_linear_workspace_bytes(K, N);
+  return a > b ? a : b;
+}
+
 extern "C" int sgb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b, int64_t M,
                               int64_t N, int64_t K, float* y, int64_t ldy, int act, float* y_act, int64_t ldya,
-                              int exact, void* stream) {
+                              int exact, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_dims("linear_fwd", M, N, K);
   if (rc != SGB_OK) return rc;
   if (M == 0 || N == 0) return SGB_OK;
@@ -21,21 +28,26 @@ extern "C" int sgb_linear_fwd(const float* x, int64_t ldx, const float* w, int64
   SGB_REQUIRE(ldx >= K && ldw >= K && ldy >= N && (!y_act || ldya >= N), SGB_ERR_ARG, "linear_fwd: leading dimension too small");
   SGB_REQUIRE(act >= SGB_ACT_NONE && act <= SGB_ACT_SILU, SGB_ERR_ARG, "linear_fwd: unknown activation %d", act);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!exact && tc_linear_fwd_ok(x, ldx, w, ldw, M, N, K)) return tc_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, act, y_act, ldya, st);
+  if (exact != 2 && tc_linear_fwd_ok(x, ldx, w, ldw, M, N, K)) {
+    SGB_REQUIRE(ws && ws_bytes >= tc_linear_workspace_bytes(N, K), SGB_ERR_WORKSPACE, "linear_fwd: workspace too small");
+    return tc_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, act, y_act, ldya, exact, ws, st);
+  }
   return simt_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, act, y_act, ldya, st);
 }
 
 extern "C" int sgb_linear_dgrad(const float* dy, int64_t ldy, const float* w, int64_t ldw, int64_t M, int64_t N,
                                 int64_t K, float* dx, int64_t ldx, int accumulate, int act, const float* act_pre,
-                                int64_t ld_pre, void* stream) {
+                                int64_t ld_pre, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_dims("linear_dgrad", M, N, K);
   if (rc != SGB_OK) return rc;
   if (M == 0 || K == 0) return SGB_OK;
   SGB_REQUIRE(dx && (N == 0 || (dy && w)), SGB_ERR_ARG, "linear_dgrad: null tensor");
   SGB_REQUIRE(ldy >= N && ldw >= K && ldx >= K && (!act_pre || ld_pre >= K), SGB_ERR_ARG, "linear_dgrad: leading dimension too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tc_linear_dgrad_ok(dy, ldy, w, ldw, M, N, K))
-    return tc_linear_dgrad(dy, ldy, w, ldw, M, N, K, dx, ldx, accumulate, act, act_pre, ld_pre, st);
+  if (tc_linear_dgrad_ok(dy, ldy, w, ldw, M, N, K)) {
+    SGB_REQUIRE(ws && ws_bytes >= tc_linear_workspace_bytes(K, N), SGB_ERR_WORKSPACE, "linear_dgrad: workspace too small");
+    return tc_linear_dgrad(dy, ldy, w, ldw, M, N, K, dx, ldx, accumulate, act, act_pre, ld_pre, ws, st);
+  }
   return simt_linear_dgrad(dy, ldy, w, ldw, M, N, K, dx, ldx, accumulate, act, act_pre, ld_pre, st);
 }
 

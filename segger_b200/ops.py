@@ -140,10 +140,11 @@ def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE,
                want_pre: bool = True, exact: Optional[bool] = None) -> Tuple[Optional[Tensor], Optional[Tensor]]:
     """(y, act(y)) with y = x w^T + b.  y / y_act may be preallocated (strided) views.
 
-    ``exact``: force the round-to-nearest fp32 SIMT GEMM instead of the tcgen05 split-TF32 one.
-    Default: exact while autograd is recording (the result will be differentiated through the
-    attention layers, whose backward amplifies the tensor core's biased accumulation error --
-    DESIGN.md "GEMM precision"), tensor cores under ``torch.no_grad()`` (inference)."""
+    ``exact``: 0/False = 3-product split-TF32, 1/True = 4 products (fp32-exact operand products);
+    both accumulate 32-deep TMEM chunks in registers with round-to-nearest; 2 = force the fp32 SIMT
+    kernel.  Default: exact while autograd is recording (the result will be
+    differentiated through the attention layers, whose backward amplifies the tensor core's biased
+    round-toward-zero accumulation -- DESIGN.md "GEMM precision"), fast under ``torch.no_grad()``."""
     if exact is None:
         exact = torch.is_grad_enabled()
     x, w = _rowmajor(x), _rowmajor(w)
@@ -157,11 +158,13 @@ def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE,
     if act != ACT_NONE and y_act is None:
         y_act = torch.empty(M, N, dtype=torch.float32, device=dev)
     b = _vec(b)
-    check(_lib.load().sgb_linear_fwd(ptr(x), _ld(x), ptr(w), _ld(w), ptr(b), M, N, K, ptr(y), _ld(y), act,
-                                     ptr(y_act), _ld(y_act) if y_act is not None else 0, int(bool(exact)),
-                                     stream_ptr(dev)),
+    lib = _lib.load()
+    ws = _ws(lib.sgb_linear_workspace_bytes(N, K), dev)
+    check(lib.sgb_linear_fwd(ptr(x), _ld(x), ptr(w), _ld(w), ptr(b), M, N, K, ptr(y), _ld(y), act,
+                             ptr(y_act), _ld(y_act) if y_act is not None else 0, int(exact),
+                             ptr(ws), ws.numel(), stream_ptr(dev)),
           "linear_fwd")
-    _count(1)
+    _count(2)
     return y, y_act
 
 
@@ -172,11 +175,14 @@ def linear_dgrad(dy: Tensor, w: Tensor, dx: Optional[Tensor] = None, accumulate:
     K = w.size(1)
     if dx is None:
         dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
-    check(_lib.load().sgb_linear_dgrad(ptr(dy), _ld(dy), ptr(w), _ld(w), M, N, K, ptr(dx), _ld(dx),
-                                       int(accumulate), act, ptr(act_pre),
-                                       _ld(act_pre) if act_pre is not None else 0, stream_ptr(dy.device)),
+    lib = _lib.load()
+    ws = _ws(lib.sgb_linear_workspace_bytes(N, K), dy.device)
+    check(lib.sgb_linear_dgrad(ptr(dy), _ld(dy), ptr(w), _ld(w), M, N, K, ptr(dx), _ld(dx),
+                               int(accumulate), act, ptr(act_pre),
+                               _ld(act_pre) if act_pre is not None else 0, ptr(ws), ws.numel(),
+                               stream_ptr(dy.device)),
           "linear_dgrad")
-    _count(1)
+    _count(2)
     return dx
 
 
