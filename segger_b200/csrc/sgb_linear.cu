@@ -72,8 +72,9 @@ extern "C" int sgb_linear_wgrad(const float* dy, int64_t ldy, const float* x, in
   SGB_REQUIRE(ws && ws_bytes >= sgb_linear_wgrad_workspace_bytes(M, N, K), SGB_ERR_WORKSPACE, "linear_wgrad: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (K > 0) {
-    if (tc_linear_wgrad_ok(dy, ldy, x, ldx, M, N, K)) rc = tc_linear_wgrad(dy, ldy, x, ldx, M, N, K, dw, lddw, accumulate, ws, st);
-    else rc = simt_linear_wgrad(dy, ldy, x, ldx, M, N, K, dw, lddw, accumulate, ws, st);
+    if (tc_linear_wgrad_ok(dy, ldy, x, ldx, M, N, K))   // the tensor-core kernel also produces db (fused column sums)
+      return tc_linear_wgrad(dy, ldy, x, ldx, M, N, K, dw, lddw, db, accumulate, ws, st);
+    rc = simt_linear_wgrad(dy, ldy, x, ldx, M, N, K, dw, lddw, accumulate, ws, st);
     if (rc != SGB_OK) return rc;
   }
   if (db) rc = linear_colsum(dy, ldy, M, N, db, accumulate, static_cast<char*>(ws) + wgrad_gemm_ws(M, N, K), st);

@@ -29,6 +29,6 @@ int tc_linear_dgrad(const float* dy, int64_t ldy, const float* w, int64_t ldw, i
 bool tc_linear_wgrad_ok(const float* dy, int64_t ldy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K);
 size_t tc_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int tc_linear_wgrad(const float* dy, int64_t ldy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* dw,
-                    int64_t lddw, int accumulate, void* ws, cudaStream_t stream);
+                    int64_t lddw, float* db, int accumulate, void* ws, cudaStream_t stream);
 
 }  // namespace sgb

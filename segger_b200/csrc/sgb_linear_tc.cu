@@ -14,8 +14,8 @@
 // 8 products; kc = 4 (one 32-deep stage) is the fast setting for gradients.
 //
 // Persistent, warp-specialised CTA (one per SM, 288 threads):
-//   warps 0-3   producers: cp.async (LDGSTS) of the raw A (and, for wgrad, B) k-slab several slabs ahead into a
-//               shared-memory ring, then hi/lo split and swizzle-128B stores into the UMMA canonical shared-memory layout (K-major or
+//   warps 0-3   producers: cp.async (LDGSTS) of the raw A (and, for wgrad, B) k-slab straight into the stage slot
+//               S-1 slabs ahead, then an in-place hi/lo split with swizzle-128B stores into the UMMA canonical shared-memory layout (K-major or
 //               MN-major, so x W^T, dy W and dy^T x all run without a transpose), fence.proxy.async + mbarrier
 //               arrive.  Weights (forward / dgrad B operand) are split and laid out ONCE per call by
 //               pack_b_kernel in the exact shared-memory image, and a stage's B tile is one cp.async.bulk
@@ -45,6 +45,7 @@ constexpr int kEpiWarps = 8;       // two per TMEM lane quarter, each owning hal
 constexpr int kThreads = (kProducerWarps + 1 + kEpiWarps) * 32;   // 416
 constexpr int kMaxStages = 4;
 // epilogue transpose buffer: per warp 32 rows x (PW + 4) floats, PW = columns written out per pass
+constexpr int kPW = 16;            // 64-byte row segments per write-out pass: leaves shared memory for a third 64 KB stage
 constexpr size_t stg_bytes(int pw) { return static_cast<size_t>(kEpiWarps) * 32 * (pw + 4) * sizeof(float); }
 constexpr int kAccBufs = 4;        // TMEM chunk accumulators in flight (4 x BN columns <= 512)
 
@@ -66,6 +67,9 @@ struct TcParams {
   int stages;
   int terms;                // 3: hi*hi + lo*hi + hi*lo (~2^-22);  4: + lo*lo (fp32-exact products)
   int kc;                   // K=8 steps per TMEM chunk (1, 2 or 4): accumulations done inside the tensor core
+  float* colsum;            // wgrad only: column sums of A's source (db = sum_m dy[m, :]): [splits][M] partials, or db itself
+  int colsum_accumulate;    // splits == 1: add into db
+  int dbg;                  // timing experiments only (SEGGER_B200_TC_DBG bitmask): results are wrong when set
   const float* Bp;          // B_PACKED: pre-split weights in the shared-memory tile image [n-tile][k-stage][hi|lo]
 };
 
@@ -213,8 +217,10 @@ __device__ __forceinline__ void stage_raw(const float* __restrict__ src, int64_t
   }
 }
 
-template <int EXT, bool MN>
-__device__ __forceinline__ void split_slab(const uint8_t* raw_tile, uint8_t* hi_tile, uint8_t* lo_tile, int t) {
+// SUM (MN-major only): also accumulate the raw values per 32-wide MN block into cs[] -- thread t sees, for every
+// block, the same 4 columns (chunk t & 7) of two reduction rows per slab, so cs[blk] is a partial column sum.
+template <int EXT, bool MN, bool SUM = false>
+__device__ __forceinline__ void split_slab(const uint8_t* raw_tile, uint8_t* hi_tile, uint8_t* lo_tile, int t, float4* cs = nullptr) {
   constexpr int NV = EXT * 8 / kProducerThreads;
   const int chunk = t & 7;
 #pragma unroll
@@ -222,6 +228,10 @@ __device__ __forceinline__ void split_slab(const uint8_t* raw_tile, uint8_t* hi_
     const int ri = (t >> 3) + (kProducerThreads / 8) * i;
     const uint32_t off = chunk_offset<EXT, MN>(ri, chunk);
     const float4 v = *reinterpret_cast<const float4*>(raw_tile + off);
+    if constexpr (SUM) {
+      float4& c = cs[(kProducerThreads / 8) * i / 32];     // blk = ri >> 5 (t >> 3 < 16)
+      c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+    }
     float4 h, l;
     h.x = rn_tf32(v.x); l.x = rn_tf32(v.x - h.x);
     h.y = rn_tf32(v.y); l.y = rn_tf32(v.y - h.y);
@@ -264,17 +274,16 @@ __global__ void pack_b_kernel(const float* __restrict__ w, int64_t ldw, int64_t 
   *reinterpret_cast<float4*>(blk + BN * 128 + off) = l;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool B_PACKED, int RS>
+template <int BN, bool A_MN, bool B_MN, bool B_PACKED, int S>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t kATile = BM * 128;            // bytes of one hi (or lo) A tile
   constexpr uint32_t kBTile = BN * 128;
   constexpr uint32_t kStageBytes = 2 * kATile + 2 * kBTile;
-  constexpr uint32_t kRawBytes = kATile + (B_PACKED ? 0 : kBTile);     // one raw (unsplit) slab
   constexpr uint32_t kTmemCols = kAccBufs * BN;    // 256 or 512: a power of two >= 32
   static_assert(BN <= 128, "the register accumulator holds one row x BN/2 columns per epilogue thread");
   constexpr int CW = BN / 2;                        // columns per epilogue warp
-  constexpr int PW = B_PACKED ? 32 : 16;            // columns per write-out pass (wgrad tiles are tiny: keep smem for the raw ring)
+  constexpr int PW = kPW;                           // columns per write-out pass
   constexpr int kStgLd = PW + 4;
   static_assert(!(B_PACKED && B_MN), "packed weights are always K-major in shared memory");
 
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
   __shared__ uint32_t tmem_base_holder;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int stages = p.stages;
+  constexpr int stages = S;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -311,11 +320,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
 
   if (warp < kProducerWarps) {
     // ===================================== producers =====================================
-    // cp.async keeps RS-1 raw slabs in flight ahead of the slab being split (no register staging).
+    // A stage slot is filled in place: cp.async lands the RAW fp32 slab in the slot's hi tiles as soon as the
+    // MMAs of the slot's previous use retire (S-1 slabs ahead of the split), the same threads later read their
+    // own chunks back, write hi over them and lo beside them.  The packed weights of the slot are one bulk copy
+    // issued at the same moment.
     const int t = threadIdx.x;
-    uint8_t* raw_base = smem + static_cast<size_t>(stages) * kStageBytes;
-    int stage = 0;
-    uint32_t phase = 0;
     struct Cur { int64_t tile, k0, ke; bool live; };
     auto tile_range = [&](Cur& c) {
       const int64_t sp = c.tile / (num_n * num_m);
@@ -335,42 +344,75 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
         if (c.live) tile_range(c);
       }
     };
-    auto issue = [&](const Cur& c, int slot) {
+    int istage = 0, cstage = 0;
+    uint32_t iphase = 0;
+    auto issue = [&](const Cur& c) {
       const int64_t nb = c.tile % num_n, mb = (c.tile / num_n) % num_m;
-      const uint32_t raw = smem_u32(raw_base + static_cast<size_t>(slot) * kRawBytes);
-      stage_raw<BM, A_MN>(p.A, p.lda, mb * BM, p.M, c.k0, c.ke, raw, t);
-      if constexpr (!B_PACKED) stage_raw<BN, B_MN>(p.B, p.ldb, nb * BN, p.N, c.k0, c.ke, raw + kATile, t);
+      mbar_wait(smem_u32(&bar_empty[istage]), iphase ^ 1u);
+      uint8_t* st = smem + static_cast<size_t>(istage) * kStageBytes;
+      if (B_PACKED && t == 0) {
+        const int64_t blk = nb * num_ks + c.k0 / BK;
+        mbar_arrive_expect_tx(smem_u32(&bar_full[istage]), 2 * kBTile);
+        bulk_g2s(smem_u32(st + 2 * kATile), p.Bp + static_cast<size_t>(blk) * (2 * BN * 32), 2 * kBTile, smem_u32(&bar_full[istage]));
+      }
+      stage_raw<BM, A_MN>(p.A, p.lda, mb * BM, p.M, c.k0, c.ke, smem_u32(st), t);
+      if constexpr (!B_PACKED) stage_raw<BN, B_MN>(p.B, p.ldb, nb * BN, p.N, c.k0, c.ke, smem_u32(st + 2 * kATile), t);
+      if (++istage == S) { istage = 0; iphase ^= 1u; }
+    };
+    // fused bias gradient (wgrad): column sums of dy, accumulated while its slabs pass through the producers
+    constexpr bool kColsum = A_MN;
+    float4 cs[kColsum ? BM / 32 : 1];
+#pragma unroll
+    for (int i = 0; i < (kColsum ? BM / 32 : 1); ++i) cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* red = reinterpret_cast<float*>(smem + static_cast<size_t>(S) * kStageBytes + stg_bytes(kPW));
+    auto flush_colsum = [&](int64_t tl) {
+      if constexpr (kColsum) {
+        const int64_t nb = tl % num_n, mb = (tl / num_n) % num_m, sp = tl / (num_n * num_m);
+        if (p.colsum && nb == 0) {                   // one n-tile per (m-block, split) owns the sum
+#pragma unroll
+          for (int i = 0; i < BM / 32; ++i) *reinterpret_cast<float4*>(red + t * (BM / 8) + i * 4) = cs[i];
+          asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
+          if (t < BM / 4) {
+            const int blk = t >> 3, chunk = t & 7;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < kProducerThreads / 8; ++j) {     // fixed order: deterministic
+              const float4 v = *reinterpret_cast<const float4*>(red + ((j << 3) | chunk) * (BM / 8) + blk * 4);
+              a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            const int64_t n = mb * BM + blk * 32 + chunk * 4;
+            float* dst = p.colsum + (p.splits > 1 ? sp * p.M : 0) + n;
+            const float o[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < p.M) dst[e] = (p.splits == 1 && p.colsum_accumulate) ? dst[e] + o[e] : o[e];
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < BM / 32; ++i) cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     };
     Cur pi, ci;
     init(pi);
     init(ci);
-    int pslot = 0, cslot = 0;
 #pragma unroll
-    for (int i = 0; i < RS - 1; ++i) {
-      if (pi.live) { issue(pi, pslot); advance(pi); }
+    for (int i = 0; i < S - 1; ++i) {
+      if (pi.live) { issue(pi); advance(pi); }
       cp_async_commit();
-      pslot = (pslot + 1 == RS) ? 0 : pslot + 1;
     }
     while (ci.live) {
-      if (pi.live) { issue(pi, pslot); advance(pi); }
-      cp_async_commit();
-      pslot = (pslot + 1 == RS) ? 0 : pslot + 1;
-      cp_async_wait<RS - 1>();                      // this thread's chunks of slab `ci` have landed
-      mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-      uint8_t* st = smem + static_cast<size_t>(stage) * kStageBytes;
-      if (B_PACKED && t == 0) {
-        const int64_t blk = (ci.tile % num_n) * num_ks + ci.k0 / BK;
-        mbar_arrive_expect_tx(smem_u32(&bar_full[stage]), 2 * kBTile);
-        bulk_g2s(smem_u32(st + 2 * kATile), p.Bp + static_cast<size_t>(blk) * (2 * BN * 32), 2 * kBTile, smem_u32(&bar_full[stage]));
-      }
-      const uint8_t* raw = raw_base + static_cast<size_t>(cslot) * kRawBytes;
-      split_slab<BM, A_MN>(raw, st, st + kATile, t);
-      if constexpr (!B_PACKED) split_slab<BN, B_MN>(raw + kATile, st + 2 * kATile, st + 2 * kATile + kBTile, t);
+      cp_async_wait<S - 2>();                       // this thread's chunks of slab `ci` have landed
+      uint8_t* st = smem + static_cast<size_t>(cstage) * kStageBytes;
+      if (!(p.dbg & 2)) split_slab<BM, A_MN, kColsum>(st, st, st + kATile, t, cs);
+      if constexpr (!B_PACKED) if (!(p.dbg & 2)) split_slab<BN, B_MN>(st + 2 * kATile, st + 2 * kATile, st + 2 * kATile + kBTile, t);
       fence_proxy_async();
-      mbar_arrive(smem_u32(&bar_full[stage]));
-      if (++stage == stages) { stage = 0; phase ^= 1u; }
-      cslot = (cslot + 1 == RS) ? 0 : cslot + 1;
+      mbar_arrive(smem_u32(&bar_full[cstage]));
+      if (++cstage == S) cstage = 0;
+      const int64_t done_tile = ci.tile;
       advance(ci);
+      if (!ci.live || ci.tile != done_tile) flush_colsum(done_tile);
+      if (pi.live) { issue(pi); advance(pi); }      // refill the slot the tensor core finished with
+      cp_async_commit();
     }
     cp_async_wait<0>();
   } else if (warp == kMmaWarp) {
@@ -402,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
             const uint32_t d_tmem = tmem_base + buf * BN;
             uint32_t accum = 0;
             // small terms first: the truncating accumulator then sees the big hi*hi products last
-            for (int term = (p.terms >= 4 ? 0 : 1); term < 4; ++term) {
+            for (int term = ((p.dbg & 4) ? 3 : (p.terms >= 4 ? 0 : 1)); term < 4; ++term) {
               const uint32_t ab = (term == 3 || term == 2) ? a_hi : a_lo;      // 0: lo*lo  1: lo*hi  2: hi*lo  3: hi*hi
               const uint32_t bb = (term == 3 || term == 1) ? b_hi : b_lo;
               for (int j = j0; j < j0 + kc; ++j) {
@@ -422,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
     // ===================================== epilogue =====================================
     const int q = warp & 3;                                  // TMEM lane quarter this warp may access
     const int half = (warp - kEpiWarp0) >> 2;                // which half of the tile's columns
-    float* stg = reinterpret_cast<float*>(smem + static_cast<size_t>(stages) * kStageBytes + static_cast<size_t>(RS) * kRawBytes) +
+    float* stg = reinterpret_cast<float*>(smem + static_cast<size_t>(stages) * kStageBytes) +
                  (warp - kEpiWarp0) * (32 * kStgLd);
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * CW);
     const int chunks_per_stage = (BK / 8) / p.kc;
@@ -443,6 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
         // 32-column read-back is in flight per warp; two epilogue warps per sub-partition interleave
 #pragma unroll
         for (int c0 = 0; c0 < CW; c0 += 32) {
+          if (p.dbg & 1) break;
           uint32_t r0[32];
           tc_ld32(lane_base + buf * BN + c0, r0);
           tc_wait_ld();
@@ -464,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
       const bool vec_p = p.act_pre && (p.ld_pre % 4 == 0) && aligned16(p.act_pre) && (n0 % 4 == 0);
 #pragma unroll
       for (int c0 = 0; c0 < CW; c0 += PW) {
+        if (p.dbg & 8) break;
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < PW; j += 4)
@@ -546,29 +590,44 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, int spli
   *dst = accumulate ? *dst + s : s;
 }
 
+int env_int(const char* name, int lo, int hi, int dflt) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  const int v = atoi(e);
+  return (v < lo || v > hi) ? dflt : v;
+}
+
+__global__ void tc_colsum_reduce_kernel(const float* __restrict__ part, int splits, int64_t N, float* __restrict__ db, int accumulate) {
+  const int64_t n = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[static_cast<int64_t>(z) * N + n];
+  db[n] = accumulate ? db[n] + s : s;
+}
+
 template <int BN>
 constexpr size_t stage_bytes() { return static_cast<size_t>(2 * BM * 128 + 2 * BN * 128); }
 
 template <int BN, bool A_MN, bool B_MN, bool B_PACKED>
 int launch_tc(TcParams p, cudaStream_t stream) {
-  constexpr size_t kBudget = 226 * 1024;
-  constexpr size_t kRaw = static_cast<size_t>(BM * 128 + (B_PACKED ? 0 : BN * 128));
-  constexpr int RS = B_PACKED ? (BN == 128 ? 3 : 4) : (BN == 128 ? 2 : 4);
-  constexpr size_t kStgBytes = stg_bytes(B_PACKED ? 32 : 16);
-  int stages = static_cast<int>((kBudget - 1024 - kStgBytes - RS * kRaw) / stage_bytes<BN>());
-  if (stages > kMaxStages) stages = kMaxStages;
-  p.stages = stages;
-  const size_t smem = stages * stage_bytes<BN>() + RS * kRaw + kStgBytes + 1024;
+  constexpr int S = (BN == 128) ? 3 : 4;            // 3 x 64 KB or 4 x 48 KB stage slots
+  constexpr size_t kStgBytes = stg_bytes(kPW);
+  static_assert(S <= kMaxStages, "stage count");
+  p.stages = S;
+  p.dbg = env_int("SEGGER_B200_TC_DBG", 0, 255, 0);
+  constexpr size_t kRedBytes = A_MN ? kProducerThreads * (BM / 8) * sizeof(float) : 0;   // fused column sums
+  const size_t smem = S * stage_bytes<BN>() + kStgBytes + kRedBytes + 1024;
+  static_assert(S * stage_bytes<BN>() + kStgBytes + kRedBytes + 1024 + 256 <= 227 * 1024, "shared memory budget");
   static bool configured = false;   // per instantiation
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, A_MN, B_MN, B_PACKED, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, A_MN, B_MN, B_PACKED, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return set_error(SGB_ERR_CUDA, "tc gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   const int64_t tiles = ceil_div(p.M, BM) * ceil_div(p.N, BN) * p.splits;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  gemm_tf32x3_kernel<BN, A_MN, B_MN, B_PACKED, RS><<<grid, kThreads, smem, stream>>>(p);
+  gemm_tf32x3_kernel<BN, A_MN, B_MN, B_PACKED, S><<<grid, kThreads, smem, stream>>>(p);
   return check_launch("gemm_tf32x3");
 }
 
@@ -606,12 +665,6 @@ bool is_blackwell() {
 
 bool ok_ptr(const float* p, int64_t ld) { return aligned16(p) && ld % 4 == 0; }
 
-int env_int(const char* name, int lo, int hi, int dflt) {
-  const char* e = getenv(name);
-  if (!e) return dflt;
-  const int v = atoi(e);
-  return (v < lo || v > hi) ? dflt : v;
-}
 
 }  // namespace
 
@@ -688,29 +741,35 @@ bool tc_linear_wgrad_ok(const float* dy, int64_t ldy, const float* x, int64_t ld
   return tc_enabled() && M >= 256 && N >= 8 && K >= 8 && N % 4 == 0 && K % 4 == 0 && ok_ptr(dy, ldy) && ok_ptr(x, ldx);
 }
 size_t tc_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-  return align_up(static_cast<size_t>(tc_wgrad_splits(M, N, K)) * N * K * sizeof(float));
+  const size_t sp = static_cast<size_t>(tc_wgrad_splits(M, N, K));
+  return align_up(sp * N * K * sizeof(float)) + align_up(sp * N * sizeof(float));
 }
+// db (optional) = column sums of dy, produced by the same kernel (its producers see every dy element anyway)
 int tc_linear_wgrad(const float* dy, int64_t ldy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* dw,
-                    int64_t lddw, int accumulate, void* ws, cudaStream_t stream) {
+                    int64_t lddw, float* db, int accumulate, void* ws, cudaStream_t stream) {
   TcParams p{};
-  const int splits = tc_wgrad_splits(M, N, K);
-  p.A = dy; p.lda = ldy; p.B = x; p.ldb = ldx; p.M = N; p.N = K; p.K = M; p.splits = splits;
-  p.k_per_split = ceil_div(ceil_div(M, splits), BK) * BK;
+  const int splits0 = tc_wgrad_splits(M, N, K);
+  p.A = dy; p.lda = ldy; p.B = x; p.ldb = ldx; p.M = N; p.N = K; p.K = M; p.splits = splits0;
+  p.k_per_split = ceil_div(ceil_div(M, splits0), BK) * BK;
   p.terms = tc_terms(false);
   p.kc = tc_kc(false);
   // every split must own at least one k-stage
   while (p.splits > 1 && static_cast<int64_t>(p.splits - 1) * p.k_per_split >= M) --p.splits;
   const bool narrow = pick_bn(K) == 64;
+  float* db_part = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up(static_cast<size_t>(splits0) * N * K * sizeof(float)));
   if (p.splits == 1) {
     p.C = dw; p.ldc = lddw; p.accumulate = accumulate;
+    p.colsum = db; p.colsum_accumulate = accumulate;
     return narrow ? launch_tc<64, true, true, false>(p, stream) : launch_tc<128, true, true, false>(p, stream);
   }
   p.C = static_cast<float*>(ws); p.ldc = K;
+  p.colsum = db ? db_part : nullptr;
   int rc = narrow ? launch_tc<64, true, true, false>(p, stream) : launch_tc<128, true, true, false>(p, stream);
   if (rc != SGB_OK) return rc;
   const int64_t MN = N * K;
   tc_splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div(MN, 256)), 256, 0, stream>>>(static_cast<const float*>(ws), p.splits, MN, K,
                                                                                        dw, lddw, accumulate);
+  if (db) tc_colsum_reduce_kernel<<<static_cast<unsigned>(ceil_div(N, 128)), 128, 0, stream>>>(db_part, p.splits, N, db, accumulate);
   return check_launch("tc_splitk_reduce");
 }
 
