@@ -5,6 +5,7 @@
 // normalisation), :312 (Embedding), :320,325 (GELU), :331-332 (F.normalize).
 #include "sgb_api_internal.cuh"
 #include "sgb_sort.cuh"
+#include <algorithm>
 
 namespace sgb {
 namespace {
@@ -216,6 +217,39 @@ __global__ void posfreq_kernel(const float* __restrict__ pos, int64_t N, const I
   if ((dim & 1) && k == 0) row[dim - 1] = 0.f;
 }
 
+// Vectorised variant (half % 4 == 0, ldf % 4 == 0, 16-byte aligned feat): one thread per 4 consecutive
+// frequencies of one (axis, node) row -> two 128-bit stores; a warp covers whole rows, so the per-row loads
+// (tile id, min/max, coordinate) are warp-uniform broadcasts and the row index needs one 64-bit division
+// per thread on a power-of-two-friendly quotient instead of three.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+posfreq_vec_kernel(const float* __restrict__ pos, int64_t N, const IdxT* __restrict__ batch, int64_t n_batches,
+                   const int* __restrict__ mm, const float* __restrict__ freqs, int half, int q_per_row,
+                   float* __restrict__ feat, int64_t ldf) {
+  const int64_t total = 2 * N * q_per_row;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t node2 = i / q_per_row;            // d * N + node
+    const int k = static_cast<int>(i - node2 * q_per_row) * 4;
+    const int d = node2 >= N ? 1 : 0;
+    const int64_t node = node2 - (d ? N : 0);
+    int64_t b = batch ? static_cast<int64_t>(__ldg(batch + node)) : 0;
+    b = b < 0 ? 0 : (b >= n_batches ? n_batches - 1 : b);
+    const float mn = ord2f(__ldg(mm + b * 4 + d)), mx = ord2f(__ldg(mm + b * 4 + 2 + d));
+    const float v = __ldg(pos + 2 * node + d);
+    const float pn = batch ? (v - mn) / (mx - mn + 1e-8f) : (v - mn) / (mx - mn);
+    const float4 f = ldg4(freqs + k);
+    float4 sn, cs;
+    sincosf(pn * f.x, &sn.x, &cs.x);
+    sincosf(pn * f.y, &sn.y, &cs.y);
+    sincosf(pn * f.z, &sn.z, &cs.z);
+    sincosf(pn * f.w, &sn.w, &cs.w);
+    float* row = feat + node2 * ldf;
+    st4(row + k, cs);
+    st4(row + half + k, sn);
+  }
+}
+
 // ---- L2 normalise ----
 __global__ void __launch_bounds__(256)
 l2norm_fwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t M, int D, float eps, float* __restrict__ y,
@@ -357,7 +391,18 @@ extern "C" int sgb_posfreq_fwd(const float* pos, int64_t N, const void* batch, i
   const unsigned nb = static_cast<unsigned>(ceil_div(N, 256));
   const int64_t total = 2 * N * (dim / 2);
   const unsigned fb = static_cast<unsigned>(ceil_div(total, 256));
-  if (batch && idx_bytes == 8) {
+  const int half = dim / 2;
+  const bool vec = (dim % 2 == 0) && (half % 4 == 0) && (ldf % 4 == 0) && aligned16(feat) && aligned16(freqs);
+  const int qpr = half / 4;
+  const unsigned vb = static_cast<unsigned>(std::min<int64_t>(ceil_div(2 * N * (vec ? qpr : 1), 256), static_cast<int64_t>(sm_count()) * 64));
+  if (vec && batch && idx_bytes == 8) {
+    minmax_kernel<int64_t><<<nb, 256, 0, stream>>>(pos, N, static_cast<const int64_t*>(batch), n_batches, mm);
+    posfreq_vec_kernel<int64_t><<<vb, 256, 0, stream>>>(pos, N, static_cast<const int64_t*>(batch), n_batches, mm, freqs, half, qpr, feat, ldf);
+  } else if (vec) {
+    const int32_t* b32 = static_cast<const int32_t*>(batch);
+    minmax_kernel<int32_t><<<nb, 256, 0, stream>>>(pos, N, b32, n_batches, mm);
+    posfreq_vec_kernel<int32_t><<<vb, 256, 0, stream>>>(pos, N, b32, n_batches, mm, freqs, half, qpr, feat, ldf);
+  } else if (batch && idx_bytes == 8) {
     minmax_kernel<int64_t><<<nb, 256, 0, stream>>>(pos, N, static_cast<const int64_t*>(batch), n_batches, mm);
     posfreq_kernel<int64_t><<<fb, 256, 0, stream>>>(pos, N, static_cast<const int64_t*>(batch), n_batches, mm, freqs, dim, feat, ldf);
   } else {

@@ -259,3 +259,28 @@ def test_score_argmax_no_edges():
                                      torch.zeros(2, 0, dtype=torch.int32).cuda(), torch.arange(3).int().cuda())
     assert float(sim.abs().max()) == 0.0 and torch.equal(idx.cpu(), torch.zeros(10, dtype=torch.long))
     assert torch.equal(seg.cpu(), torch.full((10,), -1))
+
+
+# ---------------------------------------------------------------------------------------------- posfreq
+@pytest.mark.parametrize("dim,with_batch", [(256, True), (256, False), (64, True), (10, True), (7, False)])
+def test_posfreq_vs_oracle(dim, with_batch):
+    """sinusoid features of per-tile normalised coordinates (ist_encoder.py:22-31,57-79): the vectorised
+    kernel (half % 4 == 0) and the scalar fallback (odd / small dims) against the oracle's restatement."""
+    from oracle.ist_encoder_ref import sinusoidal_embedding
+    g = torch.Generator().manual_seed(dim)
+    N, nb = 3001, 4
+    pos = torch.rand(N, 2, generator=g) * 300.0
+    batch = torch.sort(torch.randint(0, nb, (N,), generator=g)).values if with_batch else None
+    if with_batch:
+        mins, maxs = torch.zeros(nb, 2), torch.zeros(nb, 2)
+        for b in range(nb):
+            mins[b], maxs[b] = pos[batch == b].min(0).values, pos[batch == b].max(0).values
+        pn = (pos - mins[batch]) / (maxs[batch] - mins[batch] + 1e-8)
+    else:
+        pn = pos - pos.min(0).values
+        pn = pn / pn.max(0).values
+    ref = sinusoidal_embedding(pn.flatten(), dim, max_period=10000).reshape(N, 2, dim).permute(1, 0, 2)
+    got = ops.posfreq(pos.cuda(), batch.cuda() if with_batch else None, nb if with_batch else 1, dim,
+                      ops.sinusoid_freqs(dim, 10000, "cuda"))
+    assert got.shape == (2, N, dim)
+    assert float((got.cpu() - ref).abs().max()) < 2e-6
