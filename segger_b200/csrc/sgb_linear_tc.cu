@@ -37,12 +37,15 @@ namespace {
 
 constexpr int BM = 128;            // UMMA M (cta_group::1)
 constexpr int BK = 32;             // fp32 per 128-byte swizzle row = reduction elements per stage
-constexpr int kProducerWarps = 4;
+constexpr int kProducerWarps = 4;   // warpgroup 0
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kMmaWarp = kProducerWarps;
-constexpr int kEpiWarp0 = kProducerWarps + 1;
+constexpr int kEpiWarp0 = kProducerWarps;      // warpgroups 1-2
 constexpr int kEpiWarps = 8;       // two per TMEM lane quarter, each owning half of the tile's columns
-constexpr int kThreads = (kProducerWarps + 1 + kEpiWarps) * 32;   // 416
+constexpr int kMmaWarp = kEpiWarp0 + kEpiWarps;   // warpgroup 3: MMA issuer, packed-weight loader, two idle warps
+constexpr int kBLoadWarp = kMmaWarp + 1;
+constexpr int kThreads = 16 * 32;  // 512: four whole warpgroups, so setmaxnreg can move registers between the roles
+// Register budget (64K per SM, 128 per thread at launch): warpgroup 3 gives up 72 per thread, the producers take them.
+constexpr int kRegsProducer = 200, kRegsControl = 56;
 constexpr int kMaxStages = 4;
 // epilogue transpose buffer: per warp 32 rows x (PW + 4) floats, PW = columns written out per pass
 constexpr int kPW = 16;            // 64-byte row segments per write-out pass: leaves shared memory for a third 64 KB stage
@@ -318,43 +321,46 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
   const int64_t tiles = num_m * num_n * p.splits;
   const int64_t num_ks = (p.K + BK - 1) / BK;      // k-stages of the whole reduction (packed-B block index)
 
-  if (warp < kProducerWarps) {
-    // ===================================== producers =====================================
-    // A stage slot is filled in place: cp.async lands the RAW fp32 slab in the slot's hi tiles as soon as the
-    // MMAs of the slot's previous use retire (S-1 slabs ahead of the split), the same threads later read their
-    // own chunks back, write hi over them and lo beside them.  The packed weights of the slot are one bulk copy
-    // issued at the same moment.
-    const int t = threadIdx.x;
-    struct Cur { int64_t tile, k0, ke; bool live; };
-    auto tile_range = [&](Cur& c) {
-      const int64_t sp = c.tile / (num_n * num_m);
-      c.k0 = sp * p.k_per_split;
-      c.ke = min(p.K, c.k0 + p.k_per_split);
-    };
-    auto init = [&](Cur& c) {
-      c.tile = blockIdx.x;
+  // tile / k-slab cursor shared by the producer, loader and (implicitly) MMA / epilogue loops: tiles are dealt
+  // round-robin to the persistent CTAs, a tile's reduction range is cut into BK-deep slabs
+  struct Cur { int64_t tile, k0, ke, mb, nb; bool live; };
+  auto tile_range = [&](Cur& c) {
+    const int64_t sp = c.tile / (num_n * num_m);
+    c.nb = c.tile % num_n;
+    c.mb = (c.tile / num_n) % num_m;
+    c.k0 = sp * p.k_per_split;
+    c.ke = min(p.K, c.k0 + p.k_per_split);
+  };
+  auto init = [&](Cur& c) {
+    c.tile = blockIdx.x;
+    c.live = c.tile < tiles;
+    if (c.live) tile_range(c);
+  };
+  auto advance = [&](Cur& c) {
+    c.k0 += BK;
+    if (c.k0 >= c.ke) {
+      c.tile += gridDim.x;
       c.live = c.tile < tiles;
       if (c.live) tile_range(c);
-    };
-    auto advance = [&](Cur& c) {
-      c.k0 += BK;
-      if (c.k0 >= c.ke) {
-        c.tile += gridDim.x;
-        c.live = c.tile < tiles;
-        if (c.live) tile_range(c);
-      }
-    };
+    }
+  };
+
+  if (warp < kProducerWarps) {
+    // ===================================== producers =====================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+    const int t = threadIdx.x;
+    // A stage slot is filled in place: cp.async lands the RAW fp32 slab(s) in the slot's hi tiles as soon as the
+    // MMAs of the slot's previous use retire (S-1 slabs ahead of the split), the same threads later read their
+    // own chunks back, write hi over them and lo beside them.  Packed weights (forward / dgrad) arrive through
+    // the loader warp instead.  (A register-staged variant -- global loads held in registers four slabs ahead,
+    // slots written the moment they free up -- measured no faster: these GEMMs are bound by shared-memory
+    // bandwidth, which the tensor core's own operand reads nearly saturate at N = 128; profiles/r1c_gemm_knockouts.txt.)
     int istage = 0, cstage = 0;
     uint32_t iphase = 0;
     auto issue = [&](const Cur& c) {
       const int64_t nb = c.tile % num_n, mb = (c.tile / num_n) % num_m;
       mbar_wait(smem_u32(&bar_empty[istage]), iphase ^ 1u);
       uint8_t* st = smem + static_cast<size_t>(istage) * kStageBytes;
-      if (B_PACKED && t == 0) {
-        const int64_t blk = nb * num_ks + c.k0 / BK;
-        mbar_arrive_expect_tx(smem_u32(&bar_full[istage]), 2 * kBTile);
-        bulk_g2s(smem_u32(st + 2 * kATile), p.Bp + static_cast<size_t>(blk) * (2 * BN * 32), 2 * kBTile, smem_u32(&bar_full[istage]));
-      }
       stage_raw<BM, A_MN>(p.A, p.lda, mb * BM, p.M, c.k0, c.ke, smem_u32(st), t);
       if constexpr (!B_PACKED) stage_raw<BN, B_MN>(p.B, p.ldb, nb * BN, p.N, c.k0, c.ke, smem_u32(st + 2 * kATile), t);
       if (++istage == S) { istage = 0; iphase ^= 1u; }
@@ -415,9 +421,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
       cp_async_commit();
     }
     cp_async_wait<0>();
-  } else if (warp == kMmaWarp) {
+  } else if (warp >= kMmaWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
+    if (B_PACKED && warp == kBLoadWarp && lane == 0) {
+      // ===================================== packed-weight loader =====================================
+      // one bulk copy (hi tile + lo tile of the slot's k-slab, pre-split by pack_b_kernel) per stage slot, issued
+      // the moment the tensor core frees the slot: S-1 slots ahead of the MMAs.
+      Cur b;
+      init(b);
+      int stage = 0;
+      uint32_t phase = 0;
+      while (b.live) {
+        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+        uint8_t* st = smem + static_cast<size_t>(stage) * kStageBytes;
+        const int64_t blk = b.nb * num_ks + b.k0 / BK;
+        mbar_arrive_expect_tx(smem_u32(&bar_full[stage]), 2 * kBTile);
+        bulk_g2s(smem_u32(st + 2 * kATile), p.Bp + static_cast<size_t>(blk) * (2 * BN * 32), 2 * kBTile, smem_u32(&bar_full[stage]));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        advance(b);
+      }
+    }
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    if (warp == kMmaWarp && lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
       // K-major: LBO unused (1 -> encoded 16 B), SBO = 1024 B between 8-row groups, +32 B per k-step.
       // MN-major: LBO = 512 B between 32-wide MN blocks, SBO = (EXT/32)*512 B between 4-deep k groups;
@@ -678,15 +703,17 @@ bool tc_enabled() {
 }
 
 // Number of TF32 products per fp32 product and K=8 steps accumulated inside the tensor core per chunk.
-//   exact (forward projections that an attention layer will be differentiated through): 4 terms, kc = 4
-//   fast  (gradients, inference): 3 terms, kc = 4
-// Measured on the encoder parity case (scripts/debug_param_err.py): with 32-deep chunks the worst parameter
-// gradient is within 1e-6 of the fp64 oracle for kc = 1, 2 and 4 alike (un-chunked TMEM accumulation: 5e-3).
-// SEGGER_B200_TF32_TERMS / SEGGER_B200_TC_KC / SEGGER_B200_TC_KC_EXACT override (debug / tuning).
+//   3 terms (hi*hi + lo*hi + hi*lo), kc = 4 for every GEMM.  The dropped lo*lo term is <= 2^-24 |a||b| per product
+//   (|lo| <= 2^-12 |x| after the round-to-nearest split), i.e. below the fp32 rounding of the product itself:
+//   measured on the encoder parity case (scripts/debug_param_err.py) the worst parameter gradient is 8.2e-7 from
+//   the fp64 oracle with 3 terms and 9.7e-7 with 4, outputs 3.5e-7 vs 2.9e-7 -- while the fourth MMA pass costs
+//   8-18 % of every forward GEMM (shared-memory operand reads are the binding resource).  What matters for the
+//   attention backward is the ROUNDING of the accumulation, which the 32-deep chunks fix (kc = 1, 2, 4 alike
+//   within 1e-6; un-chunked TMEM accumulation: 5e-3).
+// SEGGER_B200_TF32_TERMS=4 restores the fourth term for `exact` calls; SEGGER_B200_TC_KC / _KC_EXACT override kc.
 static int tc_terms(bool exact) {
-  static int env = env_int("SEGGER_B200_TF32_TERMS", 3, 4, 0);
-  if (env) return env;
-  return exact ? 4 : 3;
+  static int env = env_int("SEGGER_B200_TF32_TERMS", 3, 4, 3);
+  return (exact && env == 4) ? 4 : 3;
 }
 static int tc_kc(bool exact) {
   static int fast = env_int("SEGGER_B200_TC_KC", 1, 4, 4), ex = env_int("SEGGER_B200_TC_KC_EXACT", 1, 4, 4);

@@ -61,15 +61,18 @@ def test_tc_wgrad(M, N, K):
 
 
 def test_exact_flag_selects_round_to_nearest_fp32_path():
-    """exact=True must give the fp32 SIMT result (error ~1e-7), exact=False the tensor-core one."""
+    """exact=2 must give the fp32 SIMT result, exact=True/False the split-TF32 tensor-core one; both within
+    fp32 rounding of the fp64 product."""
     g = torch.Generator().manual_seed(5)
     x, w = torch.randn(4096, 256, generator=g), torch.randn(384, 256, generator=g)
     ref = x.double() @ w.double().t()
+    ys, _ = ops.linear_fwd(x.cuda(), w.cuda(), None, exact=2)
     ye, _ = ops.linear_fwd(x.cuda(), w.cuda(), None, exact=True)
     yt, _ = ops.linear_fwd(x.cuda(), w.cuda(), None, exact=False)
+    assert rel_err(ys, ref) < 1.5e-6
     assert rel_err(ye, ref) < 1.5e-6
-    assert rel_err(yt, ref) < TOL
-    assert not torch.equal(ye, yt)
+    assert rel_err(yt, ref) < 1.5e-6
+    assert not torch.equal(ys, yt)
 
 
 def test_tc_strided_operands_and_views():
