@@ -167,6 +167,13 @@ SGB_API size_t sgb_posfreq_workspace_bytes(int64_t n_batches);
 SGB_API int sgb_posfreq_fwd(const float* pos, int64_t N, const void* batch, int idx_bytes, int64_t n_batches,
                     int dim, const float* freqs, float* feat, int64_t ldf, void* ws, size_t ws_bytes,
                     void* stream);
+/* Same front end, low-rank form: out[2N, deg] (ld ldo) = Chebyshev basis T_0..T_{deg-1}(2p - 1) of the normalised
+ * coordinates p (x rows of all nodes, then y rows).  The 256 sinusoid columns of sgb_posfreq_fwd equal
+ * out @ M to fp32 rounding for a constant [deg, dim] matrix M (deg = 12 suffices: f_k <= 1, p in [0,1]), so the
+ * first Linear of the positional MLP (ist_encoder.py:43-47,76-79) contracts over deg instead of dim columns and
+ * the [2N, dim] feature matrix is never written.  deg % 4 == 0; workspace as sgb_posfreq_workspace_bytes. */
+SGB_API int sgb_poscheb_fwd(const float* pos, int64_t N, const void* batch, int idx_bytes, int64_t n_batches,
+                    int deg, float* out, int64_t ldo, void* ws, size_t ws_bytes, void* stream);
 /* F.normalize(x, dim=-1, eps=1e-12) forward / backward (ist_encoder.py:331-332). */
 SGB_API int sgb_l2norm_fwd(const float* x, int64_t ldx, int64_t M, int D, float eps, float* y, int64_t ldy,
                    float* norm /*[M]*/, void* stream);

@@ -250,6 +250,40 @@ posfreq_vec_kernel(const float* __restrict__ pos, int64_t N, const IdxT* __restr
   }
 }
 
+// Chebyshev basis of the normalised coordinates: out[d*N + node][n] = T_n(2p - 1), n < deg, p as in posfreq.
+// The sinusoid features cos(p f_k), sin(p f_k) (f_k <= 1, p in [0,1]) are entire functions of p whose Chebyshev
+// coefficients decay like (f_k/4)^n / n!, so a dozen basis columns reproduce all 256 feature columns to fp32
+// rounding: feat = T M with a constant [deg, 256] coefficient matrix M.  The first positional Linear and its
+// weight gradient then contract over deg instead of 256 columns, and the [2N, 256] feature matrix is never
+// materialised (ops.InputStageFn).  One thread per (axis, node) row; deg % 4 == 0 -> 128-bit stores.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+poscheb_kernel(const float* __restrict__ pos, int64_t N, const IdxT* __restrict__ batch, int64_t n_batches,
+               const int* __restrict__ mm, int deg, float* __restrict__ out, int64_t ldo) {
+  for (int64_t node2 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; node2 < 2 * N;
+       node2 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int d = node2 >= N ? 1 : 0;
+    const int64_t node = node2 - (d ? N : 0);
+    int64_t b = batch ? static_cast<int64_t>(__ldg(batch + node)) : 0;
+    b = b < 0 ? 0 : (b >= n_batches ? n_batches - 1 : b);
+    const float mn = ord2f(__ldg(mm + b * 4 + d)), mx = ord2f(__ldg(mm + b * 4 + 2 + d));
+    const float v = __ldg(pos + 2 * node + d);
+    const float pn = batch ? (v - mn) / (mx - mn + 1e-8f) : (v - mn) / (mx - mn);
+    const float t = 2.0f * pn - 1.0f, t2 = 2.0f * t;
+    float* row = out + node2 * ldo;
+    float a = 1.0f, bb = t;                      // T_n, T_{n+1}
+    for (int n = 0; n < deg; n += 4) {
+      float4 o;
+      o.x = a; o.y = bb;
+      const float c = fmaf(t2, bb, -a), e = fmaf(t2, c, -bb);
+      o.z = c; o.w = e;
+      st4(row + n, o);
+      a = fmaf(t2, e, -c);
+      bb = fmaf(t2, a, -e);
+    }
+  }
+}
+
 // ---- L2 normalise ----
 __global__ void __launch_bounds__(256)
 l2norm_fwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t M, int D, float eps, float* __restrict__ y,
@@ -411,6 +445,30 @@ extern "C" int sgb_posfreq_fwd(const float* pos, int64_t N, const void* batch, i
     posfreq_kernel<int32_t><<<fb, 256, 0, stream>>>(pos, N, b32, n_batches, mm, freqs, dim, feat, ldf);
   }
   return check_launch("posfreq_fwd");
+}
+
+extern "C" int sgb_poscheb_fwd(const float* pos, int64_t N, const void* batch, int idx_bytes, int64_t n_batches,
+                               int deg, float* out, int64_t ldo, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(N >= 0 && deg >= 4 && deg % 4 == 0 && n_batches >= 1, SGB_ERR_ARG, "poscheb_fwd: bad size (deg % 4 == 0)");
+  SGB_REQUIRE(!batch || idx_bytes == 4 || idx_bytes == 8, SGB_ERR_ARG, "poscheb_fwd: idx_bytes must be 4 or 8");
+  if (N == 0) return SGB_OK;
+  SGB_REQUIRE(pos && out && ws && ldo >= deg, SGB_ERR_ARG, "poscheb_fwd: null tensor");
+  SGB_REQUIRE(ldo % 4 == 0 && aligned16(out), SGB_ERR_ALIGN, "poscheb_fwd: out must be 16-byte aligned with ldo % 4 == 0");
+  SGB_REQUIRE(ws_bytes >= sgb_posfreq_workspace_bytes(n_batches), SGB_ERR_WORKSPACE, "poscheb_fwd: workspace too small");
+  int* mm = static_cast<int*>(ws);
+  minmax_init_kernel<<<static_cast<unsigned>(ceil_div(n_batches * 4, 256)), 256, 0, stream>>>(mm, n_batches);
+  const unsigned nb = static_cast<unsigned>(ceil_div(N, 256));
+  const unsigned cb = static_cast<unsigned>(std::min<int64_t>(ceil_div(2 * N, 256), static_cast<int64_t>(sm_count()) * 32));
+  if (batch && idx_bytes == 8) {
+    minmax_kernel<int64_t><<<nb, 256, 0, stream>>>(pos, N, static_cast<const int64_t*>(batch), n_batches, mm);
+    poscheb_kernel<int64_t><<<cb, 256, 0, stream>>>(pos, N, static_cast<const int64_t*>(batch), n_batches, mm, deg, out, ldo);
+  } else {
+    const int32_t* b32 = static_cast<const int32_t*>(batch);
+    minmax_kernel<int32_t><<<nb, 256, 0, stream>>>(pos, N, b32, n_batches, mm);
+    poscheb_kernel<int32_t><<<cb, 256, 0, stream>>>(pos, N, b32, n_batches, mm, deg, out, ldo);
+  }
+  return check_launch("poscheb_fwd");
 }
 
 extern "C" int sgb_l2norm_fwd(const float* x, int64_t ldx, int64_t M, int D, float eps, float* y, int64_t ldy,

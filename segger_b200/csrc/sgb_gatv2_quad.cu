@@ -292,8 +292,11 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
 // ================================================================================================
 // Backward, dst-CSR pass: grad_x_r, per-edge records (delta, alpha'), partial grad_att / grad_bias
 // ================================================================================================
-template <int V, int LPR, int H, int D>
-__global__ void __launch_bounds__(kQThreads) gatv2_bwd_dst_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
+// MINB = resident CTAs per SM the register allocation is sized for (the persistent grid is MINB x #SMs, so
+// that every CTA is resident from the start: a grid of 4 x #SMs with only 3 CTAs fitting runs a second,
+// two-thirds-empty wave).
+template <int V, int LPR, int H, int D, int MINB>
+__global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
   constexpr int G = 32 / LPR, VPH = V / H, F4 = V * LPR;
   constexpr int SH = (2 * H + 3) / 4 * 4;
   extern __shared__ float4 q_smem[];
@@ -451,13 +454,10 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_dst_quad_kernel(const Gat
         }
 #pragma unroll
         for (int t = 0; t < V; ++t) {
-          const float d = delta[t / VPH];
+          const float d = delta[t / VPH], ds = d * slope;     // delta * lrelu'(z): d where z > 0, d * slope elsewhere
           const float4 zz = z[t];
-          const float4 sel = make_float4(zz.x > 0.f ? 1.f : slope, zz.y > 0.f ? 1.f : slope,
-                                         zz.z > 0.f ? 1.f : slope, zz.w > 0.f ? 1.f : slope);
-          const float4 da = make_float4(d * a[t].x, d * a[t].y, d * a[t].z, d * a[t].w);
-          gr[t].x = fmaf(da.x, sel.x, gr[t].x); gr[t].y = fmaf(da.y, sel.y, gr[t].y);
-          gr[t].z = fmaf(da.z, sel.z, gr[t].z); gr[t].w = fmaf(da.w, sel.w, gr[t].w);
+          gr[t].x = fmaf(zz.x > 0.f ? d : ds, a[t].x, gr[t].x); gr[t].y = fmaf(zz.y > 0.f ? d : ds, a[t].y, gr[t].y);
+          gr[t].z = fmaf(zz.z > 0.f ? d : ds, a[t].z, gr[t].z); gr[t].w = fmaf(zz.w > 0.f ? d : ds, a[t].w, gr[t].w);
           fma4(gatt[t], d, zz);
         }
       }
@@ -712,10 +712,19 @@ bool quad_fwd_launch(const GatParams& p, cudaStream_t stream) {
   return false;
 }
 
+// resident CTAs per SM of the dst pass: 3 (no register cap) or 4 (128 registers, a few spilled scalars)
+static int quad_dst_minb() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEGGER_B200_GAT_DST_OCC");
+    v = (e && e[0] == '4') ? 4 : 3;
+  }
+  return v;
+}
 static int quad_dst_blocks(int64_t n_dst, int rpw) {
   const int64_t nchunks = ceil_div(n_dst > 0 ? n_dst : 1, rpw);
   const int64_t want = ceil_div(nchunks, kQW);
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * quad_dst_minb();
   return static_cast<int>(want < cap ? want : cap);
 }
 
@@ -737,9 +746,15 @@ bool quad_bwd_launch(const GatParams& p, float* grad_att, float* grad_bias, cuda
 #define X(V, L, Hh)                                                                                   \
   if (qs.v == V && qs.lpr == L && p.H == Hh) {                                                        \
     const size_t smem = static_cast<size_t>(kQW) * (kDDst + 1) * V * 512;                             \
-    auto kern = gatv2_bwd_dst_quad_kernel<V, L, Hh, kDDst>;                                           \
-    if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                      \
-    kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks);                                           \
+    if (quad_dst_minb() == 4) {                                                                       \
+      auto kern = gatv2_bwd_dst_quad_kernel<V, L, Hh, kDDst, 4>;                                      \
+      if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                    \
+      kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks);                                         \
+    } else {                                                                                          \
+      auto kern = gatv2_bwd_dst_quad_kernel<V, L, Hh, kDDst, 3>;                                      \
+      if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                    \
+      kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks);                                         \
+    }                                                                                                 \
   }
     SGB_QUAD_COMBOS(X)
 #undef X

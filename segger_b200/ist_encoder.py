@@ -54,6 +54,21 @@ class Positional2dEmbedder(Module):
             self._freqs[device] = f
         return f
 
+    def cheb_coef(self, device) -> Optional[Tensor]:
+        """[deg, freq] matrix M with sinusoid features = chebyshev basis @ M (None if the layout has a pad column)."""
+        if self.frequency_embedding_size % 2:
+            return None
+        key = ("cheb", device)
+        m = self._freqs.get(key)
+        if m is None:
+            m = ops.cheb_feature_matrix(self.freqs(device))
+            self._freqs[key] = m
+        return m
+
+    def basis(self, pos: Tensor, batch: Optional[Tensor]) -> Tensor:
+        """[2N, deg] Chebyshev basis of the normalised coordinates: the low-rank form of ``features``."""
+        return ops.poscheb(pos, batch, _num_batches(batch))
+
     def features(self, pos: Tensor, batch: Optional[Tensor]) -> Tensor:
         """[2, N, freq] sinusoid features of the normalised coordinates (no parameters involved)."""
         return ops.posfreq(pos, batch, _num_batches(batch), self.frequency_embedding_size, self.freqs(pos.device))
@@ -185,16 +200,18 @@ class ISTEncoder(torch.nn.Module):
 
     def _input_stage(self, k: str, x: Tensor, pos: Optional[Tensor], batch: Optional[Tensor]) -> Tensor:
         first = self.lin_first[k]
-        feat = w0 = b0 = w2 = b2 = None
+        feat = w0 = b0 = w2 = b2 = coef = None
         if self.use_positional_embeddings:
-            feat = self.pos_emb.features(pos, batch)
+            coef = self.pos_emb.cheb_coef(pos.device)
+            feat = self.pos_emb.basis(pos, batch) if coef is not None else self.pos_emb.features(pos, batch)
             w0, b0 = self.pos_emb.mlp[0].weight, self.pos_emb.mlp[0].bias
             w2, b2 = self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias
         if isinstance(first, Embedding):
-            return ops.InputStageFn.apply(x, first.weight, None, feat, w0, b0, w2, b2, True, torch.is_grad_enabled())
+            return ops.InputStageFn.apply(x, first.weight, None, feat, w0, b0, w2, b2, True, torch.is_grad_enabled(),
+                                          coef)
         first.materialize(x.size(-1), x)
         return ops.InputStageFn.apply(x, first.weight, first.bias, feat, w0, b0, w2, b2, False,
-                                      torch.is_grad_enabled())
+                                      torch.is_grad_enabled(), coef)
 
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict: Dict[str, Tensor], pos_dict: Dict[str, Tensor],
                 batch_dict: Dict[str, Tensor]) -> Dict[str, Tensor]:

@@ -463,6 +463,51 @@ def posfreq(pos: Tensor, batch: Optional[Tensor], n_batches: int, dim: int, freq
     return feat
 
 
+CHEB_DEG = 12   # basis columns of the low-rank positional front end (multiple of 4)
+
+
+def cheb_feature_matrix(freqs: Tensor, deg: int = CHEB_DEG) -> Tensor:
+    """Constant M [deg, 2*half] (fp32, on freqs' device) with  sinusoid(p) = T(2p-1) @ M  for p in [0,1]:
+    column k < half holds the Chebyshev coefficients of cos(f_k (t+1)/2), column half+k those of
+    sin(f_k (t+1)/2).  Computed in float64 by Chebyshev-Gauss quadrature; raises if the series is not
+    converged to 1e-9 at ``deg`` (cannot happen for the reference's table, f_k <= 1)."""
+    import numpy as np
+    f = freqs.detach().double().cpu().numpy()
+    m = 64
+    j = np.arange(m)
+    theta = np.pi * (j + 0.5) / m
+    t = np.cos(theta)                                        # nodes
+    arg = f[None, :] * (t[:, None] + 1.0) * 0.5              # [m, half]
+    g = np.concatenate([np.cos(arg), np.sin(arg)], axis=1)   # [m, 2*half]
+    n = np.arange(deg + 4)
+    basis = np.cos(n[:, None] * theta[None, :])              # [deg+4, m]
+    c = (2.0 / m) * basis @ g
+    c[0] *= 0.5
+    tail = float(np.abs(c[deg:]).max())
+    if not tail < 1e-9:
+        raise ValueError(f"Chebyshev series of the sinusoid features not converged at degree {deg} (tail {tail:.1e})")
+    return torch.from_numpy(c[:deg].astype(np.float32)).to(freqs.device)
+
+
+def poscheb(pos: Tensor, batch: Optional[Tensor], n_batches: int, deg: int = CHEB_DEG) -> Tensor:
+    """[2N, deg] Chebyshev basis T_n(2p-1) of the per-tile-normalised coordinates (x rows, then y rows)."""
+    require_cuda(pos, batch)
+    pos = pos.to(torch.float32).contiguous()
+    N = pos.size(0)
+    dev = pos.device
+    out = torch.empty(2 * N, deg, dtype=torch.float32, device=dev)
+    if batch is not None:
+        if batch.dtype not in (torch.int32, torch.int64):
+            batch = batch.long()
+        batch = batch.contiguous()
+    lib = _lib.load()
+    ws = _ws(lib.sgb_posfreq_workspace_bytes(n_batches), dev)
+    check(lib.sgb_poscheb_fwd(ptr(pos), N, ptr(batch), batch.element_size() if batch is not None else 0, n_batches,
+                              deg, ptr(out), deg, ptr(ws), ws.numel(), stream_ptr(dev)), "poscheb_fwd")
+    _count(3)
+    return out
+
+
 class InputStageFn(torch.autograd.Function):
     """Input stage of ISTEncoder.forward for one node type
     (/root/reference/src/segger/models/ist_encoder.py:312-320):
@@ -471,10 +516,15 @@ class InputStageFn(torch.autograd.Function):
 
     ``first`` is an Embedding gather (tx: integer gene ids) or a Linear (bd: float features).
     GELU is applied per column block straight into the concatenated buffer.
+
+    ``feat`` is either the [2, N, 256] sinusoid features (``coef`` None) or their low-rank form: the
+    [2N, deg] Chebyshev basis from ``poscheb`` with ``coef`` = ``cheb_feature_matrix`` ([deg, 256]),
+    sinusoid = feat @ coef.  In the low-rank form the first positional Linear runs as
+    feat @ (w0 coef^T)^T and its weight gradient as (dy^T feat) coef: both contract over deg columns.
     """
 
     @staticmethod
-    def forward(ctx, x, first_w, first_b, feat, w0, b0, w2, b2, is_embedding, exact):
+    def forward(ctx, x, first_w, first_b, feat, w0, b0, w2, b2, is_embedding, exact, coef=None):
         dev = first_w.device
         N = x.size(0)
         D = first_w.size(1) if is_embedding else first_w.size(0)
@@ -498,19 +548,22 @@ class InputStageFn(torch.autograd.Function):
         y0 = a0 = y2 = None
         if use_pos:
             f2 = feat.view(2 * N, feat.size(-1))
-            y0, a0 = linear_fwd(f2, w0, b0, ACT_SILU, exact=exact)         # [2N, dim] pre / SiLU
+            w_in = w0
+            if coef is not None:
+                w_in, _ = linear_fwd(w0, coef, None, exact=exact)         # [dim, deg] = w0 coef^T
+            y0, a0 = linear_fwd(f2, w_in, b0, ACT_SILU, exact=exact)       # [2N, dim] pre / SiLU
             y2 = torch.empty(2 * N, dim, dtype=torch.float32, device=dev)
             for d in range(2):                                            # x block, y block
                 linear_fwd(a0[d * N:(d + 1) * N], w2, b2, ACT_GELU, y=y2[d * N:(d + 1) * N],
                            y_act=h[:, D + d * dim: D + (d + 1) * dim], exact=exact)
         ctx.is_embedding, ctx.use_pos, ctx.D, ctx.dim, ctx.N = is_embedding, use_pos, D, dim, N
         ctx.has_first_b = first_b is not None
-        ctx.save_for_backward(saved_x, first_w, pre_first, feat, w0, y0, a0, w2, y2)
+        ctx.save_for_backward(saved_x, first_w, pre_first, feat, w0, y0, a0, w2, y2, coef)
         return h
 
     @staticmethod
     def backward(ctx, dh):
-        saved_x, first_w, pre_first, feat, w0, y0, a0, w2, y2 = ctx.saved_tensors
+        saved_x, first_w, pre_first, feat, w0, y0, a0, w2, y2, coef = ctx.saved_tensors
         N, D, dim = ctx.N, ctx.D, ctx.dim
         dev = dh.device
         dh = _rowmajor(dh)
@@ -536,7 +589,9 @@ class InputStageFn(torch.autograd.Function):
             dw2, db2 = linear_wgrad(dy2, a0)
             dy0 = linear_dgrad(dy2, w2, act=ACT_SILU, act_pre=y0)
             dw0, db0 = linear_wgrad(dy0, feat.view(2 * N, feat.size(-1)))
-        return None, d_first_w, d_first_b, None, dw0, db0, dw2, db2, None, None
+            if coef is not None:
+                dw0 = linear_dgrad(dw0, coef)                             # [dim, deg] @ [deg, 256]
+        return None, d_first_w, d_first_b, None, dw0, db0, dw2, db2, None, None, None
 
 
 class OutputStageFn(torch.autograd.Function):

@@ -16,6 +16,7 @@ SHAPES = [  # (M, N, K)
     (128, 64, 32), (128, 128, 32), (128, 192, 32), (128, 256, 32), (128, 256, 64),
     (300, 384, 256), (1000, 64, 128), (4096, 128, 256), (5000, 384, 128), (777, 100, 36), (129, 72, 40),
     (20000, 64, 256), (20000, 256, 384), (333, 512, 128), (64, 16, 8),
+    (50000, 64, 12), (64, 12, 256),      # low-rank positional front end: K = 12 basis columns / N = 12 reduction rows
 ]
 
 

@@ -284,3 +284,22 @@ def test_posfreq_vs_oracle(dim, with_batch):
                       ops.sinusoid_freqs(dim, 10000, "cuda"))
     assert got.shape == (2, N, dim)
     assert float((got.cpu() - ref).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("with_batch", [True, False])
+def test_poscheb_lowrank_reproduces_sinusoid_features(with_batch):
+    """Chebyshev basis @ constant coefficient matrix == the 256 sinusoid columns (ist_encoder.py:22-31) to fp32
+    rounding: the identity the fused input stage relies on to contract over 12 columns instead of 256."""
+    g = torch.Generator().manual_seed(11)
+    N, nb = 5003, 3
+    pos = torch.rand(N, 2, generator=g) * 1000.0
+    batch = torch.sort(torch.randint(0, nb, (N,), generator=g)).values if with_batch else None
+    freqs = ops.sinusoid_freqs(256, 10000, "cuda")
+    feat = ops.posfreq(pos.cuda(), batch.cuda() if with_batch else None, nb if with_batch else 1, 256, freqs)
+    T = ops.poscheb(pos.cuda(), batch.cuda() if with_batch else None, nb if with_batch else 1)
+    M = ops.cheb_feature_matrix(freqs)
+    assert T.shape == (2 * N, ops.CHEB_DEG) and M.shape == (ops.CHEB_DEG, 256)
+    low = (T.double() @ M.double()).view(2, N, 256)
+    assert float((low - feat.double()).abs().max()) < 2e-6
+    with pytest.raises(ValueError):
+        ops.cheb_feature_matrix(freqs * 40.0)          # frequencies far above 1: series not converged at deg 12
