@@ -369,6 +369,9 @@ def main():
             "l2": "inputs larger than L2 (per-layer activations 0.5-1.5 GB vs 126 MB L2); kernel-alone timings flush L2",
             "parallelism": f"dp{world} (one tile set per rank, one flat-gradient all-reduce of {flat.nbytes} B per step)",
             "timing": "CUDA events on the launching stream, barrier+synchronize on both sides, max over ranks",
+            "roofline": "`roofline` = the slowest fused message-passing launch group (HBM-bound; the kernels BASELINE.json's "
+                        "metric names); `roofline_kernels` adds the other one and the largest projection GEMM against the "
+                        "tensor pipe",
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
@@ -422,11 +425,37 @@ def kernel_rooflines(model, d, n_tx, n_cells, H, C, device, hbm_peak, peak_src):
         return {"kernel": name, "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
                 "traffic": traffic, "algorithmic_bytes": nbytes, "ms": t * 1e3, "peak_source": peak_src}
 
-    ents = [entry("gatv2_fwd_vec_kernel<1,16> (tx-neighbors-tx, fused logits+softmax+dropout+aggregate+bias+GELU)", fwd_b, t_fwd),
-            entry("gatv2_bwd (dst pass + src pass + partial reduce, tx-neighbors-tx)", bwd_b, t_bwd)]
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
+    # exactly these launches on this workload (profiles/r1c_ncu_full_summary.txt); null for other workloads.
+    cfg2 = (n_tx, n_cells, H, C) == (1_000_000, 10_000, 2, 64)
+    tr_fwd = 1.278294e9 + 1.000695e9 if cfg2 else None
+    tr_bwd = (2.379958e9 + 1.077137e9) + (2.470092e9 + 0.499027e9) if cfg2 else None
+    ents = [entry("gatv2_fwd_quad_kernel<4,8,2,4> (tx-neighbors-tx: fused logits + segment softmax + dropout + aggregate "
+                  "+ bias + GELU)", fwd_b, t_fwd, tr_fwd),
+            entry("gatv2_bwd_dst_quad_kernel<4,8,2,4,3> + gatv2_bwd_src_quad_kernel<4,8,2,3> + quad_colsum_kernel "
+                  "(tx-neighbors-tx backward)", bwd_b, t_bwd, tr_bwd)]
+
+    # the largest projection GEMM of the step (layer-1 tx projection, [N, 256] x [256, 3F]) on the tensor pipe:
+    # achieved = TF32 flops actually issued (3 split products per fp32 product) / time; peak = dense TF32 =
+    # half the measured bf16 cuBLAS rate of MEASURED_PEAKS.json (tcgen05 kind::tf32 runs at half the bf16 rate).
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tf32_peak, tsrc = float(json.load(f)["bf16_tflops"]) / 2, "measured bf16 / 2 (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        tf32_peak, tsrc = 2250.0 / 2, "nominal bf16 / 2"
+    xk = torch.randn(n_tx, 256, device=device)
+    wk = torch.randn(3 * F, 256, device=device) / 16
+    t_gemm = time_it(lambda: ops.linear_fwd(xk, wk, None, exact=1), reps=5)
+    fl = 2.0 * n_tx * 3 * F * 256
+    gemm = {"kernel": "gemm_tf32x3_kernel<128,0,0,1,3> (layer-1 tx projection, split-TF32 x3 on tcgen05, fp32-exact)",
+            "bound": "tensor", "achieved": 3 * fl / t_gemm / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+            "frac": 3 * fl / t_gemm / 1e12 / tf32_peak, "traffic": (1.026795e9 + 1.489735e9) if cfg2 else None,
+            "algorithmic_flops": fl, "issued_tf32_flops": 3 * fl, "fp32_equivalent_tflops": fl / t_gemm / 1e12,
+            "algorithmic_bytes": 4 * n_tx * (256 + 3 * F), "ms": t_gemm * 1e3, "peak_source": tsrc}
+    del xk, wk
     dom = max(ents, key=lambda e: e["ms"])
     return {"dominant": {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "ms",
-                                            "algorithmic_bytes", "peak_source")}, "all": ents}
+                                            "algorithmic_bytes", "peak_source")}, "all": ents + [gemm]}
 
 
 def segmentation_throughput(lit, host, ts, device, world, timed):

@@ -104,13 +104,13 @@ extern "C" int sgb_csr_build(const void* edge_index, int idx_bytes, int64_t row_
     csr_convert_kernel<int32_t><<<blocks, 256, 0, stream>>>(static_cast<const int32_t*>(edge_index), row_stride,
                                                             col_stride, E, n_src, n_dst, c.src32, c.dst32, status);
   int rc = sort_pairs(c.dst32, nullptr, c.skeys, reinterpret_cast<uint32_t*>(dst_eid), E, bits_for(n_dst), c.sort_ws,
-                      c.sort_bytes, stream);
+                      c.sort_bytes, stream, true);
   if (rc != SGB_OK) return rc;
   rc = rowptr_from_sorted(c.skeys, E, dst_rowptr, n_dst, stream);
   if (rc != SGB_OK) return rc;
   csr_gather_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(dst_eid), c.src32, dst_col, E);
   if (want_t) {
-    rc = sort_pairs(c.src32, nullptr, c.skeys, c.seid, E, bits_for(n_src), c.sort_ws, c.sort_bytes, stream);
+    rc = sort_pairs(c.src32, nullptr, c.skeys, c.seid, E, bits_for(n_src), c.sort_ws, c.sort_bytes, stream, true);
     if (rc != SGB_OK) return rc;
     rc = rowptr_from_sorted(c.skeys, E, src_rowptr, n_src, stream);
     if (rc != SGB_OK) return rc;

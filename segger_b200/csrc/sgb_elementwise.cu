@@ -39,6 +39,32 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, int64_t ldy, const 
   dx[r * lddx + c] = dy[r * ldy + c] * act_grad(x[r * ldx + c], act);
 }
 
+// 128-bit variants (N % 4 == 0, all leading dimensions % 4 == 0, 16-byte aligned bases); Q = N/4
+__global__ void __launch_bounds__(256)
+act_fwd_vec_kernel(const float* __restrict__ x, int64_t ldx, int64_t M, int Q, int act, float* __restrict__ y, int64_t ldy) {
+  const int64_t total = M * Q;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / Q;
+    const int c = static_cast<int>(i - r * Q) * 4;
+    const float4 v = ldg4(x + r * ldx + c);
+    st4(y + r * ldy + c, make_float4(act_apply(v.x, act), act_apply(v.y, act), act_apply(v.z, act), act_apply(v.w, act)));
+  }
+}
+__global__ void __launch_bounds__(256)
+act_bwd_vec_kernel(const float* __restrict__ dy, int64_t ldy, const float* __restrict__ x, int64_t ldx, int64_t M, int Q,
+                   int act, float* __restrict__ dx, int64_t lddx) {
+  const int64_t total = M * Q;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / Q;
+    const int c = static_cast<int>(i - r * Q) * 4;
+    const float4 g = ldg4(dy + r * ldy + c), v = ldg4(x + r * ldx + c);
+    st4(dx + r * lddx + c, make_float4(g.x * act_grad(v.x, act), g.y * act_grad(v.y, act), g.z * act_grad(v.z, act),
+                                       g.w * act_grad(v.w, act)));
+  }
+}
+
 template <typename IdxT>
 __global__ void embedding_fwd_kernel(const float* __restrict__ table, int64_t n_rows, int D, const IdxT* __restrict__ ids,
                                      int64_t N, float* __restrict__ out, int64_t ldo, float* __restrict__ out_act,
@@ -52,6 +78,25 @@ __global__ void embedding_fwd_kernel(const float* __restrict__ table, int64_t n_
   const float v = __ldg(table + g * D + c);
   if (out) out[r * ldo + c] = v;
   if (out_act) out_act[r * lda + c] = act_apply(v, act);
+}
+
+// D % 4 == 0, 16-byte aligned rows: one thread per 128-bit chunk of an output row (Q = D/4 chunks per row)
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+embedding_fwd_vec_kernel(const float* __restrict__ table, int64_t n_rows, int D, int Q, const IdxT* __restrict__ ids,
+                         int64_t N, float* __restrict__ out, int64_t ldo, float* __restrict__ out_act, int64_t lda, int act) {
+  const int64_t total = N * Q;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / Q;
+    const int c = static_cast<int>(i - r * Q) * 4;
+    int64_t g = static_cast<int64_t>(__ldg(ids + r));
+    g = g < 0 ? 0 : (g >= n_rows ? n_rows - 1 : g);
+    const float4 v = ldg4(table + g * D + c);
+    if (out) st4(out + r * ldo + c, v);
+    if (out_act)
+      st4(out_act + r * lda + c, make_float4(act_apply(v.x, act), act_apply(v.y, act), act_apply(v.z, act), act_apply(v.w, act)));
+  }
 }
 
 template <typename IdxT>
@@ -319,6 +364,50 @@ l2norm_bwd_kernel(const float* __restrict__ dy, int64_t ldy, const float* __rest
   }
 }
 
+// D = 4 * LPR (32, 64 or 128 columns): LPR lanes own a row, one 128-bit chunk each -> a warp covers 32/LPR rows
+template <int LPR>
+__global__ void __launch_bounds__(256)
+l2norm_fwd_vec_kernel(const float* __restrict__ x, int64_t ldx, int64_t M, float eps, float* __restrict__ y,
+                      int64_t ldy, float* __restrict__ norm) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, s = lane % LPR;
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r = w * RPW + lane / LPR;
+  const bool ok = r < M;
+  const float4 v = ok ? ldg4(x + r * ldx + s * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+  for (int o = LPR / 2; o >= 1; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
+  const float nrm = sqrtf(ss);
+  const float inv = 1.0f / fmaxf(nrm, eps);
+  if (ok) {
+    st4(y + r * ldy + s * 4, make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv));
+    if (s == 0 && norm) norm[r] = nrm;
+  }
+}
+template <int LPR>
+__global__ void __launch_bounds__(256)
+l2norm_bwd_vec_kernel(const float* __restrict__ dy, int64_t ldy, const float* __restrict__ y, int64_t ldyy,
+                      const float* __restrict__ norm, int64_t M, float eps, float* __restrict__ dx, int64_t lddx) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, s = lane % LPR;
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r = w * RPW + lane / LPR;
+  const bool ok = r < M;
+  const float4 g = ok ? ldg4(dy + r * ldy + s * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 e = ok ? ldg4(y + r * ldyy + s * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float nrm = ok ? __ldg(norm + r) : 1.f;
+  float dot = g.x * e.x + g.y * e.y + g.z * e.z + g.w * e.w;
+#pragma unroll
+  for (int o = LPR / 2; o >= 1; o >>= 1) dot += __shfl_xor_sync(kFull, dot, o);
+  const bool clamped = !(nrm > eps);
+  const float inv = 1.0f / fmaxf(nrm, eps);
+  if (ok)
+    st4(dx + r * lddx + s * 4, clamped ? make_float4(g.x * inv, g.y * inv, g.z * inv, g.w * inv)
+                                       : make_float4((g.x - e.x * dot) * inv, (g.y - e.y * dot) * inv,
+                                                     (g.z - e.z * dot) * inv, (g.w - e.w * dot) * inv));
+}
+
 }  // namespace
 }  // namespace sgb
 
@@ -328,6 +417,11 @@ extern "C" int sgb_act_fwd(const float* x, int64_t ldx, int64_t M, int64_t N, in
   SGB_REQUIRE(M >= 0 && N >= 0, SGB_ERR_ARG, "act_fwd: negative size");
   if (M * N == 0) return SGB_OK;
   SGB_REQUIRE(x && y && ldx >= N && ldy >= N, SGB_ERR_ARG, "act_fwd: bad argument");
+  if (N % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && aligned16(x) && aligned16(y)) {
+    const unsigned vb = static_cast<unsigned>(std::min<int64_t>(ceil_div(M * (N / 4), 256), static_cast<int64_t>(sm_count()) * 32));
+    act_fwd_vec_kernel<<<vb, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, M, static_cast<int>(N / 4), act, y, ldy);
+    return check_launch("act_fwd");
+  }
   act_fwd_kernel<<<static_cast<unsigned>(ceil_div(M * N, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, M, N, act, y, ldy);
   return check_launch("act_fwd");
 }
@@ -336,6 +430,11 @@ extern "C" int sgb_act_bwd(const float* dy, int64_t ldy, const float* x, int64_t
   SGB_REQUIRE(M >= 0 && N >= 0, SGB_ERR_ARG, "act_bwd: negative size");
   if (M * N == 0) return SGB_OK;
   SGB_REQUIRE(x && dy && dx && ldx >= N && ldy >= N && lddx >= N, SGB_ERR_ARG, "act_bwd: bad argument");
+  if (N % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && lddx % 4 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx)) {
+    const unsigned vb = static_cast<unsigned>(std::min<int64_t>(ceil_div(M * (N / 4), 256), static_cast<int64_t>(sm_count()) * 32));
+    act_bwd_vec_kernel<<<vb, 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, ldy, x, ldx, M, static_cast<int>(N / 4), act, dx, lddx);
+    return check_launch("act_bwd");
+  }
   act_bwd_kernel<<<static_cast<unsigned>(ceil_div(M * N, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, ldy, x, ldx, M, N, act, dx, lddx);
   return check_launch("act_bwd");
 }
@@ -347,6 +446,17 @@ extern "C" int sgb_embedding_fwd(const float* table, int64_t n_rows, int D, cons
   SGB_REQUIRE(N >= 0 && D >= 1 && n_rows >= 1, SGB_ERR_ARG, "embedding_fwd: bad size");
   if (N == 0) return SGB_OK;
   SGB_REQUIRE(table && ids && (out || out_act), SGB_ERR_ARG, "embedding_fwd: null tensor");
+  const bool vec = D % 4 == 0 && aligned16(table) && (!out || (aligned16(out) && ldo % 4 == 0)) &&
+                   (!out_act || (aligned16(out_act) && lda % 4 == 0));
+  if (vec) {
+    const int Q = D / 4;
+    const unsigned vb = static_cast<unsigned>(std::min<int64_t>(ceil_div(N * Q, 256), static_cast<int64_t>(sm_count()) * 32));
+    if (idx_bytes == 8)
+      embedding_fwd_vec_kernel<int64_t><<<vb, 256, 0, stream>>>(table, n_rows, D, Q, static_cast<const int64_t*>(ids), N, out, ldo, out_act, lda, act);
+    else
+      embedding_fwd_vec_kernel<int32_t><<<vb, 256, 0, stream>>>(table, n_rows, D, Q, static_cast<const int32_t*>(ids), N, out, ldo, out_act, lda, act);
+    return check_launch("embedding_fwd");
+  }
   const unsigned blocks = static_cast<unsigned>(ceil_div(N * D, 256));
   if (idx_bytes == 8)
     embedding_fwd_kernel<int64_t><<<blocks, 256, 0, stream>>>(table, n_rows, D, static_cast<const int64_t*>(ids), N, out, ldo, out_act, lda, act);
@@ -476,6 +586,15 @@ extern "C" int sgb_l2norm_fwd(const float* x, int64_t ldx, int64_t M, int D, flo
   SGB_REQUIRE(M >= 0 && D >= 1, SGB_ERR_ARG, "l2norm_fwd: bad size");
   if (M == 0) return SGB_OK;
   SGB_REQUIRE(x && y, SGB_ERR_ARG, "l2norm_fwd: null tensor");
+  if ((D == 32 || D == 64 || D == 128) && ldx % 4 == 0 && ldy % 4 == 0 && aligned16(x) && aligned16(y)) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rpw = 32 / (D / 4);
+    const unsigned vb = static_cast<unsigned>(ceil_div(ceil_div(M, rpw), 8));
+    if (D == 32) l2norm_fwd_vec_kernel<8><<<vb, 256, 0, st>>>(x, ldx, M, eps, y, ldy, norm);
+    else if (D == 64) l2norm_fwd_vec_kernel<16><<<vb, 256, 0, st>>>(x, ldx, M, eps, y, ldy, norm);
+    else l2norm_fwd_vec_kernel<32><<<vb, 256, 0, st>>>(x, ldx, M, eps, y, ldy, norm);
+    return check_launch("l2norm_fwd");
+  }
   l2norm_fwd_kernel<<<static_cast<unsigned>(ceil_div(M, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, M, D, eps, y, ldy, norm);
   return check_launch("l2norm_fwd");
 }
@@ -484,6 +603,16 @@ extern "C" int sgb_l2norm_bwd(const float* dy, int64_t ldy, const float* y, int6
   SGB_REQUIRE(M >= 0 && D >= 1, SGB_ERR_ARG, "l2norm_bwd: bad size");
   if (M == 0) return SGB_OK;
   SGB_REQUIRE(dy && y && norm && dx, SGB_ERR_ARG, "l2norm_bwd: null tensor");
+  if ((D == 32 || D == 64 || D == 128) && ldy % 4 == 0 && ldyy % 4 == 0 && lddx % 4 == 0 && aligned16(dy) && aligned16(y) &&
+      aligned16(dx)) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rpw = 32 / (D / 4);
+    const unsigned vb = static_cast<unsigned>(ceil_div(ceil_div(M, rpw), 8));
+    if (D == 32) l2norm_bwd_vec_kernel<8><<<vb, 256, 0, st>>>(dy, ldy, y, ldyy, norm, M, eps, dx, lddx);
+    else if (D == 64) l2norm_bwd_vec_kernel<16><<<vb, 256, 0, st>>>(dy, ldy, y, ldyy, norm, M, eps, dx, lddx);
+    else l2norm_bwd_vec_kernel<32><<<vb, 256, 0, st>>>(dy, ldy, y, ldyy, norm, M, eps, dx, lddx);
+    return check_launch("l2norm_bwd");
+  }
   l2norm_bwd_kernel<<<static_cast<unsigned>(ceil_div(M, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, ldy, y, ldyy, norm, M, D, eps, dx, lddx);
   return check_launch("l2norm_bwd");
 }

@@ -11,7 +11,8 @@ namespace {
 
 __global__ void __launch_bounds__(kRsThreads)
 rs_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int32_t* __restrict__ hist,
-               int nblk) {
+               int nblk, const int32_t* __restrict__ skip) {
+  if (skip && *skip) return;   // keys already sorted: presorted_copy_kernel produces the output
   __shared__ int cnt[kRadix];
   cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -28,7 +29,8 @@ rs_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int32_t*
 __global__ void __launch_bounds__(kRsThreads)
 rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
-                  int shift, const int32_t* __restrict__ offs, int nblk) {
+                  int shift, const int32_t* __restrict__ offs, int nblk, const int32_t* __restrict__ skip) {
+  if (skip && *skip) return;
   constexpr int kWarps = kRsThreads / 32;
   constexpr int kPerWarp = kRsTile / kWarps;  // 512 consecutive keys per warp
   __shared__ int cnt[kWarps][kRadix];
@@ -179,6 +181,23 @@ __global__ void rowptr_kernel(const uint32_t* __restrict__ keys, int64_t n, int3
   rowptr[r] = static_cast<int32_t>(lo);
 }
 
+// flag[0] starts at 1 and is cleared by any adjacent pair out of order (under the key mask)
+__global__ void sorted_flag_init_kernel(int32_t* flag) { *flag = 1; }
+__global__ void sorted_check_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t mask, int32_t* __restrict__ flag) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i + 1 < n && (keys[i] & mask) > (keys[i + 1] & mask)) *flag = 0;
+}
+__global__ void presorted_copy_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
+                                      const int32_t* __restrict__ flag) {
+  if (!*flag) return;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys_out[i] = keys_in[i];
+    vals_out[i] = vals_in ? vals_in[i] : static_cast<uint32_t>(i);
+  }
+}
+
 }  // namespace
 
 size_t scan_workspace_bytes(int64_t n) {
@@ -208,12 +227,12 @@ size_t sort_pairs_workspace_bytes(int64_t n) {
   const int64_t nh = nblk * kRadix;
   return 2 * align_up(static_cast<size_t>(nn) * 4)        // tmp keys, tmp vals
          + 2 * align_up(static_cast<size_t>(nh + 1) * 4)  // histogram + scanned offsets
-         + scan_workspace_bytes(nh);
+         + scan_workspace_bytes(nh) + 256;                 // + presorted flag
 }
 
 int sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
                uint32_t* vals_out, int64_t n, int key_bits, void* ws, size_t ws_bytes,
-               cudaStream_t stream) {
+               cudaStream_t stream, bool detect_presorted) {
   SGB_REQUIRE(n >= 0 && n < (int64_t(1) << 31), SGB_ERR_RANGE, "sort_pairs: n=%lld out of range", (long long)n);
   SGB_REQUIRE(keys_out && vals_out && ws, SGB_ERR_ARG, "sort_pairs: null argument");
   SGB_REQUIRE(keys_in != keys_out, SGB_ERR_ARG, "sort_pairs: in-place sort is not supported");
@@ -233,6 +252,17 @@ int sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_
   int32_t* offs = reinterpret_cast<int32_t*>(p); p += align_up(static_cast<size_t>(nh + 1) * 4);
   void* scan_ws = p;
   const size_t scan_bytes = scan_workspace_bytes(nh);
+  p += scan_bytes;
+  // Presorted inputs (the src-major edge lists kNN and setup_heterodata emit): one check pass sets a device flag,
+  // the histogram / scatter passes return at once and a single copy produces the (identical) stable result.
+  int32_t* flag = nullptr;
+  const bool detect = detect_presorted && keys_in != keys_out && vals_in != vals_out;
+  if (detect) {
+    flag = reinterpret_cast<int32_t*>(p);
+    const uint32_t mask = key_bits >= 32 ? 0xFFFFFFFFu : ((1u << key_bits) - 1u);
+    sorted_flag_init_kernel<<<1, 1, 0, stream>>>(flag);
+    sorted_check_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, stream>>>(keys_in, n, mask, flag);
+  }
 
   const uint32_t* sk = keys_in;
   const uint32_t* sv = vals_in;
@@ -240,13 +270,15 @@ int sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_
     const bool to_out = ((passes - 1 - ps) % 2) == 0;
     uint32_t* dk = to_out ? keys_out : tk;
     uint32_t* dv = to_out ? vals_out : tv;
-    rs_hist_kernel<<<nblk, kRsThreads, 0, stream>>>(sk, n, ps * 8, hist, nblk);
+    rs_hist_kernel<<<nblk, kRsThreads, 0, stream>>>(sk, n, ps * 8, hist, nblk, flag);
     int rc = exclusive_scan_i32(hist, offs, nh, scan_ws, scan_bytes, stream);
     if (rc != SGB_OK) return rc;
-    rs_scatter_kernel<<<nblk, kRsThreads, 0, stream>>>(sk, sv, dk, dv, n, ps * 8, offs, nblk);
+    rs_scatter_kernel<<<nblk, kRsThreads, 0, stream>>>(sk, sv, dk, dv, n, ps * 8, offs, nblk, flag);
     sk = dk;
     sv = dv;
   }
+  if (detect)
+    presorted_copy_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, n, flag);
   return check_launch("sort_pairs");
 }
 

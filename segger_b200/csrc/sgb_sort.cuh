@@ -15,9 +15,11 @@ size_t sort_pairs_workspace_bytes(int64_t n);
 // Sorts n pairs by the low `key_bits` bits of the key, stable.  keys_in/vals_in are preserved
 // unless they alias the outputs.  Result lands in keys_out/vals_out.
 // vals_in == nullptr means "values are 0..n-1".
+// detect_presorted: check on the device whether the keys are already non-decreasing; if so the radix passes
+// return immediately and one copy writes the result (bit-identical to what the stable sort would produce).
 int sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
                uint32_t* vals_out, int64_t n, int key_bits, void* ws, size_t ws_bytes,
-               cudaStream_t stream);
+               cudaStream_t stream, bool detect_presorted = false);
 
 // out[i] = sum_{j<i} in[j] for i in [0, n]; out has n+1 entries (out[n] = total).  in may alias out+0..n-1? no.
 size_t scan_workspace_bytes(int64_t n);

@@ -39,6 +39,26 @@ def test_csr_build_bit_exact(E, n_src, n_dst, dtype):
     assert int(csr.status.item()) == 0
 
 
+@pytest.mark.parametrize("sorted_row", [0, 1])
+def test_csr_build_presorted_inputs_take_the_copy_path(sorted_row):
+    """kNN / setup_heterodata emit src-major edge lists: the sort detects non-decreasing keys on the device and
+    copies instead of sorting; the result must equal the stable sort's."""
+    ei = random_graph(3000, 2500, 40000, seed=9)
+    order = torch.argsort(ei[sorted_row], stable=True)
+    ei = ei[:, order].contiguous()
+    csr = ops.build_csr(ei.cuda(), 3000, 2500, transpose=True)
+    src, dst = ei[0], ei[1]
+    o = torch.argsort(dst, stable=True)
+    assert torch.equal(csr.eid.cpu().long(), o) and torch.equal(csr.col.cpu().long(), src[o])
+    to = torch.argsort(src, stable=True)
+    inv = torch.empty(ei.size(1), dtype=torch.long)
+    inv[o] = torch.arange(ei.size(1))
+    assert torch.equal(csr.t_dst.cpu().long(), dst[to]) and torch.equal(csr.t_pos.cpu().long(), inv[to])
+    rp = torch.zeros(2501, dtype=torch.long); rp[1:] = torch.bincount(dst, minlength=2500).cumsum(0)
+    trp = torch.zeros(3001, dtype=torch.long); trp[1:] = torch.bincount(src, minlength=3000).cumsum(0)
+    assert torch.equal(csr.rowptr.cpu().long(), rp) and torch.equal(csr.t_rowptr.cpu().long(), trp)
+
+
 def test_csr_strided_view_and_range_flag():
     ei = random_graph(50, 60, 400, seed=3)
     eit = ei.t().contiguous().cuda().t()          # [2,E] view with strides (1, 2)
@@ -303,3 +323,62 @@ def test_poscheb_lowrank_reproduces_sinusoid_features(with_batch):
     assert float((low - feat.double()).abs().max()) < 2e-6
     with pytest.raises(ValueError):
         ops.cheb_feature_matrix(freqs * 40.0)          # frequencies far above 1: series not converged at deg 12
+
+
+@pytest.mark.parametrize("D,dtype", [(128, torch.int32), (16, torch.int64), (6, torch.int32)])
+def test_embedding_gather_gelu_vs_torch(D, dtype):
+    """Input stage of the transcript branch without positional features: GELU(Embedding(ids))
+    (ist_encoder.py:312-320); vectorised kernel for D % 4 == 0, scalar fallback otherwise; backward =
+    deterministic segment sum of the incoming gradient times GELU'."""
+    g = torch.Generator().manual_seed(D)
+    n_rows, N = 37, 4001
+    table = torch.randn(n_rows, D, generator=g, dtype=torch.float64).float().requires_grad_()
+    ids = torch.randint(0, n_rows, (N,), generator=g).to(dtype)
+    ref = torch.nn.functional.gelu(table.double()[ids.long()])
+    go = torch.randn(N, D, generator=g)
+    ref.backward(go.double())
+    t_cuda = table.detach().cuda().requires_grad_()
+    h = ops.InputStageFn.apply(ids.cuda(), t_cuda, None, None, None, None, None, None, True, True)
+    assert rel_err(h, ref) < 1e-6
+    h.backward(go.cuda())
+    assert rel_err(t_cuda.grad, table.grad) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,sliced", [(1000, 64, False), (999, 7, False), (500, 64, True)])
+@pytest.mark.parametrize("act", [ACT_GELU, ACT_SILU])
+def test_act_fwd_bwd_vs_torch(M, N, sliced, act):
+    """erf-GELU / SiLU (ist_encoder.py:46,320,325) forward and derivative: 128-bit kernel for aligned
+    shapes (also on column slices of a wider buffer), scalar fallback otherwise."""
+    g = torch.Generator().manual_seed(M + N)
+    big = torch.randn(M, 3 * N if sliced else N, generator=g) * 2
+    x = big[:, N:2 * N] if sliced else big
+    dy = torch.randn(M, N, generator=g)
+    xd = x.double().requires_grad_()
+    f = torch.nn.functional.gelu if act == ACT_GELU else torch.nn.functional.silu
+    ref = f(xd)
+    ref.backward(dy.double())
+    xc = big.cuda()[:, N:2 * N] if sliced else big.cuda()
+    assert rel_err(ops.act_fwd(xc, act), ref) < 1e-6
+    assert rel_err(ops.act_bwd(dy.cuda(), xc, act), xd.grad) < 1e-5
+
+
+@pytest.mark.parametrize("D", [64, 32, 128, 20])
+def test_output_stage_linear_normalize_vs_torch(D):
+    """lin_last + F.normalize(dim=-1, eps=1e-12) (ist_encoder.py:328-332), forward and backward, with an
+    all-zero row (norm clamped at eps); sub-warp 128-bit kernels for D in {32, 64, 128}, scalar otherwise."""
+    g = torch.Generator().manual_seed(D)
+    M, K = 777, 48
+    h = torch.randn(M, K, generator=g)
+    h[5] = 0.0
+    w, b = torch.randn(D, K, generator=g) / 7, torch.zeros(D)
+    go = torch.randn(M, D, generator=g)
+    go[5] = 0.0          # the clamped row's gradient is g / eps = 1e12 * g: keep it out of the max-norm comparison
+    hd, wd, bd = h.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
+    ref = torch.nn.functional.normalize(hd @ wd.t() + bd, dim=-1)
+    ref.backward(go.double())
+    hc, wc, bc = h.cuda().requires_grad_(), w.cuda().requires_grad_(), b.cuda().requires_grad_()
+    out = ops.OutputStageFn.apply(hc, wc, bc, True)
+    assert rel_err(out, ref) < 1e-5
+    assert float(out[5].abs().max()) == 0.0
+    out.backward(go.cuda())
+    assert rel_err(hc.grad, hd.grad) < 1e-4 and rel_err(wc.grad, wd.grad) < 1e-4
