@@ -1,6 +1,7 @@
 // C ABI of the dense projections: argument validation + back-end selection.
 #include "sgb_api_internal.cuh"
 #include "sgb_linear.cuh"
+#include <algorithm>
 
 using namespace sgb;
 
@@ -28,6 +29,8 @@ extern "C" int sgb_linear_fwd(const float* x, int64_t ldx, const float* w, int64
   SGB_REQUIRE(ldx >= K && ldw >= K && ldy >= N && (!y_act || ldya >= N), SGB_ERR_ARG, "linear_fwd: leading dimension too small");
   SGB_REQUIRE(act >= SGB_ACT_NONE && act <= SGB_ACT_SILU, SGB_ERR_ARG, "linear_fwd: unknown activation %d", act);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (skinny_linear_fwd_ok(x, ldx, M, N, K, y, ldy, y_act, ldya))   // K <= 16: HBM streaming on the fp32 pipe
+    return skinny_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, act, y_act, ldya, st);
   if (exact != 2 && tc_linear_fwd_ok(x, ldx, w, ldw, M, N, K)) {
     SGB_REQUIRE(ws && ws_bytes >= tc_linear_workspace_bytes(N, K), SGB_ERR_WORKSPACE, "linear_fwd: workspace too small");
     return tc_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, act, y_act, ldya, exact, ws, st);
@@ -54,7 +57,8 @@ extern "C" int sgb_linear_dgrad(const float* dy, int64_t ldy, const float* w, in
 static size_t wgrad_gemm_ws(int64_t M, int64_t N, int64_t K) {
   const size_t a = simt_linear_wgrad_workspace_bytes(M, N, K);
   const size_t b = tc_enabled() ? tc_linear_wgrad_workspace_bytes(M, N, K) : 0;
-  return a > b ? a : b;
+  const size_t c = (K >= 4 && K <= 16 && N <= 256) ? skinny_linear_wgrad_workspace_bytes(M, N, K) : 0;
+  return std::max(a, std::max(b, c));
 }
 
 extern "C" size_t sgb_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
@@ -72,6 +76,8 @@ extern "C" int sgb_linear_wgrad(const float* dy, int64_t ldy, const float* x, in
   SGB_REQUIRE(ws && ws_bytes >= sgb_linear_wgrad_workspace_bytes(M, N, K), SGB_ERR_WORKSPACE, "linear_wgrad: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (K > 0) {
+    if (skinny_linear_wgrad_ok(dy, ldy, x, ldx, M, N, K))   // K <= 16: dw and db in one streaming pass
+      return skinny_linear_wgrad(dy, ldy, x, ldx, M, N, K, dw, lddw, db, accumulate, ws, st);
     if (tc_linear_wgrad_ok(dy, ldy, x, ldx, M, N, K))   // the tensor-core kernel also produces db (fused column sums)
       return tc_linear_wgrad(dy, ldy, x, ldx, M, N, K, dw, lddw, db, accumulate, ws, st);
     rc = simt_linear_wgrad(dy, ldy, x, ldx, M, N, K, dw, lddw, accumulate, ws, st);

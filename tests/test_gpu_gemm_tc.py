@@ -86,3 +86,21 @@ def test_tc_strided_operands_and_views():
     out = torch.zeros(3000, 256, device="cuda")
     ops.linear_fwd(x, w, None, y=out[:, 64:128], exact=False)
     assert rel_err(out[:, 64:128], y) == 0 and float(out[:, :64].abs().max()) == 0 and float(out[:, 128:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(50000, 64, 12), (8191, 100, 16), (4096, 256, 4), (20001, 32, 8)])
+def test_skinny_k_forward_and_wgrad(M, N, K):
+    """Reduction depth K <= 16 (the low-rank positional front end): streaming fp32 kernels, forward with fused
+    SiLU and weight + bias gradient in one deterministic pass."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    ref = x.double() @ w.double().t() + b.double()
+    y, a = ops.linear_fwd(x.cuda(), w.cuda(), b.cuda(), ACT_SILU)
+    assert rel_err(y, ref) < 2e-6
+    assert rel_err(a, torch.nn.functional.silu(ref)) < 2e-6
+    dy = torch.randn(M, N, generator=g)
+    dw, db = ops.linear_wgrad(dy.cuda(), x.cuda())
+    assert rel_err(dw, dy.double().t() @ x.double()) < 1e-5
+    assert rel_err(db, dy.double().sum(0)) < 1e-5
+    dw2, db2 = ops.linear_wgrad(dy.cuda(), x.cuda())
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
