@@ -187,7 +187,7 @@ def cpu_reference_step_factory(workload: str, seed: int = 0):
         loss = (out["tx"] * t_tx).sum() / 50_000 + (out["bd"] * t_bd).sum() / 500
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     sample = (f"one 50k-transcript / 500-cell tile of the workload's model (k={k}, {n_layers} layers, "
               f"hidden={hid}, heads={heads}), fwd+bwd+Adam, plain-torch CPU restatement of the PyG path "
@@ -254,6 +254,8 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set: keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     W = max(3, args.warmup)
     K = max(1, args.steps)
