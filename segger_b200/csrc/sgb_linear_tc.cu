@@ -633,9 +633,8 @@ __global__ void tc_colsum_reduce_kernel(const float* __restrict__ part, int spli
 template <int BN>
 constexpr size_t stage_bytes() { return static_cast<size_t>(2 * BM * 128 + 2 * BN * 128); }
 
-template <int BN, bool A_MN, bool B_MN, bool B_PACKED>
-int launch_tc(TcParams p, cudaStream_t stream) {
-  constexpr int S = (BN == 128) ? 3 : 4;            // 3 x 64 KB or 4 x 48 KB stage slots
+template <int BN, bool A_MN, bool B_MN, bool B_PACKED, int S>
+int launch_tc_s(TcParams p, cudaStream_t stream) {
   constexpr size_t kStgBytes = stg_bytes(kPW);
   static_assert(S <= kMaxStages, "stage count");
   p.stages = S;
@@ -654,6 +653,14 @@ int launch_tc(TcParams p, cudaStream_t stream) {
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   gemm_tf32x3_kernel<BN, A_MN, B_MN, B_PACKED, S><<<grid, kThreads, smem, stream>>>(p);
   return check_launch("gemm_tf32x3");
+}
+
+template <int BN, bool A_MN, bool B_MN, bool B_PACKED>
+int launch_tc(TcParams p, cudaStream_t stream) {
+  // 3 x 64 KB or 4 x 48 KB stage slots: all the shared memory there is.  One slot fewer costs 17-24 % on the
+  // BN = 128 kernels and on wgrad, nothing on the packed BN = 64 kernels (profiles/r1d_gemm_stage_depth.txt).
+  constexpr int S = (BN == 128) ? 3 : 4;
+  return launch_tc_s<BN, A_MN, B_MN, B_PACKED, S>(p, stream);
 }
 
 int pick_bn(int64_t N) { return N <= 64 ? 64 : 128; }
