@@ -128,6 +128,90 @@ skinny_wgrad_kernel(const float* __restrict__ dy, int64_t ldy, const float* __re
   }
 }
 
+// 128-bit variant (N % 4 == 0, N <= 128, dy 16-byte aligned with ldy % 4 == 0): thread (rg, q) owns the four
+// columns 4q..4q+3 -> one 128-bit dy load per row instead of four 32-bit ones, 4K accumulators in registers.
+// The N/4 threads of a row group sit in one warp together with 32/(N/4) - 1 other row groups: those are folded with
+// shuffles (fixed order), the per-warp sums go through shared memory.  Same partial layout as the scalar kernel.
+template <int K4>
+__global__ void __launch_bounds__(256)
+skinny_wgrad_vec_kernel(const float* __restrict__ dy, int64_t ldy, const float* __restrict__ x, int64_t ldx, int64_t M, int N,
+                        int64_t rows_per_block, float* __restrict__ partial) {
+  constexpr int K = 4 * K4, KP = K + 1;
+  extern __shared__ float red[];                 // [8 warps][N][KP]
+  const int Q = N / 4;                           // threads per row: 1, 2, 4, 8, 16 or 32 (N = 4 .. 128, power of two)
+  const int RG = blockDim.x / Q;
+  const int q = threadIdx.x % Q, rg = threadIdx.x / Q;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  const int64_t r1 = min(M, r0 + rows_per_block);
+  float acc[4][K];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[j][k] = 0.f;
+  constexpr int U = 2;
+  int64_t r = r0 + rg;
+  auto accumulate = [&](const float4 a, const float4 (&xv)[K4]) {
+    const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bsum[j] += av[j];
+#pragma unroll
+      for (int k4 = 0; k4 < K4; ++k4) {
+        acc[j][4 * k4 + 0] = fmaf(av[j], xv[k4].x, acc[j][4 * k4 + 0]);
+        acc[j][4 * k4 + 1] = fmaf(av[j], xv[k4].y, acc[j][4 * k4 + 1]);
+        acc[j][4 * k4 + 2] = fmaf(av[j], xv[k4].z, acc[j][4 * k4 + 2]);
+        acc[j][4 * k4 + 3] = fmaf(av[j], xv[k4].w, acc[j][4 * k4 + 3]);
+      }
+    }
+  };
+  for (; r + static_cast<int64_t>(U - 1) * RG < r1; r += static_cast<int64_t>(U) * RG) {
+    float4 a[U], xv[U][K4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + static_cast<int64_t>(u) * RG;
+      a[u] = ldg4(dy + rr * ldy + 4 * q);
+#pragma unroll
+      for (int k4 = 0; k4 < K4; ++k4) xv[u][k4] = ldg4(x + rr * ldx + 4 * k4);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) accumulate(a[u], xv[u]);
+  }
+  for (; r < r1; r += RG) {
+    float4 xv[K4];
+    const float4 a = ldg4(dy + r * ldy + 4 * q);
+#pragma unroll
+    for (int k4 = 0; k4 < K4; ++k4) xv[k4] = ldg4(x + r * ldx + 4 * k4);
+    accumulate(a, xv);
+  }
+  // fold the row groups that share a warp (lanes q, q + Q, q + 2Q, ...): xor butterfly over the group bits
+  for (int o = Q; o < 32; o <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bsum[j] += __shfl_xor_sync(kFull, bsum[j], o);
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[j][k] += __shfl_xor_sync(kFull, acc[j][k], o);
+    }
+  }
+  if (lane < Q) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float* mine = red + (static_cast<size_t>(warp) * N + 4 * lane + j) * KP;
+#pragma unroll
+      for (int k = 0; k < K; ++k) mine[k] = acc[j][k];
+      mine[K] = bsum[j];
+    }
+  }
+  __syncthreads();
+  const int nw = blockDim.x / 32;
+  for (int i = threadIdx.x; i < N * KP; i += blockDim.x) {
+    float s_ = red[i];
+    for (int w = 1; w < nw; ++w) s_ += red[static_cast<size_t>(w) * N * KP + i];   // fixed order
+    partial[static_cast<int64_t>(blockIdx.x) * N * KP + i] = s_;
+  }
+}
+
 // dw[c, k] (+)= sum_blk partial[blk][c][k];  db[c] (+)= sum_blk partial[blk][c][K]   (fixed order)
 __global__ void skinny_wgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int N, int K, float* __restrict__ dw,
                                            int64_t lddw, float* __restrict__ db, int accumulate) {
@@ -189,17 +273,36 @@ int skinny_linear_wgrad(const float* dy, int64_t ldy, const float* x, int64_t ld
   const int nblk = wgrad_blocks(M);
   const int64_t rpb = ceil_div(M, nblk);
   const int n = static_cast<int>(N), k = static_cast<int>(K);
-  const int RG = 256 / n;
-  const size_t smem = static_cast<size_t>(RG) * n * (k + 1) * sizeof(float);
   float* partial = static_cast<float*>(ws);
+  const bool pow2 = (n & (n - 1)) == 0;
+  if (pow2 && n >= 4 && n <= 128 && aligned16(dy) && ldy % 4 == 0) {
+    const size_t smem = static_cast<size_t>(8) * n * (k + 1) * sizeof(float);      // <= 8 * 128 * 17 * 4 = 68 KB
+#define SK_WGV(K4)                                                                                                   \
+  do {                                                                                                               \
+    auto kern = skinny_wgrad_vec_kernel<K4>;                                                                         \
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024) != cudaSuccess) \
+      return set_error(SGB_ERR_CUDA, "skinny wgrad: cudaFuncSetAttribute failed");                                  \
+    kern<<<nblk, 256, smem, stream>>>(dy, ldy, x, ldx, M, n, rpb, partial);                                          \
+  } while (0)
+    switch (K / 4) {
+      case 1: SK_WGV(1); break;
+      case 2: SK_WGV(2); break;
+      case 3: SK_WGV(3); break;
+      default: SK_WGV(4); break;
+    }
+#undef SK_WGV
+  } else {
+    const int RG = 256 / n;
+    const size_t smem = static_cast<size_t>(RG) * n * (k + 1) * sizeof(float);
 #define SK_WG(K4) skinny_wgrad_kernel<K4><<<nblk, 256, smem, stream>>>(dy, ldy, x, ldx, M, n, rpb, partial)
-  switch (K / 4) {
-    case 1: SK_WG(1); break;
-    case 2: SK_WG(2); break;
-    case 3: SK_WG(3); break;
-    default: SK_WG(4); break;
-  }
+    switch (K / 4) {
+      case 1: SK_WG(1); break;
+      case 2: SK_WG(2); break;
+      case 3: SK_WG(3); break;
+      default: SK_WG(4); break;
+    }
 #undef SK_WG
+  }
   skinny_wgrad_reduce_kernel<<<static_cast<unsigned>(ceil_div(N * (K + 1), 128)), 128, 0, stream>>>(partial, nblk, n, k, dw, lddw, db,
                                                                                                 accumulate);
   return check_launch("skinny_linear_wgrad");

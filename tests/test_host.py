@@ -153,3 +153,20 @@ def test_synth_is_deterministic():
     a, b = synth(3000, 30, seed=5), synth(3000, 30, seed=5)
     assert np.array_equal(a.tx_pos, b.tx_pos) and np.array_equal(a.edge_pred, b.edge_pred)
     assert not np.array_equal(a.tx_pos, synth(3000, 30, seed=6).tx_pos)
+
+
+def test_chebyshev_coefficient_matrix_reproduces_oracle_sinusoid():
+    """Host-side constant of the low-rank positional front end: T(2p-1) @ M equals the oracle's
+    sinusoidal_embedding (ist_encoder.py:22-31, max_period 10000, dim 256) for p in [0,1] to fp32 rounding."""
+    from oracle.ist_encoder_ref import sinusoidal_embedding
+    from segger_b200 import ops
+    freqs = ops.sinusoid_freqs(256, 10000, "cpu")
+    M = ops.cheb_feature_matrix(freqs)
+    assert M.shape == (ops.CHEB_DEG, 256) and M.dtype == torch.float32
+    p = torch.cat([torch.linspace(0, 1, 4001, dtype=torch.float64), torch.tensor([0.0, 1.0, 0.5], dtype=torch.float64)])
+    t = 2 * p - 1
+    T = torch.stack([torch.cos(n * torch.acos(t.clamp(-1, 1))) for n in range(ops.CHEB_DEG)], 1)
+    ref = sinusoidal_embedding(p.float(), 256, max_period=10000).double()
+    assert float((T @ M.double() - ref).abs().max()) < 3e-7
+    with pytest.raises(ValueError):
+        ops.cheb_feature_matrix(freqs * 50.0)
