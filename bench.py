@@ -448,10 +448,10 @@ def kernel_rooflines(model, d, n_tx, n_cells, H, C, device, hbm_peak, peak_src):
                 "traffic": traffic, "algorithmic_bytes": nbytes, "ms": t * 1e3, "peak_source": peak_src}
 
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
-    # exactly these launches on this workload (profiles/r1c_ncu_full_summary.txt); null for other workloads.
+    # exactly these launches on this workload (profiles/r1e_ncu_full_summary.txt); null for other workloads.
     cfg2 = (n_tx, n_cells, H, C) == (1_000_000, 10_000, 2, 64)
-    tr_fwd = 1.278294e9 + 1.000695e9 if cfg2 else None
-    tr_bwd = (2.379958e9 + 1.077137e9) + (2.470092e9 + 0.499027e9) if cfg2 else None
+    tr_fwd = 1.280327e9 + 0.999322e9 if cfg2 else None
+    tr_bwd = (2.398745e9 + 1.078364e9) + (2.469396e9 + 0.498534e9) if cfg2 else None
     ents = [entry("gatv2_fwd_quad_kernel<4,8,2,4> (tx-neighbors-tx: fused logits + segment softmax + dropout + aggregate "
                   "+ bias + GELU)", fwd_b, t_fwd, tr_fwd),
             entry("gatv2_bwd_dst_quad_kernel<4,8,2,4,3> + gatv2_bwd_src_quad_kernel<4,8,2,3> + quad_colsum_kernel "
@@ -471,7 +471,10 @@ def kernel_rooflines(model, d, n_tx, n_cells, H, C, device, hbm_peak, peak_src):
     fl = 2.0 * n_tx * 3 * F * 256
     gemm = {"kernel": "gemm_tf32x3_kernel<128,0,0,1,3> (layer-1 tx projection, split-TF32 x3 on tcgen05, fp32-exact)",
             "bound": "tensor", "achieved": 3 * fl / t_gemm / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": 3 * fl / t_gemm / 1e12 / tf32_peak, "traffic": (1.026795e9 + 1.489735e9) if cfg2 else None,
+            "frac": 3 * fl / t_gemm / 1e12 / tf32_peak, "traffic": (1.026287e9 + 1.487671e9) if cfg2 else None,
+            # sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed of this launch (ncu, unthrottled
+            # clocks; the cuBLAS-derived peak above is power-capped, hence the higher `frac`)
+            "ncu_tensor_pipe_active_pct": 25.1 if cfg2 else None,
             "algorithmic_flops": fl, "issued_tf32_flops": 3 * fl, "fp32_equivalent_tflops": fl / t_gemm / 1e12,
             "algorithmic_bytes": 4 * n_tx * (256 + 3 * F), "ms": t_gemm * 1e3, "peak_source": tsrc}
     del xk, wk
