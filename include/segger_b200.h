@@ -174,6 +174,16 @@ SGB_API int sgb_posfreq_fwd(const float* pos, int64_t N, const void* batch, int 
  * the [2N, dim] feature matrix is never written.  deg % 4 == 0; workspace as sgb_posfreq_workspace_bytes. */
 SGB_API int sgb_poscheb_fwd(const float* pos, int64_t N, const void* batch, int idx_bytes, int64_t n_batches,
                     int deg, float* out, int64_t ldo, void* ws, size_t ws_bytes, void* stream);
+/* Row-subset helpers for the tx-belongs-bd conv (HeteroConv fan-out, ist_encoder.py:118-124,183-189): only the
+ * transcripts that are sources of a belongs edge need the conv's lin_l projection.  When the edge list's source row
+ * is strictly increasing (each source once, as setup_heterodata emits it, data/utils/heterodata.py:147) the layer
+ * gathers those rows (sgb_embedding_fwd with the feature matrix as table), projects E rows instead of N, and adds
+ * the input gradient back with sgb_rows_add.
+ * sgb_index_strictly_increasing: flag[0] = 1 iff ids[0] < ids[1] < ... (device flag, int32).
+ * sgb_rows_add: dst[ids[k], 0:D] += src[k, 0:D], ids unique (no atomics needed), D % 4 == 0. */
+SGB_API int sgb_index_strictly_increasing(const void* ids, int idx_bytes, int64_t n, int32_t* flag, void* stream);
+SGB_API int sgb_rows_add(float* dst, int64_t ldd, int64_t n_dst_rows, const void* ids, int idx_bytes, int64_t n, int D,
+                 const float* src, int64_t lds, void* stream);
 /* F.normalize(x, dim=-1, eps=1e-12) forward / backward (ist_encoder.py:331-332). */
 SGB_API int sgb_l2norm_fwd(const float* x, int64_t ldx, int64_t M, int D, float eps, float* y, int64_t ldy,
                    float* norm /*[M]*/, void* stream);

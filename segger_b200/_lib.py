@@ -60,6 +60,8 @@ _PROTOS = {
     "sgb_posfreq_workspace_bytes": (c_sz, [c_i64]),
     "sgb_posfreq_fwd": (c_int, [c_vp, c_i64, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "sgb_poscheb_fwd": (c_int, [c_vp, c_i64, c_vp, c_int, c_i64, c_int, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "sgb_index_strictly_increasing": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp]),
+    "sgb_rows_add": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_i64, c_int, c_vp, c_i64, c_vp]),
     "sgb_l2norm_fwd": (c_int, [c_vp, c_i64, c_i64, c_int, c_f32, c_vp, c_i64, c_vp, c_vp]),
     "sgb_l2norm_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_f32, c_vp, c_i64, c_vp]),
     "sgb_score_argmax": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp,

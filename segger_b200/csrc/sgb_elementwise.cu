@@ -329,6 +329,35 @@ poscheb_kernel(const float* __restrict__ pos, int64_t N, const IdxT* __restrict_
   }
 }
 
+// ---- row subset helpers (projection of the tx-belongs-bd sources only) ----
+// flag[0] = 1 iff ids[0] < ids[1] < ... < ids[n-1] (set to 1 by the init launch, cleared by any violating pair)
+template <typename IdxT>
+__global__ void strictly_increasing_kernel(const IdxT* __restrict__ ids, int64_t n, int32_t* __restrict__ flag) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i + 1 < n && !(ids[i] < ids[i + 1])) *flag = 0;
+}
+__global__ void flag_set_kernel(int32_t* flag, int32_t v) { *flag = v; }
+
+// dst[ids[k], :] += src[k, :]; ids are unique (strictly increasing), so no two threads touch the same element.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+rows_add_kernel(float* __restrict__ dst, int64_t ldd, int64_t n_dst_rows, const IdxT* __restrict__ ids, int64_t n, int Q,
+                const float* __restrict__ src, int64_t lds) {
+  const int64_t total = n * Q;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t k = i / Q;
+    const int c = static_cast<int>(i - k * Q) * 4;
+    const int64_t r = static_cast<int64_t>(__ldg(ids + k));
+    if (r < 0 || r >= n_dst_rows) continue;
+    const float4 a = ldg4(src + k * lds + c);
+    float* d = dst + r * ldd + c;
+    float4 o = *reinterpret_cast<const float4*>(d);
+    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    *reinterpret_cast<float4*>(d) = o;
+  }
+}
+
 // ---- L2 normalise ----
 __global__ void __launch_bounds__(256)
 l2norm_fwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t M, int D, float eps, float* __restrict__ y,
@@ -579,6 +608,34 @@ extern "C" int sgb_poscheb_fwd(const float* pos, int64_t N, const void* batch, i
     poscheb_kernel<int32_t><<<cb, 256, 0, stream>>>(pos, N, b32, n_batches, mm, deg, out, ldo);
   }
   return check_launch("poscheb_fwd");
+}
+
+extern "C" int sgb_index_strictly_increasing(const void* ids, int idx_bytes, int64_t n, int32_t* flag, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, SGB_ERR_ARG, "index_strictly_increasing: idx_bytes must be 4 or 8");
+  SGB_REQUIRE(n >= 0 && flag && (n == 0 || ids), SGB_ERR_ARG, "index_strictly_increasing: bad argument");
+  flag_set_kernel<<<1, 1, 0, stream>>>(flag, 1);
+  if (n > 1) {
+    const unsigned blocks = static_cast<unsigned>(ceil_div(n, 256));
+    if (idx_bytes == 8) strictly_increasing_kernel<int64_t><<<blocks, 256, 0, stream>>>(static_cast<const int64_t*>(ids), n, flag);
+    else strictly_increasing_kernel<int32_t><<<blocks, 256, 0, stream>>>(static_cast<const int32_t*>(ids), n, flag);
+  }
+  return check_launch("index_strictly_increasing");
+}
+
+extern "C" int sgb_rows_add(float* dst, int64_t ldd, int64_t n_dst_rows, const void* ids, int idx_bytes, int64_t n, int D,
+                            const float* src, int64_t lds, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, SGB_ERR_ARG, "rows_add: idx_bytes must be 4 or 8");
+  SGB_REQUIRE(n >= 0 && D >= 4 && D % 4 == 0 && n_dst_rows >= 0, SGB_ERR_ARG, "rows_add: bad size (D % 4 == 0)");
+  if (n == 0) return SGB_OK;
+  SGB_REQUIRE(dst && ids && src && ldd >= D && lds >= D, SGB_ERR_ARG, "rows_add: null tensor");
+  SGB_REQUIRE(ldd % 4 == 0 && lds % 4 == 0 && aligned16(dst) && aligned16(src), SGB_ERR_ALIGN, "rows_add: 16-byte alignment required");
+  const int Q = D / 4;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(n * Q, 256), static_cast<int64_t>(sm_count()) * 32));
+  if (idx_bytes == 8) rows_add_kernel<int64_t><<<blocks, 256, 0, stream>>>(dst, ldd, n_dst_rows, static_cast<const int64_t*>(ids), n, Q, src, lds);
+  else rows_add_kernel<int32_t><<<blocks, 256, 0, stream>>>(dst, ldd, n_dst_rows, static_cast<const int32_t*>(ids), n, Q, src, lds);
+  return check_launch("rows_add");
 }
 
 extern "C" int sgb_l2norm_fwd(const float* x, int64_t ldx, int64_t M, int D, float eps, float* y, int64_t ldy,

@@ -132,6 +132,38 @@ def test_skipgat_standalone_generic_and_fused_agree():
     assert float((s[deg > 0] - 1).abs().max()) < 1e-5
 
 
+def test_skipgat_source_subset_path_equals_full_projection_path():
+    """tx-belongs-bd edges with unique increasing sources (what setup_heterodata emits) take the row-subset
+    projection; the same edges shuffled, or with a repeated source, take the full [N, 3F] projection.  Same graph,
+    same weights -> same outputs and gradients (fixed-order sums: only the edge order inside a bd row differs)."""
+    from segger_b200.ist_encoder import SkipGAT
+    torch.manual_seed(1)
+    ts, x, edges, pos, bat = synth_batch(4000, 40, seed=5)
+    layer = SkipGAT((-1, -1), 64, 2).cuda().eval()
+    e_tt, e_tb = edges[TT].cuda(), edges[TB].cuda()
+    assert bool((e_tb[0][1:] > e_tb[0][:-1]).all())
+    perm = torch.randperm(e_tb.size(1), generator=torch.Generator().manual_seed(0)).cuda()
+    g = torch.Generator().manual_seed(2)
+    x_tx0, x_bd0 = torch.randn(4000, 96, generator=g).cuda(), torch.randn(40, 96, generator=g).cuda()
+    go_tx, go_bd = torch.randn(4000, 128, generator=g).cuda(), torch.randn(40, 128, generator=g).cuda()
+    res = []
+    for tb in (e_tb, e_tb[:, perm].contiguous()):
+        ops.CSR_CACHE.clear()
+        layer.zero_grad()
+        x_tx, x_bd = x_tx0.clone().requires_grad_(), x_bd0.clone().requires_grad_()
+        out = layer({"tx": x_tx, "bd": x_bd}, {TT: e_tt, TB: tb})
+        ((out["tx"] * go_tx).sum() + (out["bd"] * go_bd).sum()).backward()
+        csr = ops.CSR_CACHE.get(tb, 4000, 40, True)
+        res.append((csr.sources_unique_increasing(), out["tx"].detach(), out["bd"].detach(), x_tx.grad, x_bd.grad,
+                    {n: p.grad.clone() for n, p in layer.named_parameters() if p.grad is not None}))
+    assert res[0][0] is True and res[1][0] is False
+    for a, b in zip(res[0][1:5], res[1][1:5]):
+        assert rel_err(a, b) < 1e-5
+    assert res[0][5].keys() == res[1][5].keys() and len(res[0][5]) == 12
+    for n in res[0][5]:
+        assert rel_err(res[0][5][n], res[1][5][n]) < 1e-5, n
+
+
 def test_predict_step_assignment_agreement():
     ts, x, edges, pos, bat = synth_batch(20000, 200, seed=5, train_edges=False)
     torch.manual_seed(0)
