@@ -190,6 +190,12 @@ def test_predict_step_assignment_agreement():
     assert agree >= 0.9999, agree
     assert rel_err(max_sim, sim_r[mask]) < TOL
     assert int((seg_idx >= 0).sum()) > 10000
+    # all-true mask: no gather, same contract
+    b["tx"]["predict_mask"] = torch.ones(20000, dtype=torch.bool)
+    with torch.no_grad():
+        s2, g2, m2, x2 = lit.predict_step(b.cuda(), 0)
+    assert s2.shape == (20000,) and torch.equal(s2, b["tx"]["index"]) and torch.equal(g2[mask], seg_idx)
+    assert torch.equal(m2[mask], max_sim) and torch.equal(x2, x["tx"])
 
 
 # ---------------------------------------------------------------------------------------------- kNN
