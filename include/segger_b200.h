@@ -71,13 +71,14 @@ SGB_API int sgb_csr_build(const void* edge_index, int idx_bytes, int64_t row_str
  * x_l [n_src, H*C] / x_r [n_dst, H*C] fp32 with leading dimensions ld_* (floats, multiple of 4 for
  * the vector path), so column slices of a concatenated projection buffer can be passed directly.
  * out = pre-activation (o + bias); out_act (optional) = GELU(out) (fuses ist_encoder.py:325).
+ * out may be NULL when out_act is given (inference: only the activated output is written).
  * stat_max/stat_den [n_dst,H] are saved for the backward.  seed/p_drop/training drive the
  * counter-based dropout keyed on (seed, original edge id, head).
  * ---------------------------------------------------------------------------------------- */
 SGB_API int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, int64_t ld_r, const float* att,
                   const float* bias /*or NULL*/, const int32_t* dst_rowptr, const int32_t* dst_col,
                   const int32_t* dst_eid, int64_t n_dst, int64_t E, int H, int C, float negative_slope,
-                  float p_drop, uint64_t seed, int training, float* out, int64_t ld_out,
+                  float p_drop, uint64_t seed, int training, float* out /*or NULL*/, int64_t ld_out,
                   float* out_act /*or NULL*/, int64_t ld_act, float* stat_max, float* stat_den,
                   void* stream);
 

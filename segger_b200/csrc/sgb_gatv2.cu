@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) gatv2_fwd_vec_kernel(const GatParams p) {
     float4 o = acc[v];
     scale4(o, inv[HM::slot_of(v)]);
     if (p.bias) o = add4(o, ldg4(p.bias + off));
-    st4(p.out + row * p.ld_out + off, o);
+    if (p.out) st4(p.out + row * p.ld_out + off, o);
     if (p.out_act)
       st4(p.out_act + row * p.ld_act + off,
           make_float4(gelu_erf(o.x), gelu_erf(o.y), gelu_erf(o.z), gelu_erf(o.w)));
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(256) gatv2_fwd_gen_kernel(const GatParams p) {
     if (c < C) {
       float o = acc[t] * inv;
       if (p.bias) o += __ldg(p.bias + fo + c);
-      p.out[row * p.ld_out + fo + c] = o;
+      if (p.out) p.out[row * p.ld_out + fo + c] = o;
       if (p.out_act) p.out_act[row * p.ld_act + fo + c] = gelu_erf(o);
     }
   }
@@ -691,12 +691,12 @@ extern "C" int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, i
   int rc = validate_common("gatv2_fwd", x_l, x_r, att, n_dst, E, H, C);
   if (rc != SGB_OK) return rc;
   if (n_dst == 0) return SGB_OK;
-  SGB_REQUIRE(dst_rowptr && out && stat_max && stat_den && (E == 0 || dst_col), SGB_ERR_ARG, "gatv2_fwd: null argument");
+  SGB_REQUIRE(dst_rowptr && (out || out_act) && stat_max && stat_den && (E == 0 || dst_col), SGB_ERR_ARG, "gatv2_fwd: null argument");
   const bool train = training && p_drop > 0.f;
   SGB_REQUIRE(!train || E == 0 || dst_eid, SGB_ERR_ARG, "gatv2_fwd: training dropout needs dst_eid");
   SGB_REQUIRE(p_drop >= 0.f && p_drop < 1.f, SGB_ERR_ARG, "gatv2_fwd: dropout p must be in [0,1)");
   const bool aligned = aligned16(x_l) && aligned16(x_r) && aligned16(att) && aligned16(bias) && aligned16(out) &&
-                       aligned16(out_act) && ld_ok(ld_l) && ld_ok(ld_r) && ld_ok(ld_out) && (!out_act || ld_ok(ld_act));
+                       aligned16(out_act) && ld_ok(ld_l) && ld_ok(ld_r) && (!out || ld_ok(ld_out)) && (!out_act || ld_ok(ld_act));
   const Shape sh = classify(H, C, aligned);
   SGB_REQUIRE(sh.path != Path::kNone, SGB_ERR_ARG, "gatv2_fwd: unsupported shape H=%d C=%d (aligned=%d)", H, C, (int)aligned);
   GatParams p{};

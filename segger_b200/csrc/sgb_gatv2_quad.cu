@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
           float4 o = acc[t];
           scale4(o, inv[t / VPH]);
           if (p.bias) o = add4(o, ldg4(p.bias + off));
-          st4(p.out + row * p.ld_out + off, o);
+          if (p.out) st4(p.out + row * p.ld_out + off, o);
           if (p.out_act)
             st4(p.out_act + row * p.ld_act + off,
                 make_float4(gelu_erf(o.x), gelu_erf(o.y), gelu_erf(o.z), gelu_erf(o.w)));

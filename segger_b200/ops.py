@@ -280,8 +280,9 @@ def act_fwd(x: Tensor, act: int, y: Optional[Tensor] = None) -> Tensor:
 
 def gatv2_fwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], csr: EdgeCSR, H: int, C: int,
               slope: float, p_drop: float, training: bool, seed: int, want_act: bool,
-              out: Optional[Tensor] = None, out_act: Optional[Tensor] = None):
-    """-> (out_pre, out_act|None, stat_max, stat_den)."""
+              out: Optional[Tensor] = None, out_act: Optional[Tensor] = None, want_pre: bool = True):
+    """-> (out_pre|None, out_act|None, stat_max, stat_den).  ``want_pre=False`` (with ``want_act``) writes only
+    the activated output: the pre-activation is needed by the backward alone."""
     x_l, x_r = _rowmajor(x_l), _rowmajor(x_r)
     F = H * C
     dev = x_r.device
@@ -291,7 +292,7 @@ def gatv2_fwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], csr
                          f"({csr.n_src}, {csr.n_dst})")
     if x_l.size(1) != F or x_r.size(1) != F:
         raise ValueError("gatv2: projected features must be [*, heads*out_channels]")
-    if out is None:
+    if out is None and (want_pre or not want_act):
         out = torch.empty(n_dst, F, dtype=torch.float32, device=dev)
     if want_act and out_act is None:
         out_act = torch.empty(n_dst, F, dtype=torch.float32, device=dev)
@@ -300,7 +301,7 @@ def gatv2_fwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], csr
     att, bias = _vec(att.reshape(-1)), _vec(bias)
     check(_lib.load().sgb_gatv2_fwd(ptr(x_l), _ld(x_l), ptr(x_r), _ld(x_r), ptr(att), ptr(bias), ptr(csr.rowptr),
                                     ptr(csr.col), ptr(csr.eid), n_dst, csr.E, H, C, slope, p_drop, seed,
-                                    int(training), ptr(out), _ld(out), ptr(out_act),
+                                    int(training), ptr(out), _ld(out) if out is not None else 0, ptr(out_act),
                                     _ld(out_act) if out_act is not None else 0, ptr(smax), ptr(sden),
                                     stream_ptr(dev)), "gatv2_fwd")
     _count(1)
@@ -466,10 +467,11 @@ class SkipGATLayerFn(torch.autograd.Function):
         if not subset:
             y_tb = y_tx[:, 2 * F:]
         y_bd, _ = linear_fwd(x_bd, wr_tb, br_tb, exact=exact)
+        want_pre = bool(exact) or not apply_gelu      # `exact` = autograd is recording: the backward needs v
         v_tx, h_tx, smax_tt, sden_tt = gatv2_fwd(y_tx[:, :F], y_tx[:, F:2 * F], att_tt, bias_tt, csr_tt, H, C,
-                                                 slope, p_drop, training, seed_tt, apply_gelu)
+                                                 slope, p_drop, training, seed_tt, apply_gelu, want_pre=want_pre)
         v_bd, h_bd, smax_tb, sden_tb = gatv2_fwd(y_tb, y_bd, att_tb, bias_tb, csr_tb_run, H, C, slope,
-                                                 p_drop, training, seed_tb, apply_gelu)
+                                                 p_drop, training, seed_tb, apply_gelu, want_pre=want_pre)
         ctx.csr = (csr_tt, csr_tb, csr_tb_run)
         ctx.cfg = (H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu, subset)
         ctx.att_shape = att_tt.shape

@@ -382,3 +382,18 @@ def test_output_stage_linear_normalize_vs_torch(D):
     assert float(out[5].abs().max()) == 0.0
     out.backward(go.cuda())
     assert rel_err(hc.grad, hd.grad) < 1e-4 and rel_err(wc.grad, wd.grad) < 1e-4
+
+
+@pytest.mark.parametrize("H,C", [(2, 64), (3, 32)])
+def test_gatv2_fwd_activated_output_only(H, C):
+    """Inference writes only GELU(out) (out = NULL in the C ABI): bit-identical to the two-output call."""
+    F = H * C
+    g = torch.Generator().manual_seed(H)
+    ei = random_graph(900, 700, 6000, seed=21).cuda()
+    x_l, x_r = torch.randn(900, F, generator=g).cuda(), torch.randn(700, F, generator=g).cuda()
+    att, bias = (torch.randn(F, generator=g) * 0.3).cuda(), (torch.randn(F, generator=g) * 0.1).cuda()
+    csr = ops.build_csr(ei, 900, 700, transpose=False)
+    pre, act, m1, s1 = ops.gatv2_fwd(x_l, x_r, att, bias, csr, H, C, 0.2, 0.0, False, 0, True)
+    none, act2, m2, s2 = ops.gatv2_fwd(x_l, x_r, att, bias, csr, H, C, 0.2, 0.0, False, 0, True, want_pre=False)
+    assert none is None and torch.equal(act, act2) and torch.equal(m1, m2) and torch.equal(s1, s2)
+    assert rel_err(act, torch.nn.functional.gelu(pre.double())) < 1e-6
