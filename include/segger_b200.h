@@ -239,6 +239,42 @@ SGB_API int sgb_knn_table_to_coo(const int64_t* table, const int64_t* index_ptr,
                          int64_t pad_value, int64_t row_offset, int64_t E, int64_t* edge_index /*[2,E]*/,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training losses.  All index arrays are int64 device arrays; a NULL index means
+ * "row i of the table".  Means are reduced in a fixed order (bit-reproducible); backward kernels write
+ * per-item row gradients [T,D] which the caller segment-sums by target row with sgb_embedding_bwd.
+ * `grad` is a device scalar (dL/dloss).  Workspace: sgb_loss_workspace_bytes(T).
+ * ---------------------------------------------------------------------------------------- */
+/* FastTripletSelector.sample_triplets (models/triplet_loss.py:88-125) given the index built by _build_index
+ * (:27-86: counts/offsets/sorted_idx by cluster, present clusters, row-wise CDFs of the (dis)similarity among
+ * present clusters) and the four uniform vectors the reference draws with torch.rand (:93,:99,:105,:112). */
+SGB_API int sgb_triplet_sample(const int64_t* labels, int64_t N, int C, int P, const int64_t* present_idx,
+                       const int64_t* present, const int64_t* counts, const int64_t* offsets,
+                       const int64_t* sorted_idx, const float* cdf_pos /*[P,P]*/, const float* cdf_neg /*[P,P]*/,
+                       const float* similarity /*[C,C]*/, const float* u_pos, const float* u2, const float* u_neg,
+                       const float* u3, int64_t* positives, int64_t* negatives, float* dists_pos, float* dists_neg,
+                       void* stream);
+SGB_API size_t sgb_loss_workspace_bytes(int64_t T);
+/* torch.nn.TripletMarginLoss(margin, p=2, eps, reduction='mean') over gathered rows
+ * (triplet_loss.py:128-160; lightning_model.py:116,181-186): loss = mean(max(margin + |a-p+eps| - |a-n+eps|, 0)). */
+SGB_API int sgb_triplet_margin_fwd(const float* ta, int64_t lda, const int64_t* ia, const float* tp, int64_t ldp,
+                           const int64_t* ip, const float* tn, int64_t ldn, const int64_t* in_, int64_t T, int D,
+                           float margin, float eps, float* d_ap /*[T]*/, float* d_an /*[T]*/, float* loss /*scalar*/,
+                           void* ws, size_t ws_bytes, void* stream);
+SGB_API int sgb_triplet_margin_bwd(const float* ta, int64_t lda, const int64_t* ia, const float* tp, int64_t ldp,
+                           const int64_t* ip, const float* tn, int64_t ldn, const int64_t* in_, int64_t T, int D,
+                           float margin, float eps, const float* d_ap, const float* d_an, const float* grad,
+                           float* ga /*[T,D]*/, float* gp /*[T,D]*/, float* gn /*[T,D]*/, void* stream);
+/* mode 0: mse_loss(cosine_similarity(a, b, eps), target, 'mean') -- MetricLoss (triplet_loss.py:193-204);
+ * mode 1: BCEWithLogitsLoss()(sum(a * b, -1), target) -- segmentation BCE (lightning_model.py:188-205).
+ * val [T] receives the cosine / the logit (saved for the backward). */
+SGB_API int sgb_pair_loss_fwd(const float* ta, int64_t lda, const int64_t* ia, const float* tb, int64_t ldb,
+                      const int64_t* ib, const float* target, int64_t T, int D, int mode, float eps, float* val,
+                      float* loss /*scalar*/, void* ws, size_t ws_bytes, void* stream);
+SGB_API int sgb_pair_loss_bwd(const float* ta, int64_t lda, const int64_t* ia, const float* tb, int64_t ldb,
+                      const int64_t* ib, const float* target, int64_t T, int D, int mode, float eps,
+                      const float* val, const float* grad, float* gA /*[T,D]*/, float* gB /*[T,D]*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

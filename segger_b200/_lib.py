@@ -62,6 +62,16 @@ _PROTOS = {
     "sgb_poscheb_fwd": (c_int, [c_vp, c_i64, c_vp, c_int, c_i64, c_int, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "sgb_index_strictly_increasing": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp]),
     "sgb_rows_add": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_i64, c_int, c_vp, c_i64, c_vp]),
+    "sgb_triplet_sample": (c_int, [c_vp, c_i64, c_int, c_int] + [c_vp] * 16 + [c_vp]),
+    "sgb_loss_workspace_bytes": (c_sz, [c_i64]),
+    "sgb_triplet_margin_fwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_f32, c_f32,
+                                       c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "sgb_triplet_margin_bwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_f32, c_f32,
+                                       c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sgb_pair_loss_fwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_f32, c_vp, c_vp, c_vp,
+                                  c_sz, c_vp]),
+    "sgb_pair_loss_bwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_f32, c_vp, c_vp, c_vp,
+                                  c_vp, c_vp]),
     "sgb_l2norm_fwd": (c_int, [c_vp, c_i64, c_i64, c_int, c_f32, c_vp, c_i64, c_vp, c_vp]),
     "sgb_l2norm_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_f32, c_vp, c_i64, c_vp]),
     "sgb_score_argmax": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp,

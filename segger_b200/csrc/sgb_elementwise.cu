@@ -522,7 +522,7 @@ extern "C" int sgb_embedding_bwd(const float* dy, int64_t ldy, const void* ids, 
                                  size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SGB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, SGB_ERR_ARG, "embedding_bwd: idx_bytes must be 4 or 8");
-  SGB_REQUIRE(N >= 0 && N < (int64_t(1) << 31) && D >= 1 && D <= 512 && n_rows >= 1 && n_rows <= (1 << 20), SGB_ERR_RANGE,
+  SGB_REQUIRE(N >= 0 && N < (int64_t(1) << 31) && D >= 1 && D <= 512 && n_rows >= 1 && n_rows < (int64_t(1) << 31), SGB_ERR_RANGE,
               "embedding_bwd: size out of range");
   SGB_REQUIRE(grad_table && ws, SGB_ERR_ARG, "embedding_bwd: null tensor");
   EmbWs e = emb_carve(ws, N, n_rows, D);

@@ -1,0 +1,287 @@
+// Training losses of segger: triplet sampling, triplet-margin loss, metric (cosine / MSE) loss and the
+// segmentation BCE, each as a fused gather + reduce kernel with a deterministic (fixed-order) mean and a backward that
+// writes per-triplet row gradients (the caller segment-sums them by target row with sgb_embedding_bwd: no atomics).
+//
+// Replaces, on the `segger segment` training path,
+//   FastTripletSelector.sample_triplets   /root/reference/src/segger/models/triplet_loss.py:88-125
+//   TripletLoss / TripletMarginLoss       triplet_loss.py:128-160, lightning_model.py:116,181-186
+//   MetricLoss                            triplet_loss.py:163-204
+//   BCEWithLogitsLoss over tx.bd logits   lightning_model.py:188-205
+#include "sgb_api_internal.cuh"
+
+namespace sgb {
+namespace {
+
+constexpr int kLossThreads = 256;
+constexpr int kLossWarps = kLossThreads / 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// first index in [0, n) with cdf[idx] >= u (torch.searchsorted, right=False); n if none
+__device__ __forceinline__ int lower_bound_f32(const float* __restrict__ cdf, int n, float u) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(cdf + mid) < u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void triplet_sample_kernel(const int64_t* __restrict__ labels, int64_t N, int C, int P,
+                                      const int64_t* __restrict__ present_idx, const int64_t* __restrict__ present,
+                                      const int64_t* __restrict__ counts, const int64_t* __restrict__ offsets,
+                                      const int64_t* __restrict__ sorted_idx, const float* __restrict__ cdf_pos,
+                                      const float* __restrict__ cdf_neg, const float* __restrict__ similarity,
+                                      const float* __restrict__ u_pos, const float* __restrict__ u2,
+                                      const float* __restrict__ u_neg, const float* __restrict__ u3,
+                                      int64_t* __restrict__ positives, int64_t* __restrict__ negatives,
+                                      float* __restrict__ dists_pos, float* __restrict__ dists_neg) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int64_t lab = labels[i];
+  const int64_t row = present_idx[lab];
+  // positive: cluster by the similarity CDF row of the anchor's cluster, member uniformly inside it
+  int pp = lower_bound_f32(cdf_pos + row * P, P, u_pos[i]);
+  pp = pp < P ? pp : P - 1;
+  const int64_t pc = present[pp];
+  const int64_t ppos = static_cast<int64_t>(floorf(u2[i] * static_cast<float>(counts[pc])));
+  const int64_t pos = sorted_idx[offsets[pc] + ppos];
+  int np = lower_bound_f32(cdf_neg + row * P, P, u_neg[i]);
+  np = np < P ? np : P - 1;
+  const int64_t nc = present[np];
+  const int64_t npos = static_cast<int64_t>(floorf(u3[i] * static_cast<float>(counts[nc])));
+  const int64_t neg = sorted_idx[offsets[nc] + npos];
+  positives[i] = pos;
+  negatives[i] = neg;
+  dists_pos[i] = 1.0f - similarity[lab * C + labels[pos]];
+  dists_neg[i] = 1.0f - similarity[lab * C + labels[neg]];
+}
+
+__device__ __forceinline__ const float* row_ptr(const float* __restrict__ t, int64_t ld, const int64_t* __restrict__ idx, int64_t i) {
+  return t + (idx ? idx[i] : i) * ld;
+}
+
+// block partial sums of per-item losses, fixed order inside the block
+__device__ __forceinline__ void block_partial(float item_loss, bool lane0, float* __restrict__ partial) {
+  __shared__ float s[kLossWarps];
+  const int warp = threadIdx.x >> 5;
+  if (lane0) s[warp] = item_loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLossWarps; ++w) t += s[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void mean_reduce_kernel(const float* __restrict__ partial, int64_t n, float inv_count, float* __restrict__ out) {
+  // one warp, strided fixed-order accumulation then an ordered butterfly: deterministic for a given n
+  float t = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 32) t += partial[i];
+  t = warp_sum(t);
+  if (threadIdx.x == 0) *out = t * inv_count;
+}
+
+// warp per triplet: d(x, y) = || x - y + eps ||_2 (torch.pairwise_distance), loss = max(margin + d_ap - d_an, 0)
+__global__ void __launch_bounds__(kLossThreads)
+triplet_fwd_kernel(const float* __restrict__ ta, int64_t lda, const int64_t* __restrict__ ia, const float* __restrict__ tp,
+                   int64_t ldp, const int64_t* __restrict__ ip, const float* __restrict__ tn, int64_t ldn,
+                   const int64_t* __restrict__ in_, int64_t T, int D, float margin, float eps, float* __restrict__ d_ap,
+                   float* __restrict__ d_an, float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  float loss = 0.f;
+  if (i < T) {
+    const float* a = row_ptr(ta, lda, ia, i);
+    const float* p = row_ptr(tp, ldp, ip, i);
+    const float* n = row_ptr(tn, ldn, in_, i);
+    float sp = 0.f, sn = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float av = a[c];
+      const float dp = av - p[c] + eps, dn = av - n[c] + eps;
+      sp = fmaf(dp, dp, sp);
+      sn = fmaf(dn, dn, sn);
+    }
+    const float dap = sqrtf(warp_sum(sp)), dan = sqrtf(warp_sum(sn));
+    if (lane == 0) { d_ap[i] = dap; d_an[i] = dan; }
+    loss = fmaxf(margin + dap - dan, 0.f);
+  }
+  block_partial(loss, lane == 0, partial);
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+triplet_bwd_kernel(const float* __restrict__ ta, int64_t lda, const int64_t* __restrict__ ia, const float* __restrict__ tp,
+                   int64_t ldp, const int64_t* __restrict__ ip, const float* __restrict__ tn, int64_t ldn,
+                   const int64_t* __restrict__ in_, int64_t T, int D, float margin, float eps, const float* __restrict__ d_ap,
+                   const float* __restrict__ d_an, const float* __restrict__ grad, float* __restrict__ ga,
+                   float* __restrict__ gp, float* __restrict__ gn) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (i >= T) return;
+  const float dap = d_ap[i], dan = d_an[i];
+  const bool active = margin + dap - dan > 0.f;
+  const float g = active ? __ldg(grad) / static_cast<float>(T) : 0.f;
+  const float cp = dap > 0.f ? g / dap : 0.f, cn = dan > 0.f ? g / dan : 0.f;
+  const float* a = row_ptr(ta, lda, ia, i);
+  const float* p = row_ptr(tp, ldp, ip, i);
+  const float* n = row_ptr(tn, ldn, in_, i);
+  for (int c = lane; c < D; c += 32) {
+    const float av = a[c];
+    const float up = (av - p[c] + eps) * cp, un = (av - n[c] + eps) * cn;
+    ga[i * D + c] = up - un;
+    gp[i * D + c] = -up;
+    gn[i * D + c] = un;
+  }
+}
+
+// pair losses: mode 0 = mse(cosine_similarity(a, b), target) (ATen formula: sum (a / max(|a|, eps)) (b / max(|b|, eps)));
+//              mode 1 = binary_cross_entropy_with_logits(a . b, target)
+__global__ void __launch_bounds__(kLossThreads)
+pair_fwd_kernel(const float* __restrict__ ta, int64_t lda, const int64_t* __restrict__ ia, const float* __restrict__ tb,
+                int64_t ldb, const int64_t* __restrict__ ib, const float* __restrict__ target, int64_t T, int D, int mode,
+                float eps, float* __restrict__ val, float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  float loss = 0.f;
+  if (i < T) {
+    const float* a = row_ptr(ta, lda, ia, i);
+    const float* b = row_ptr(tb, ldb, ib, i);
+    float saa = 0.f, sbb = 0.f, sab = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float av = a[c], bv = b[c];
+      saa = fmaf(av, av, saa); sbb = fmaf(bv, bv, sbb); sab = fmaf(av, bv, sab);
+    }
+    saa = warp_sum(saa); sbb = warp_sum(sbb); sab = warp_sum(sab);
+    const float t = target[i];
+    float v;
+    if (mode == 0) {
+      v = sab / (fmaxf(sqrtf(saa), eps) * fmaxf(sqrtf(sbb), eps));
+      loss = (v - t) * (v - t);
+    } else {
+      v = sab;
+      loss = fmaxf(v, 0.f) - v * t + log1pf(expf(-fabsf(v)));
+    }
+    if (lane == 0) val[i] = v;
+  }
+  block_partial(loss, lane == 0, partial);
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+pair_bwd_kernel(const float* __restrict__ ta, int64_t lda, const int64_t* __restrict__ ia, const float* __restrict__ tb,
+                int64_t ldb, const int64_t* __restrict__ ib, const float* __restrict__ target, int64_t T, int D, int mode,
+                float eps, const float* __restrict__ val, const float* __restrict__ grad, float* __restrict__ gA,
+                float* __restrict__ gB) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (i >= T) return;
+  const float* a = row_ptr(ta, lda, ia, i);
+  const float* b = row_ptr(tb, ldb, ib, i);
+  const float g = __ldg(grad) / static_cast<float>(T);
+  const float v = val[i], t = target[i];
+  if (mode == 1) {
+    const float dv = g * (1.0f / (1.0f + expf(-v)) - t);
+    for (int c = lane; c < D; c += 32) {
+      gA[i * D + c] = dv * b[c];
+      gB[i * D + c] = dv * a[c];
+    }
+    return;
+  }
+  float saa = 0.f, sbb = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float av = a[c], bv = b[c];
+    saa = fmaf(av, av, saa); sbb = fmaf(bv, bv, sbb);
+  }
+  const float ra = sqrtf(warp_sum(saa)), rb = sqrtf(warp_sum(sbb));
+  const float na = fmaxf(ra, eps), nb = fmaxf(rb, eps);
+  const bool fa = ra > eps, fb = rb > eps;          // norm not clamped: it depends on the row
+  const float dv = g * 2.0f * (v - t);
+  for (int c = lane; c < D; c += 32) {
+    const float ah = a[c] / na, bh = b[c] / nb;
+    gA[i * D + c] = dv * (bh - (fa ? v * ah : 0.f)) / na;
+    gB[i * D + c] = dv * (ah - (fb ? v * bh : 0.f)) / nb;
+  }
+}
+
+unsigned warp_blocks(int64_t T) { return static_cast<unsigned>(ceil_div(T > 0 ? T : 1, kLossWarps)); }
+
+}  // namespace
+}  // namespace sgb
+
+using namespace sgb;
+
+extern "C" int sgb_triplet_sample(const int64_t* labels, int64_t N, int C, int P, const int64_t* present_idx,
+                                  const int64_t* present, const int64_t* counts, const int64_t* offsets,
+                                  const int64_t* sorted_idx, const float* cdf_pos, const float* cdf_neg,
+                                  const float* similarity, const float* u_pos, const float* u2, const float* u_neg,
+                                  const float* u3, int64_t* positives, int64_t* negatives, float* dists_pos,
+                                  float* dists_neg, void* stream) {
+  SGB_REQUIRE(N >= 0 && C >= 1 && P >= 1 && P <= C, SGB_ERR_ARG, "triplet_sample: bad size");
+  if (N == 0) return SGB_OK;
+  SGB_REQUIRE(labels && present_idx && present && counts && offsets && sorted_idx && cdf_pos && cdf_neg && similarity && u_pos &&
+                  u2 && u_neg && u3 && positives && negatives && dists_pos && dists_neg, SGB_ERR_ARG, "triplet_sample: null tensor");
+  triplet_sample_kernel<<<static_cast<unsigned>(ceil_div(N, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      labels, N, C, P, present_idx, present, counts, offsets, sorted_idx, cdf_pos, cdf_neg, similarity, u_pos, u2, u_neg, u3,
+      positives, negatives, dists_pos, dists_neg);
+  return check_launch("triplet_sample");
+}
+
+extern "C" size_t sgb_loss_workspace_bytes(int64_t T) { return align_up(static_cast<size_t>(warp_blocks(T)) * sizeof(float)); }
+
+extern "C" int sgb_triplet_margin_fwd(const float* ta, int64_t lda, const int64_t* ia, const float* tp, int64_t ldp,
+                                      const int64_t* ip, const float* tn, int64_t ldn, const int64_t* in_, int64_t T, int D,
+                                      float margin, float eps, float* d_ap, float* d_an, float* loss, void* ws,
+                                      size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(T >= 0 && D >= 1 && loss, SGB_ERR_ARG, "triplet_margin_fwd: bad argument");
+  if (T == 0) { cudaMemsetAsync(loss, 0, sizeof(float), stream); return check_launch("triplet_margin_fwd(empty)"); }
+  SGB_REQUIRE(ta && tp && tn && d_ap && d_an && lda >= D && ldp >= D && ldn >= D, SGB_ERR_ARG, "triplet_margin_fwd: null tensor");
+  SGB_REQUIRE(ws && ws_bytes >= sgb_loss_workspace_bytes(T), SGB_ERR_WORKSPACE, "triplet_margin_fwd: workspace too small");
+  float* partial = static_cast<float*>(ws);
+  const unsigned nb = warp_blocks(T);
+  triplet_fwd_kernel<<<nb, kLossThreads, 0, stream>>>(ta, lda, ia, tp, ldp, ip, tn, ldn, in_, T, D, margin, eps, d_ap, d_an, partial);
+  mean_reduce_kernel<<<1, 32, 0, stream>>>(partial, nb, 1.0f / static_cast<float>(T), loss);
+  return check_launch("triplet_margin_fwd");
+}
+
+extern "C" int sgb_triplet_margin_bwd(const float* ta, int64_t lda, const int64_t* ia, const float* tp, int64_t ldp,
+                                      const int64_t* ip, const float* tn, int64_t ldn, const int64_t* in_, int64_t T, int D,
+                                      float margin, float eps, const float* d_ap, const float* d_an, const float* grad,
+                                      float* ga, float* gp, float* gn, void* stream) {
+  SGB_REQUIRE(T >= 0 && D >= 1, SGB_ERR_ARG, "triplet_margin_bwd: bad argument");
+  if (T == 0) return SGB_OK;
+  SGB_REQUIRE(ta && tp && tn && d_ap && d_an && grad && ga && gp && gn, SGB_ERR_ARG, "triplet_margin_bwd: null tensor");
+  triplet_bwd_kernel<<<warp_blocks(T), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      ta, lda, ia, tp, ldp, ip, tn, ldn, in_, T, D, margin, eps, d_ap, d_an, grad, ga, gp, gn);
+  return check_launch("triplet_margin_bwd");
+}
+
+extern "C" int sgb_pair_loss_fwd(const float* ta, int64_t lda, const int64_t* ia, const float* tb, int64_t ldb,
+                                 const int64_t* ib, const float* target, int64_t T, int D, int mode, float eps, float* val,
+                                 float* loss, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(T >= 0 && D >= 1 && loss && (mode == 0 || mode == 1), SGB_ERR_ARG, "pair_loss_fwd: bad argument");
+  if (T == 0) { cudaMemsetAsync(loss, 0, sizeof(float), stream); return check_launch("pair_loss_fwd(empty)"); }
+  SGB_REQUIRE(ta && tb && target && val && lda >= D && ldb >= D, SGB_ERR_ARG, "pair_loss_fwd: null tensor");
+  SGB_REQUIRE(ws && ws_bytes >= sgb_loss_workspace_bytes(T), SGB_ERR_WORKSPACE, "pair_loss_fwd: workspace too small");
+  float* partial = static_cast<float*>(ws);
+  const unsigned nb = warp_blocks(T);
+  pair_fwd_kernel<<<nb, kLossThreads, 0, stream>>>(ta, lda, ia, tb, ldb, ib, target, T, D, mode, eps, val, partial);
+  mean_reduce_kernel<<<1, 32, 0, stream>>>(partial, nb, 1.0f / static_cast<float>(T), loss);
+  return check_launch("pair_loss_fwd");
+}
+
+extern "C" int sgb_pair_loss_bwd(const float* ta, int64_t lda, const int64_t* ia, const float* tb, int64_t ldb,
+                                 const int64_t* ib, const float* target, int64_t T, int D, int mode, float eps,
+                                 const float* val, const float* grad, float* gA, float* gB, void* stream) {
+  SGB_REQUIRE(T >= 0 && D >= 1 && (mode == 0 || mode == 1), SGB_ERR_ARG, "pair_loss_bwd: bad argument");
+  if (T == 0) return SGB_OK;
+  SGB_REQUIRE(ta && tb && target && val && grad && gA && gB, SGB_ERR_ARG, "pair_loss_bwd: null tensor");
+  pair_bwd_kernel<<<warp_blocks(T), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(ta, lda, ia, tb, ldb, ib, target, T, D,
+                                                                                       mode, eps, val, grad, gA, gB);
+  return check_launch("pair_loss_bwd");
+}

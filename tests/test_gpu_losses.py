@@ -1,0 +1,118 @@
+"""GPU parity of the training losses against the CPU oracle on identical inputs: sampler indices
+bit-exact given the same uniforms, losses and gradients within 1e-5 of the scale (fp32)."""
+import pytest
+import torch
+
+from oracle import triplet_loss_ref as R
+from segger_b200 import triplet_loss as TL
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _similarity(C, seed):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.rand(C, C, generator=g) * 2 - 1
+    return ((a + a.t()) / 2).contiguous()
+
+
+@pytest.mark.parametrize("N,C,missing", [(5000, 12, 0), (20000, 40, 7), (64, 5, 2), (1, 3, 0)])
+def test_sampler_bit_exact_given_uniforms(N, C, missing):
+    """FastTripletSelector.sample_triplets (triplet_loss.py:88-125): same clusters, same members, same distances as
+    the oracle for injected uniforms; clusters absent from the batch are never sampled."""
+    g = torch.Generator().manual_seed(N + C)
+    sim = _similarity(C, 1)
+    labels = torch.randint(0, C - missing, (N,), generator=g)
+    uni = [torch.rand(N, generator=g) for _ in range(4)]
+    ref = R.FastTripletSelectorRef(sim.clone()).sample_triplets(labels, uni)
+    got = TL.FastTripletSelector(sim.clone()).sample_triplets(labels.cuda(), [u.cuda() for u in uni])
+    assert torch.equal(got[0].cpu(), ref[0]) and torch.equal(got[1].cpu(), ref[1])
+    assert torch.equal(got[2].cpu(), ref[2]) and torch.equal(got[3].cpu(), ref[3])
+    assert int(labels[got[0].cpu()].max()) < C - missing
+
+
+def test_sampler_draws_four_uniform_vectors_from_the_torch_generator():
+    sim = _similarity(9, 3)
+    labels = torch.randint(0, 9, (3000,), generator=torch.Generator().manual_seed(0)).cuda()
+    sel = TL.FastTripletSelector(sim.clone())
+    torch.manual_seed(11)
+    a = sel.sample_triplets(labels)
+    torch.manual_seed(11)
+    uni = [torch.rand(3000, device="cuda") for _ in range(4)]
+    b = sel.sample_triplets(labels, uni)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("N,D,margin", [(4000, 64, 0.3), (777, 20, 1.0), (33, 128, 0.05)])
+def test_triplet_and_metric_loss_vs_oracle(N, D, margin):
+    g = torch.Generator().manual_seed(N)
+    C = 10
+    sim = _similarity(C, 2)
+    labels = torch.randint(0, C, (N,), generator=g)
+    uni = [torch.rand(N, generator=g) for _ in range(4)]
+    emb = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1)
+    pos, neg, dp, dn = R.FastTripletSelectorRef(sim.clone()).sample_triplets(labels, uni)
+    # --- TripletLoss
+    e_ref = emb.clone().double().requires_grad_()
+    l_ref = R.triplet_loss_ref(e_ref, pos, neg, margin)
+    l_ref.backward()
+    e = emb.clone().cuda().requires_grad_()
+    l = TL.triplet_margin(e, e, e, None, pos.cuda(), neg.cuda(), margin)
+    (l * 3.0).backward()
+    assert abs(float(l.detach()) - float(l_ref.detach())) < 1e-5 * max(1.0, abs(float(l_ref.detach())))
+    assert rel_err(e.grad / 3.0, e_ref.grad) < 1e-5
+    # --- MetricLoss
+    e_ref = emb.clone().double().requires_grad_()
+    m_ref = R.metric_loss_ref(e_ref, pos, neg, dp, dn)
+    m_ref.backward()
+    e = emb.clone().cuda().requires_grad_()
+    m = (TL.cosine_mse(e, e, None, pos.cuda(), (1 - dp).cuda()) + TL.cosine_mse(e, e, None, neg.cuda(), (1 - dn).cuda()))
+    m.backward()
+    assert abs(float(m.detach()) - float(m_ref.detach())) < 1e-5 * max(1.0, abs(float(m_ref.detach())))
+    assert rel_err(e.grad, e_ref.grad) < 1e-5
+    # deterministic
+    e2 = emb.clone().cuda().requires_grad_()
+    TL.triplet_margin(e2, e2, e2, None, pos.cuda(), neg.cuda(), margin).backward()
+    e3 = emb.clone().cuda().requires_grad_()
+    TL.triplet_margin(e3, e3, e3, None, pos.cuda(), neg.cuda(), margin).backward()
+    assert torch.equal(e2.grad, e3.grad)
+
+
+def test_loss_modules_follow_the_reference_contract():
+    """TripletLoss / MetricLoss .forward(embeddings, labels): empty labels -> 0.; a seeded call equals the functional
+    form fed with the selector's own samples."""
+    sim = _similarity(6, 4)
+    lt, lm = TL.TripletLoss(sim.clone(), margin=0.3), TL.MetricLoss(sim.clone())
+    emb = torch.randn(500, 32, generator=torch.Generator().manual_seed(1)).cuda()
+    labels = torch.randint(0, 6, (500,), generator=torch.Generator().manual_seed(2)).cuda()
+    assert lt.forward(emb[:0], labels[:0]) == 0. and lm.forward(emb[:0], labels[:0]) == 0.
+    torch.manual_seed(5)
+    a = lt.forward(emb, labels)
+    torch.manual_seed(5)
+    pos, neg, _, _ = lt.selector.sample_triplets(labels)
+    assert torch.equal(a, TL.triplet_margin(emb, emb, emb, None, pos, neg, 0.3))
+    with pytest.raises(NotImplementedError):
+        TL.TripletLoss(sim.clone(), margin=0.3, p=1.0)
+    with pytest.raises(ValueError):
+        TL.TripletLoss(sim.clone(), margin=0.0)          # torch.nn.TripletMarginLoss rejects margin <= 0
+
+
+@pytest.mark.parametrize("kind", ["triplet", "bce"])
+def test_segmentation_loss_vs_oracle(kind):
+    g = torch.Generator().manual_seed(9)
+    n_tx, n_bd, D, E = 6000, 80, 64, 2500
+    tx = torch.nn.functional.normalize(torch.randn(n_tx, D, generator=g), dim=-1)
+    bd = torch.nn.functional.normalize(torch.randn(n_bd, D, generator=g), dim=-1)
+    ei = torch.stack([torch.randperm(n_tx, generator=g)[:E], torch.randint(0, n_bd, (E,), generator=g)])
+    dst_neg = (ei[1] + torch.randint(1, n_bd, (E,), generator=g)) % n_bd
+    tx_r, bd_r = tx.clone().double().requires_grad_(), bd.clone().double().requires_grad_()
+    l_ref = R.segmentation_loss_ref(tx_r, bd_r, ei, dst_neg, kind, 0.4)
+    l_ref.backward()
+    tx_c, bd_c = tx.clone().cuda().requires_grad_(), bd.clone().cuda().requires_grad_()
+    l = TL.segmentation_loss(tx_c, bd_c, ei.cuda(), kind, 0.4, dst_neg.cuda())
+    l.backward()
+    assert abs(float(l.detach()) - float(l_ref.detach())) < 1e-5 * max(1.0, abs(float(l_ref.detach())))
+    assert rel_err(tx_c.grad, tx_r.grad) < 1e-5 and rel_err(bd_c.grad, bd_r.grad) < 1e-5
+    # one boundary only: zero loss that still carries a graph (lightning_model.py:171-174)
+    z = TL.segmentation_loss(tx_c, bd_c[:1], ei.cuda(), kind, 0.4)
+    assert float(z.detach()) == 0.0 and z.requires_grad

@@ -167,3 +167,49 @@ def test_oracle_reproduces_committed_golden_vectors():
     kn = np.load(os.path.join(GOLD, "knn_small.npz"))
     _, idx = neighbors_ref.kdtree_table(kn["points"], int(kn["k"]), float(kn["max_dist"]))
     assert np.array_equal(idx, kn["scipy_idx"])
+
+
+# ---------------------------------------------------------------------------------------------- losses (N1)
+def test_triplet_selector_ref_semantics():
+    """FastTripletSelectorRef against a direct restatement of what triplet_loss.py:88-125 computes: cluster drawn from
+    the row CDF of the anchor's cluster over *present* clusters, member = floor(u * size) into the cluster's block."""
+    from oracle import triplet_loss_ref as R
+    g = torch.Generator().manual_seed(0)
+    C, N = 7, 400
+    sim = torch.rand(C, C, generator=g) * 2 - 1
+    sim = (sim + sim.t()) / 2
+    labels = torch.randint(0, 5, (N,), generator=g)              # clusters 5, 6 absent
+    uni = [torch.rand(N, generator=g) for _ in range(4)]
+    sel = R.FastTripletSelectorRef(sim.clone())
+    pos, neg, dp, dn = sel.sample_triplets(labels, uni)
+    s = sim.clone(); s.fill_diagonal_(1)
+    simc, dis = s.clamp_min(1e-8), (-s).clamp_min(1e-8)
+    present = [c for c in range(C) if (labels == c).any()]
+    members = {c: torch.nonzero(labels == c).flatten() for c in present}
+    for i in range(0, N, 7):
+        for u_c, u_m, w, got in ((uni[0], uni[1], simc, pos), (uni[2], uni[3], dis, neg)):
+            row = w[labels[i]][present]
+            cdf = torch.cumsum(row / row.sum(), 0); cdf[-1] = 1.0
+            c = present[int(torch.searchsorted(cdf, u_c[i]))]
+            m = members[c][int((u_m[i] * float(len(members[c]))).floor())]
+            assert int(got[i]) == int(m)
+    assert torch.equal(dp, 1 - simc[labels, labels[pos]]) and torch.equal(dn, 1 - simc[labels, labels[neg]])
+    assert int(labels[pos].max()) < 5 and int(labels[neg].max()) < 5
+
+
+def test_loss_refs_match_manual_formulas():
+    from oracle import triplet_loss_ref as R
+    g = torch.Generator().manual_seed(1)
+    e = torch.randn(50, 8, generator=g, dtype=torch.float64)
+    p, n = torch.randint(0, 50, (50,), generator=g), torch.randint(0, 50, (50,), generator=g)
+    d = lambda x, y: ((x - y + 1e-6) ** 2).sum(1).sqrt()
+    manual = (0.3 + d(e, e[p]) - d(e, e[n])).clamp_min(0).mean()
+    assert torch.allclose(R.triplet_loss_ref(e, p, n, 0.3), manual, atol=1e-12)
+    dp, dn = torch.rand(50, generator=g), torch.rand(50, generator=g)
+    cos = lambda x, y: (x * y).sum(1) / (x.norm(dim=1) * y.norm(dim=1))
+    manual = ((cos(e, e[p]) - (1 - dp)) ** 2).mean() + ((cos(e, e[n]) - (1 - dn)) ** 2).mean()
+    assert torch.allclose(R.metric_loss_ref(e, p, n, dp, dn), manual, atol=1e-12)
+    w = R.scheduled_weights_ref(torch.tensor([1., 1., 0.]), torch.tensor([1., 1., .5]), 0, 10)
+    assert torch.allclose(w, torch.tensor([.5, .5, 0.]), atol=1e-6)
+    w = R.scheduled_weights_ref(torch.tensor([1., 1., 0.]), torch.tensor([1., 1., .5]), 99, 10)
+    assert torch.allclose(w, torch.tensor([.4, .4, .2]), atol=1e-6)
