@@ -1,19 +1,22 @@
 """B200-native drop-in for the hot-path methods of ``segger.models.lightning_model.LitISTEncoder``
 (/root/reference/src/segger/models/lightning_model.py): ``forward`` (:127-134), ``predict_step``
-(:263-298) and ``configure_optimizers`` (:300-303).  The losses (``get_losses``, :151-213) are
-callers of the hot path and stay out of scope.
+(:263-298), ``configure_optimizers`` (:300-303) and -- SURVEY.md section 8f row N1 -- the loss assembly
+``get_losses`` / ``training_step`` / ``validation_step`` (:136-262) on the fused loss kernels of
+``segger_b200.triplet_loss``.
 
 Lightning is optional: when it is importable the class derives from ``LightningModule`` so it can
 be handed to a ``Trainer``; otherwise it is a plain ``torch.nn.Module`` with the same methods.
 """
 from __future__ import annotations
 
+import math
 from typing import Optional
 
 import torch
 
 from . import ops
 from .ist_encoder import ISTEncoder
+from .triplet_loss import MetricLoss, TripletLoss, segmentation_loss
 
 try:  # pragma: no cover - lightning is not part of the build image
     from lightning import LightningModule as _Base
@@ -75,6 +78,72 @@ class LitISTEncoder(_Base):
             outs.append(host)
         torch.cuda.current_stream(max_sim.device).synchronize()
         return tuple(outs)
+
+    # ---- losses (lightning_model.py:86-125,136-262) ---------------------------------------------
+    def setup_losses(self, tx_similarity: torch.Tensor, bd_similarity: torch.Tensor) -> None:
+        """The loss part of ``setup`` (:108-124); the reference reads the two cluster-similarity matrices from
+        ``trainer.datamodule`` (tx_similarity / bd_similarity)."""
+        if self._sg_loss_type not in ("triplet", "bce"):
+            raise ValueError(f"Unrecognized segmentation loss: '{self._sg_loss_type}'. "
+                             f"Acceptable values are 'triplet' and 'bce'.")
+        self.loss_tx = TripletLoss(tx_similarity, margin=self._tx_margin)
+        self.loss_bd = MetricLoss(bd_similarity)
+
+    def setup(self, stage=None):
+        dm = getattr(getattr(self, "trainer", None), "datamodule", None)
+        if dm is not None and hasattr(dm, "tx_similarity") and hasattr(dm, "bd_similarity"):
+            self.setup_losses(dm.tx_similarity, dm.bd_similarity)
+        parent = getattr(super(), "setup", None)
+        return parent(stage) if callable(parent) else None
+
+    def set_epoch(self, current_epoch: int, max_epochs: int) -> None:
+        """Epoch counters for the loss-weight schedule when no Lightning Trainer drives the module."""
+        self._current_epoch, self._max_epochs = int(current_epoch), int(max_epochs)
+
+    def _epoch_info(self):
+        try:      # under a Lightning Trainer: the reference's self.current_epoch / self.trainer.max_epochs
+            return int(self.current_epoch), int(self.trainer.max_epochs)
+        except Exception:  # noqa: BLE001
+            return int(getattr(self, "_current_epoch", 0)), int(getattr(self, "_max_epochs", 1))
+
+    def _scheduled_weights(self, w_start: torch.Tensor, w_end: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+        """:136-149: cosine ramp from w_start (epoch 0) to w_end (last epoch)."""
+        cur, max_ep = self._epoch_info()
+        max_epochs = max(1, max_ep - 1)
+        t = min(cur, max_epochs) / max_epochs
+        alpha = 0.5 * (1.0 + math.cos(math.pi * t))
+        w = w_end + (w_start - w_end) * alpha
+        if normalize:
+            w = w / (w.sum() + 1e-8)
+        return w
+
+    def get_losses(self, batch):
+        """:151-211 -> (loss_tx, loss_bd, loss_sg, loss)."""
+        embeddings = self.forward(batch)
+        tx_mask = batch["tx"]["mask"]
+        bd_mask = batch["bd"]["mask"] & (batch["bd"]["cluster"] >= 0)
+        loss_tx = self.loss_tx.forward(ops.select_rows(embeddings["tx"], tx_mask), batch["tx"]["cluster"][tx_mask])
+        loss_bd = self.loss_bd.forward(ops.select_rows(embeddings["bd"], bd_mask), batch["bd"]["cluster"][bd_mask])
+        loss_sg = segmentation_loss(embeddings["tx"], embeddings["bd"], batch[("tx", "belongs", "bd")]["edge_index"],
+                                    self._sg_loss_type, self._sg_margin)
+        w_tx, w_bd, w_sg = [float(v) for v in self._scheduled_weights(self._w_start, self._w_end)]
+        loss = w_tx * loss_tx + w_bd * loss_bd + w_sg * loss_sg
+        return loss_tx, loss_bd, loss_sg, loss
+
+    def _log_losses(self, prefix: str, batch, losses) -> None:
+        if hasattr(self, "log") and getattr(self, "_trainer", None) is not None:   # only under a Lightning Trainer
+            for name, v in zip(("loss_tx", "loss_bd", "loss_sg"), losses):
+                self.log(f"{prefix}:{name}", v, prog_bar=True, batch_size=getattr(batch, "num_graphs", 1))
+
+    def training_step(self, batch, batch_idx: int = 0) -> torch.Tensor:
+        loss_tx, loss_bd, loss_sg, loss = self.get_losses(batch)
+        self._log_losses("train", batch, (loss_tx, loss_bd, loss_sg))
+        return loss
+
+    def validation_step(self, batch, batch_idx: int = 0) -> torch.Tensor:
+        loss_tx, loss_bd, loss_sg, loss = self.get_losses(batch)
+        self._log_losses("val", batch, (loss_tx, loss_bd, loss_sg))
+        return loss
 
     def configure_optimizers(self) -> torch.optim.Optimizer:
         return torch.optim.Adam(self.parameters(), lr=self.learning_rate)

@@ -257,6 +257,36 @@ def rows_add(dst: Tensor, ids: Tensor, src: Tensor) -> Tensor:
     return dst
 
 
+class SelectRowsFn(torch.autograd.Function):
+    """x[idx] for unique row indices (e.g. torch.nonzero(mask)): gather forward, rows_add into zeros backward."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        require_cuda(x, idx)
+        ctx.n = x.size(0)
+        ctx.save_for_backward(idx)
+        return gather_rows(x, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        dx = torch.zeros(ctx.n, g.size(1), dtype=torch.float32, device=g.device)
+        if idx.numel() > 0:
+            if g.size(1) % 4 == 0:
+                rows_add(dx, idx, g.contiguous())
+            else:
+                dx.index_add_(0, idx, g)
+        return dx, None
+
+
+def select_rows(x: Tensor, mask: Tensor) -> Tensor:
+    """x[mask] (boolean row mask) with the gather / scatter done by library kernels."""
+    idx = torch.nonzero(mask, as_tuple=False).flatten()
+    if idx.numel() == x.size(0):
+        return x
+    return SelectRowsFn.apply(x, idx)
+
+
 def act_bwd(dy: Tensor, pre: Tensor, act: int, dx: Optional[Tensor] = None) -> Tensor:
     dy, pre = _rowmajor(dy), _rowmajor(pre)
     M, N = dy.shape

@@ -116,3 +116,58 @@ def test_segmentation_loss_vs_oracle(kind):
     # one boundary only: zero loss that still carries a graph (lightning_model.py:171-174)
     z = TL.segmentation_loss(tx_c, bd_c[:1], ei.cuda(), kind, 0.4)
     assert float(z.detach()) == 0.0 and z.requires_grad
+
+
+@pytest.mark.parametrize("kind", ["triplet", "bce"])
+def test_get_losses_assembly_vs_oracle(kind):
+    """LitISTEncoder.get_losses (lightning_model.py:151-211): masks, the three losses and the scheduled weights,
+    against the oracle assembled from the same embeddings, the same samples and the same negatives."""
+    from segger_b200.hetero import HeteroBatch
+    from segger_b200.lightning_model import LitISTEncoder
+    from tests.util import synth_batch
+    from oracle.ist_encoder_ref import TB, TT
+    ts, x, edges, pos, bat = synth_batch(3000, 30, seed=3)
+    torch.manual_seed(0)
+    lit = LitISTEncoder(ts.n_genes, in_channels=32, hidden_channels=32, out_channels=32, n_mid_layers=0,
+                        sg_loss_type=kind).cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    sim_tx, sim_bd = _similarity(8, 5), _similarity(4, 6)
+    lit.setup_losses(sim_tx.clone(), sim_bd.clone())
+    lit.set_epoch(3, 10)
+    b = HeteroBatch()
+    for k in ("tx", "bd"):
+        b[k]["x"], b[k]["pos"], b[k]["batch"] = x[k], pos[k], bat[k]
+    b["tx"]["mask"] = torch.rand(3000, generator=g) < 0.7
+    b["tx"]["cluster"] = torch.randint(0, 8, (3000,), generator=g)
+    b["bd"]["mask"] = torch.rand(30, generator=g) < 0.9
+    b["bd"]["cluster"] = torch.randint(-1, 4, (30,), generator=g)
+    b[TT]["edge_index"], b[TB]["edge_index"] = edges[TT], edges[TB]
+    bc = b.cuda()
+    with torch.no_grad():
+        lit.forward(bc)              # materialise the lazy (-1) parameters first: their init draws random numbers
+    torch.manual_seed(21)
+    l_tx, l_bd, l_sg, loss = lit.get_losses(bc)
+    loss.backward()
+    # oracle: same embeddings (detached product output), same random draws replayed in the reference's order
+    with torch.no_grad():
+        emb = lit.forward(bc)
+    e_tx, e_bd = emb["tx"].cpu().double().requires_grad_(), emb["bd"].cpu().double().requires_grad_()
+    tx_mask = b["tx"]["mask"]
+    bd_mask = b["bd"]["mask"] & (b["bd"]["cluster"] >= 0)
+    torch.manual_seed(21)
+    n_t, n_b = int(tx_mask.sum()), int(bd_mask.sum())
+    u_t = [torch.rand(n_t, device="cuda").cpu() for _ in range(4)]
+    u_b = [torch.rand(n_b, device="cuda").cpu() for _ in range(4)]
+    E = edges[TB].size(1)
+    dst_neg = ((edges[TB][1].cuda() + torch.randint(1, 30, (E,), device="cuda")) % 30).cpu()
+    p, n, _, _ = R.FastTripletSelectorRef(sim_tx.clone()).sample_triplets(b["tx"]["cluster"][tx_mask], u_t)
+    r_tx = R.triplet_loss_ref(e_tx[tx_mask], p, n, 0.3)
+    p, n, dp, dn = R.FastTripletSelectorRef(sim_bd.clone()).sample_triplets(b["bd"]["cluster"][bd_mask], u_b)
+    r_bd = R.metric_loss_ref(e_bd[bd_mask], p, n, dp, dn)
+    r_sg = R.segmentation_loss_ref(e_tx, e_bd, edges[TB], dst_neg, kind, 0.4)
+    w = R.scheduled_weights_ref(torch.tensor([1., 1., 0.]), torch.tensor([1., 1., .5]), 3, 10)
+    r = w[0] * r_tx + w[1] * r_bd + w[2] * r_sg
+    for got, ref in ((l_tx, r_tx), (l_bd, r_bd), (l_sg, r_sg), (loss, r)):
+        assert abs(float(got.detach()) - float(ref.detach())) < 2e-5 * max(1.0, abs(float(ref.detach())))
+    assert all(p_.grad is not None and bool(torch.isfinite(p_.grad).all()) for n_, p_ in lit.model.named_parameters()
+               if "contains" not in n_)
