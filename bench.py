@@ -355,6 +355,13 @@ def main():
     ms_e2e = timed(lambda: e2e_run(K), 1) / K
     e2e_value = world * edge_layers / (ms_e2e * 1e-3)
 
+    # ---- the same step with segger's own losses instead of the linear synthetic loss -----------
+    loss_step = None
+    try:
+        loss_step = losses_step_time(lit, dev_in, n_tx, n_cells, device, flat, opt, timed, K, ms_step)
+    except Exception as e:  # noqa: BLE001 -- secondary measurement: never take the headline line down with it
+        loss_step = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- roofline of the dominant kernels, timed alone with CUDA events, L2 flushed between ------
     hbm_peak, peak_src = peaks()
     roof = kernel_rooflines(model, dev_in, n_tx, n_cells, heads, hid, device, hbm_peak, peak_src)
@@ -402,11 +409,52 @@ def main():
         "roofline": roof["dominant"],
         "roofline_kernels": roof["all"],
         "segmentation": seg,
+        "training_step_with_losses": loss_step,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def losses_step_time(lit, d, n_tx, n_cells, device, flat, opt, timed, K, ms_synth):
+    """Training step through LitISTEncoder.training_step: triplet loss on transcripts (20 synthetic clusters), metric
+    loss on boundaries (10 clusters), segmentation triplet loss on the tx-belongs-bd edges -- sampling included."""
+    from segger_b200 import ops
+    from segger_b200.hetero import HeteroBatch
+    g = torch.Generator().manual_seed(5)
+
+    def sim(c):
+        a = torch.rand(c, c, generator=g) * 2 - 1
+        return ((a + a.t()) / 2).contiguous()
+
+    lit.setup_losses(sim(20), sim(10))
+    lit.set_epoch(5, 10)
+    b = HeteroBatch()
+    b["tx"]["x"], b["tx"]["pos"], b["tx"]["batch"] = d["tx_x"], d["tx_pos"], d["tx_batch"]
+    b["bd"]["x"], b["bd"]["pos"], b["bd"]["batch"] = d["bd_x"], d["bd_pos"], d["bd_batch"]
+    b["tx"]["mask"] = torch.ones(n_tx, dtype=torch.bool, device=device)
+    b["bd"]["mask"] = torch.ones(n_cells, dtype=torch.bool, device=device)
+    b["tx"]["cluster"] = torch.randint(0, 20, (n_tx,), generator=g).to(device)
+    b["bd"]["cluster"] = torch.randint(0, 10, (n_cells,), generator=g).to(device)
+    b[TT]["edge_index"], b[TB]["edge_index"] = d["e_tt"], d["e_tb"]
+
+    def step():
+        ops.CSR_CACHE.clear()
+        flat.zero()
+        loss = lit.training_step(b, 0)
+        loss.backward()
+        flat.reduce()
+        opt.step()
+
+    for _ in range(3):
+        step()
+    l0 = ops.LAUNCHES
+    ms = timed(step, K) / K
+    return {"ms_per_step": ms, "ms_per_step_synthetic_loss": ms_synth, "loss_overhead_ms": ms - ms_synth,
+            "gpu_launches_per_step": (ops.LAUNCHES - l0) / K,
+            "losses": "TripletLoss(tx, 20 clusters, margin 0.3) + MetricLoss(bd, 10 clusters) + segmentation triplet "
+                      "(margin 0.4), weights at epoch 5/10; sampling, forward and backward in sgb_loss.cu kernels"}
 
 
 def kernel_rooflines(model, d, n_tx, n_cells, H, C, device, hbm_peak, peak_src):
