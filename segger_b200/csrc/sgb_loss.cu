@@ -79,12 +79,22 @@ __device__ __forceinline__ void block_partial(float item_loss, bool lane0, float
   }
 }
 
-__global__ void mean_reduce_kernel(const float* __restrict__ partial, int64_t n, float inv_count, float* __restrict__ out) {
-  // one warp, strided fixed-order accumulation then an ordered butterfly: deterministic for a given n
+__global__ void __launch_bounds__(1024)
+mean_reduce_kernel(const float* __restrict__ partial, int64_t n, float inv_count, float* __restrict__ out) {
+  // one CTA: fixed strided accumulation per thread, ordered butterfly per warp, ordered sum over the 32 warps:
+  // deterministic for a given n
+  __shared__ float s[32];
   float t = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += 32) t += partial[i];
+  for (int64_t i = threadIdx.x; i < n; i += 1024) t += partial[i];
   t = warp_sum(t);
-  if (threadIdx.x == 0) *out = t * inv_count;
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) a += s[w];
+    *out = a * inv_count;
+  }
 }
 
 // warp per triplet: d(x, y) = || x - y + eps ||_2 (torch.pairwise_distance), loss = max(margin + d_ap - d_an, 0)
@@ -244,7 +254,7 @@ extern "C" int sgb_triplet_margin_fwd(const float* ta, int64_t lda, const int64_
   float* partial = static_cast<float*>(ws);
   const unsigned nb = warp_blocks(T);
   triplet_fwd_kernel<<<nb, kLossThreads, 0, stream>>>(ta, lda, ia, tp, ldp, ip, tn, ldn, in_, T, D, margin, eps, d_ap, d_an, partial);
-  mean_reduce_kernel<<<1, 32, 0, stream>>>(partial, nb, 1.0f / static_cast<float>(T), loss);
+  mean_reduce_kernel<<<1, 1024, 0, stream>>>(partial, nb, 1.0f / static_cast<float>(T), loss);
   return check_launch("triplet_margin_fwd");
 }
 
@@ -271,7 +281,7 @@ extern "C" int sgb_pair_loss_fwd(const float* ta, int64_t lda, const int64_t* ia
   float* partial = static_cast<float*>(ws);
   const unsigned nb = warp_blocks(T);
   pair_fwd_kernel<<<nb, kLossThreads, 0, stream>>>(ta, lda, ia, tb, ldb, ib, target, T, D, mode, eps, val, partial);
-  mean_reduce_kernel<<<1, 32, 0, stream>>>(partial, nb, 1.0f / static_cast<float>(T), loss);
+  mean_reduce_kernel<<<1, 1024, 0, stream>>>(partial, nb, 1.0f / static_cast<float>(T), loss);
   return check_launch("pair_loss_fwd");
 }
 
