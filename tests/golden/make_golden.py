@@ -51,8 +51,39 @@ def main():
     pts = rng.uniform(0, 40, (600, 2)).astype(np.float32)
     _, idx = neighbors_ref.kdtree_table(pts, 5, 5.0)
     np.savez(os.path.join(HERE, "knn_small.npz"), points=pts, k=5, max_dist=5.0, scipy_idx=idx)
+    make_losses()
     print("golden fixtures written to", HERE)
 
 
+def make_losses():
+    """losses_small.pt: freezes oracle/triplet_loss_ref.py (sampler indices for injected uniforms, the three loss
+    values and the embedding gradients)."""
+    from oracle import triplet_loss_ref as R
+    g = torch.Generator().manual_seed(4321)
+    C, N, D, M = 6, 90, 16, 12
+    a = torch.rand(C, C, generator=g) * 2 - 1
+    sim = ((a + a.t()) / 2).contiguous()
+    labels = torch.randint(0, 5, (N,), generator=g)
+    uni = [torch.rand(N, generator=g) for _ in range(4)]
+    emb = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1)
+    bd = torch.nn.functional.normalize(torch.randn(M, D, generator=g), dim=-1)
+    ei = torch.stack([torch.randperm(N, generator=g)[:40], torch.randint(0, M, (40,), generator=g)])
+    dst_neg = (ei[1] + torch.randint(1, M, (40,), generator=g)) % M
+    pos, neg, dp, dn = R.FastTripletSelectorRef(sim.clone()).sample_triplets(labels, uni)
+    e = emb.clone().requires_grad_()
+    l_t = R.triplet_loss_ref(e, pos, neg, 0.3)
+    l_m = R.metric_loss_ref(e, pos, neg, dp, dn)
+    l_s = R.segmentation_loss_ref(e, bd, ei, dst_neg, "triplet", 0.4)
+    l_b = R.segmentation_loss_ref(e, bd, ei, dst_neg, "bce", 0.4)
+    (l_t + l_m + l_s + l_b).backward()
+    torch.save(dict(similarity=sim, labels=labels, uniforms=uni, emb=emb, bd=bd, edge_index=ei, dst_neg=dst_neg,
+                    positives=pos, negatives=neg, dists_pos=dp, dists_neg=dn, loss_triplet=l_t.detach(),
+                    loss_metric=l_m.detach(), loss_seg_triplet=l_s.detach(), loss_seg_bce=l_b.detach(), grad=e.grad),
+               os.path.join(HERE, "losses_small.pt"))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "losses":
+        make_losses()
+    else:
+        main()

@@ -171,3 +171,24 @@ def test_get_losses_assembly_vs_oracle(kind):
         assert abs(float(got.detach()) - float(ref.detach())) < 2e-5 * max(1.0, abs(float(ref.detach())))
     assert all(p_.grad is not None and bool(torch.isfinite(p_.grad).all()) for n_, p_ in lit.model.named_parameters()
                if "contains" not in n_)
+
+
+def test_losses_against_committed_golden_fixture():
+    """tests/golden/losses_small.pt (oracle outputs frozen by tests/golden/make_golden.py): sampler bit-exact, the four
+    losses and the summed embedding gradient within fp32 rounding."""
+    import os
+    gd = torch.load(os.path.join(os.path.dirname(__file__), "golden", "losses_small.pt"))
+    sel = TL.FastTripletSelector(gd["similarity"].clone())
+    pos, neg, dp, dn = sel.sample_triplets(gd["labels"].cuda(), [u.cuda() for u in gd["uniforms"]])
+    assert torch.equal(pos.cpu(), gd["positives"]) and torch.equal(neg.cpu(), gd["negatives"])
+    assert torch.equal(dp.cpu(), gd["dists_pos"]) and torch.equal(dn.cpu(), gd["dists_neg"])
+    e, bd = gd["emb"].cuda().requires_grad_(), gd["bd"].cuda()
+    ei, dst_neg = gd["edge_index"].cuda(), gd["dst_neg"].cuda()
+    l_t = TL.triplet_margin(e, e, e, None, pos, neg, 0.3)
+    l_m = TL.cosine_mse(e, e, None, pos, 1 - dp) + TL.cosine_mse(e, e, None, neg, 1 - dn)
+    l_s = TL.segmentation_loss(e, bd, ei, "triplet", 0.4, dst_neg)
+    l_b = TL.segmentation_loss(e, bd, ei, "bce", 0.4, dst_neg)
+    (l_t + l_m + l_s + l_b).backward()
+    for got, key in ((l_t, "loss_triplet"), (l_m, "loss_metric"), (l_s, "loss_seg_triplet"), (l_b, "loss_seg_bce")):
+        assert abs(float(got.detach()) - float(gd[key])) < 2e-6
+    assert rel_err(e.grad, gd["grad"]) < 1e-5

@@ -169,6 +169,23 @@ def test_oracle_reproduces_committed_golden_vectors():
     assert np.array_equal(idx, kn["scipy_idx"])
 
 
+def test_losses_oracle_reproduces_committed_golden_vectors():
+    from oracle import triplet_loss_ref as R
+    gd = torch.load(os.path.join(GOLD, "losses_small.pt"))
+    pos, neg, dp, dn = R.FastTripletSelectorRef(gd["similarity"].clone()).sample_triplets(gd["labels"], gd["uniforms"])
+    assert torch.equal(pos, gd["positives"]) and torch.equal(neg, gd["negatives"])
+    assert torch.equal(dp, gd["dists_pos"]) and torch.equal(dn, gd["dists_neg"])
+    e = gd["emb"].clone().requires_grad_()
+    l_t = R.triplet_loss_ref(e, pos, neg, 0.3)
+    l_m = R.metric_loss_ref(e, pos, neg, dp, dn)
+    l_s = R.segmentation_loss_ref(e, gd["bd"], gd["edge_index"], gd["dst_neg"], "triplet", 0.4)
+    l_b = R.segmentation_loss_ref(e, gd["bd"], gd["edge_index"], gd["dst_neg"], "bce", 0.4)
+    (l_t + l_m + l_s + l_b).backward()
+    for got, key in ((l_t, "loss_triplet"), (l_m, "loss_metric"), (l_s, "loss_seg_triplet"), (l_b, "loss_seg_bce")):
+        assert torch.allclose(got.detach(), gd[key], atol=1e-6)
+    assert torch.allclose(e.grad, gd["grad"], atol=1e-6)
+
+
 # ---------------------------------------------------------------------------------------------- losses (N1)
 def test_triplet_selector_ref_semantics():
     """FastTripletSelectorRef against a direct restatement of what triplet_loss.py:88-125 computes: cluster drawn from
