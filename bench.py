@@ -38,6 +38,7 @@ WORKLOADS = {
     "cfg2": (1_000_000, 10_000, 5, 128, 64, 64, 0, 2),
     "cfg4": (1_000_000, 10_000, 20, 128, 128, 128, 1, 4),
 }
+WORKLOADS_K = {}          # n_tx -> k of the workload being run (filled in main)
 METRIC = "gatv2_fwd_bwd_edge_layers_per_sec"
 UNIT = "edge-layers/s"
 TT = ("tx", "neighbors", "tx")
@@ -261,6 +262,7 @@ def main():
     K = max(1, args.steps)
     n_tx, n_cells, k, in_c, hid, out_c, n_mid, heads = WORKLOADS[args.workload]
     n_layers = n_mid + 2
+    WORKLOADS_K[n_tx] = k
 
     ts, host = build_workload(args.workload, seed=rank, device=device)
     torch.manual_seed(0)
@@ -556,10 +558,26 @@ def segmentation_throughput(lit, host, ts, device, world, timed):
     ms = timed(step, 5) / 5
     n = d["tx_x"].size(0)
     assigned = float((res["out"][1] >= 0).float().mean())
+
+    # the same with the transcript kNN graph rebuilt every step ("with and without graph construction");
+    # the tx-neighbors-bd candidate list (points in buffered polygons) is host preprocessing in both arms
+    from segger_b200.neighbors import kdtree_neighbors
+    def step_knn():
+        ei, _ = kdtree_neighbors(d["tx_pos"], knn_k, 5.0, device_output=True, device=device)
+        b[TT]["edge_index"] = ei
+        step()
+
+    knn_k = WORKLOADS_K.get(n, 5)
+    for _ in range(2):
+        step_knn()
+    ms_knn = timed(step_knn, 5) / 5
+    b[TT]["edge_index"] = d["e_tt_full"]
     lit.train()
     return {"metric": "segmentation_transcripts_per_sec", "value": world * n / (ms * 1e-3), "unit": "transcripts/s",
             "ms_per_step": ms, "assigned_frac": assigned,
-            "step": "predict_step: CSR build + forward + fused score/arg-max + masked D2H of (index, cell, sim, gene)"}
+            "step": "predict_step: CSR build + forward + fused score/arg-max + masked D2H of (index, cell, sim, gene)",
+            "with_knn_graph_construction": {"value": world * n / (ms_knn * 1e-3), "unit": "transcripts/s",
+                                            "ms_per_step": ms_knn, "knn_ms": ms_knn - ms, "k": knn_k, "max_dist": 5.0}}
 
 
 if __name__ == "__main__":

@@ -221,9 +221,17 @@ int run_knn(const sgb_knn_plan* plan, const T* points, const T* query, int64_t* 
   const int k = plan->k;
 #define SGB_KNN_LAUNCH(KK) \
   knn_query_kernel<KK, T><<<qb, 128, 0, stream>>>(w.sorted, w.perm, w.cell_start, g, query, nq, n, k, r2, table, count)
+  // register top-K capacity = smallest instantiation >= k: every accepted candidate costs K - 1 compare-swaps, and the
+  // register footprint (3 per slot) sets the occupancy (k = 20 on K = 32: 204 registers, 2 CTAs/SM)
   if (k <= 4) SGB_KNN_LAUNCH(4);
+  else if (k <= 5) SGB_KNN_LAUNCH(5);
+  else if (k <= 6) SGB_KNN_LAUNCH(6);
   else if (k <= 8) SGB_KNN_LAUNCH(8);
+  else if (k <= 10) SGB_KNN_LAUNCH(10);
+  else if (k <= 12) SGB_KNN_LAUNCH(12);
   else if (k <= 16) SGB_KNN_LAUNCH(16);
+  else if (k <= 20) SGB_KNN_LAUNCH(20);
+  else if (k <= 24) SGB_KNN_LAUNCH(24);
   else SGB_KNN_LAUNCH(32);
 #undef SGB_KNN_LAUNCH
   return check_launch("knn2d");
