@@ -275,6 +275,26 @@ SGB_API int sgb_pair_loss_bwd(const float* ta, int64_t lda, const int64_t* ia, c
                       const int64_t* ib, const float* target, int64_t T, int D, int mode, float eps,
                       const float* val, const float* grad, float* gA /*[T,D]*/, float* gB /*[T,D]*/, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Points-in-polygons spatial join: the tx-neighbors-bd candidate edges.
+ * Replaces cuspatial.quadtree_point_in_polygon behind points_in_polygons(predicate='contains')
+ * (geometry/query.py:21-100) as called by setup_prediction_graph (data/utils/neighbors.py:226-238).
+ * points [N,2] fp32 or fp64; polygons = one ring each: verts [V,2] fp64, ring_off [n_poly+1] int64
+ * (a closing duplicate of the first vertex is tolerated).  Inside = even-odd crossing rule in fp64.
+ * The uniform grid (xmin, ymin, cell, nx, ny) must cover the bounding box of all polygons.
+ * Two passes over one workspace: sgb_pip_count -> total[0] (device int32, read it back to allocate),
+ * then sgb_pip_fill -> edge_index [2,E] int32 (row 0 = point, row 1 = polygon; point-major, polygons
+ * ascending per point; rows ld apart).
+ * ---------------------------------------------------------------------------------------- */
+SGB_API size_t sgb_pip_workspace_bytes(int64_t n_points, int64_t n_poly, int nx, int ny);
+SGB_API int sgb_pip_count(const void* points, int points_f64, int64_t n_points, const double* verts, const int64_t* ring_off,
+                  int64_t n_poly, double xmin, double ymin, double cell, int nx, int ny, int32_t* total, void* ws,
+                  size_t ws_bytes, void* stream);
+SGB_API size_t sgb_pip_fill_scratch_bytes(int64_t E);
+SGB_API int sgb_pip_fill(const double* verts, const int64_t* ring_off, int64_t n_points, int64_t n_poly, double xmin, double ymin,
+                 double cell, int nx, int ny, int64_t E, int32_t* edge_index, int64_t ld, void* ws, size_t ws_bytes,
+                 void* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

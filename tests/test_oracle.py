@@ -230,3 +230,32 @@ def test_loss_refs_match_manual_formulas():
     assert torch.allclose(w, torch.tensor([.5, .5, 0.]), atol=1e-6)
     w = R.scheduled_weights_ref(torch.tensor([1., 1., 0.]), torch.tensor([1., 1., .5]), 99, 10)
     assert torch.allclose(w, torch.tensor([.4, .4, .2]), atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------- geometry (N2)
+def test_points_in_polygons_ref_known_answers():
+    """Even-odd crossing rule on hand-checkable shapes: convex square, concave L, a ring closed by repeating its first
+    vertex, degenerate rings; agreement with an independent winding-number evaluation on random interior points."""
+    from oracle.geometry_ref import points_in_polygons_ref
+    sq = np.array([[0.0, 0.0], [4.0, 0.0], [4.0, 4.0], [0.0, 4.0]])
+    lshape = np.array([[10.0, 0.0], [16.0, 0.0], [16.0, 2.0], [12.0, 2.0], [12.0, 6.0], [10.0, 6.0]])
+    closed = np.concatenate([sq + 20.0, (sq + 20.0)[:1]])
+    rings = [sq, lshape, closed, np.zeros((0, 2)), np.array([[1.0, 1.0], [2.0, 2.0]])]
+    off = np.zeros(len(rings) + 1, dtype=np.int64); off[1:] = np.cumsum([len(r) for r in rings])
+    verts = np.concatenate(rings)
+    pts = np.array([[2.0, 2.0], [11.0, 5.0], [15.0, 1.0], [14.0, 4.0], [22.0, 22.0], [100.0, 100.0], [-1.0, 2.0]])
+    got = set(map(tuple, points_in_polygons_ref(pts, verts, off).T))
+    assert got == {(0, 0), (1, 1), (2, 1), (4, 2)}
+    # random points vs winding number (angle sum) for a star-shaped 16-gon
+    rng = np.random.default_rng(0)
+    ang = np.linspace(0, 2 * np.pi, 16, endpoint=False)
+    rad = 5.0 * (1 + 0.4 * rng.uniform(-1, 1, 16))
+    ring = np.stack([rad * np.cos(ang), rad * np.sin(ang)], 1)
+    p = rng.uniform(-8, 8, (4000, 2))
+    a = ring[None] - p[:, None]
+    b = np.roll(ring, -1, 0)[None] - p[:, None]
+    wind = np.arctan2(a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0], (a * b).sum(-1)).sum(1) / (2 * np.pi)
+    inside = np.abs(wind) > 0.5
+    res = points_in_polygons_ref(p, ring, np.array([0, 16]))
+    mask = np.zeros(4000, bool); mask[res[0]] = True
+    assert np.array_equal(mask, inside)
