@@ -27,14 +27,14 @@ def pack_rings(rings) -> Tuple[np.ndarray, np.ndarray]:
 def _grid(verts: np.ndarray, ring_off: np.ndarray):
     """Uniform grid over the polygons' bounding box, cell ~ the median polygon extent (host side: the rings come from
     host geometry anyway); capped at 2^26 cells."""
-    lo, hi = verts.min(0), verts.max(0)
-    n = len(ring_off) - 1
-    idx = np.repeat(np.arange(n), np.diff(ring_off))
-    ext = np.zeros((n, 2))
-    for d in range(2):
-        mx = np.full(n, -np.inf); mn = np.full(n, np.inf)
-        np.maximum.at(mx, idx, verts[:, d]); np.minimum.at(mn, idx, verts[:, d])
-        ext[:, d] = mx - mn
+    sizes = np.diff(ring_off)
+    starts = ring_off[:-1][sizes > 0]
+    # per-ring boxes with reduceat (rings are contiguous runs; empty rings are skipped), then the union box
+    mx = np.maximum.reduceat(verts, starts, axis=0)
+    mn = np.minimum.reduceat(verts, starts, axis=0)
+    ext = mx - mn
+    lo = np.array([mn[:, 0].min(), mn[:, 1].min()])
+    hi = np.array([mx[:, 0].max(), mx[:, 1].max()])
     cell = float(max(np.median(ext.max(1)), 1e-9))
     span = np.maximum(hi - lo, cell)
     while (np.floor(span[0] / cell) + 1) * (np.floor(span[1] / cell) + 1) >= 2 ** 26:
@@ -43,13 +43,31 @@ def _grid(verts: np.ndarray, ring_off: np.ndarray):
     return float(lo[0]), float(lo[1]), cell, nx, ny
 
 
-def points_in_polygons(points, verts: np.ndarray, ring_off: np.ndarray, device=None, device_output: bool = False) -> Tensor:
+class PackedPolygons:
+    """Rings + their grid + device copies, built once per boundary set (the outlines of a dataset do not change
+    between prediction tiles)."""
+
+    def __init__(self, verts: np.ndarray, ring_off: np.ndarray):
+        self.verts = np.ascontiguousarray(verts, dtype=np.float64).reshape(-1, 2)
+        self.ring_off = np.ascontiguousarray(ring_off, dtype=np.int64)
+        self.n_poly = len(self.ring_off) - 1
+        self.grid = _grid(self.verts, self.ring_off) if self.n_poly > 0 and self.verts.shape[0] > 0 else None
+        self._dev = {}
+
+    def on(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = (torch.from_numpy(self.verts).to(device), torch.from_numpy(self.ring_off).to(device))
+        return self._dev[key]
+
+
+def points_in_polygons(points, verts, ring_off=None, device=None, device_output: bool = False) -> Tensor:
     """-> int32 [2, E] (index_query = point, index_match = polygon), strict containment, point-major order.
-    ``points``: [N, 2] numpy / tensor (float32 or float64; device tensors are used in place)."""
+    ``points``: [N, 2] numpy / tensor (float32 or float64; device tensors are used in place); polygons either as
+    (``verts``, ``ring_off``) arrays or as a ``PackedPolygons`` (pass it as ``verts``)."""
     device = torch.device(device if device is not None else "cuda")
-    verts = np.ascontiguousarray(verts, dtype=np.float64)
-    ring_off = np.ascontiguousarray(ring_off, dtype=np.int64)
-    n_poly = len(ring_off) - 1
+    polys = verts if isinstance(verts, PackedPolygons) else PackedPolygons(verts, ring_off)
+    n_poly = polys.n_poly
     if isinstance(points, np.ndarray):
         pts = torch.from_numpy(np.ascontiguousarray(points if points.dtype in (np.float32, np.float64)
                                                     else points.astype(np.float64)))
@@ -58,11 +76,11 @@ def points_in_polygons(points, verts: np.ndarray, ring_off: np.ndarray, device=N
     pts = pts.to(device).contiguous()
     n = pts.size(0)
     empty = torch.zeros(2, 0, dtype=torch.int32, device=device if device_output else "cpu")
-    if n == 0 or n_poly == 0 or verts.shape[0] == 0:
+    if n == 0 or polys.grid is None:
         return empty
-    xmin, ymin, cell, nx, ny = _grid(verts, ring_off)
+    xmin, ymin, cell, nx, ny = polys.grid
     lib = _lib.load()
-    d_verts, d_off = torch.from_numpy(verts).to(device), torch.from_numpy(ring_off).to(device)
+    d_verts, d_off = polys.on(device)
     ws = torch.empty(max(int(lib.sgb_pip_workspace_bytes(n, n_poly, nx, ny)), 16), dtype=torch.uint8, device=device)
     total = torch.zeros(1, dtype=torch.int32, device=device)
     f64 = int(pts.dtype == torch.float64)
@@ -80,7 +98,7 @@ def points_in_polygons(points, verts: np.ndarray, ring_off: np.ndarray, device=N
     return out if device_output else out.cpu()
 
 
-def setup_prediction_graph(points, verts: np.ndarray, ring_off: np.ndarray, device=None) -> Tensor:
+def setup_prediction_graph(points, verts, ring_off=None, device=None) -> Tensor:
     """Shape modes of setup_prediction_graph (neighbors.py:226-238) for already-buffered outlines: int32 CPU
     edge_index [2, E] = (transcript row, boundary row), as the reference returns it."""
     return points_in_polygons(points, verts, ring_off, device=device, device_output=False)

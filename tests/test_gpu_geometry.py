@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle.geometry_ref import points_in_polygons_ref
-from segger_b200.geometry import pack_rings, points_in_polygons, setup_prediction_graph
+from segger_b200.geometry import PackedPolygons, pack_rings, points_in_polygons, setup_prediction_graph
 from segger_b200.synth import synth
 
 pytestmark = pytest.mark.gpu
@@ -62,6 +62,10 @@ def test_prediction_graph_on_synthetic_tile_matches_oracle_and_feeds_scoring():
     ref = points_in_polygons_ref(ts.tx_pos, verts, off)
     got = setup_prediction_graph(ts.tx_pos, verts, off)
     assert np.array_equal(got.numpy(), ref)
+    polys = PackedPolygons(verts, off)                         # packed once, reused across calls / tiles
+    half = ts.tx_pos[:25_000]
+    assert np.array_equal(points_in_polygons(half, polys).numpy(), points_in_polygons_ref(half, verts, off))
+    assert np.array_equal(points_in_polygons(ts.tx_pos, polys).numpy(), ref)
     own = ts.tx_cell >= 0
     d = np.linalg.norm(ts.tx_pos[own].astype(np.float64) - ts.bd_pos[ts.tx_cell[own]].astype(np.float64), axis=1)
     deep = np.nonzero(own)[0][d < r_buf * np.cos(np.pi / 16) - 1e-6]          # inside the inscribed circle
