@@ -332,26 +332,31 @@ def main():
     # the timed region (K copies for K steps; the first one is not overlapped) and reads its loss back.
     copy_stream = torch.cuda.Stream(device)
     compute_stream = torch.cuda.current_stream(device)
-    pending = {}
+    # two preallocated device input sets (double buffering): no allocator traffic across streams inside the loop
+    bufs = [{k_: torch.empty_like(host[k_], device=device) for k_ in TRAIN_KEYS} for _ in range(2)]
+    done = [None, None]
 
-    def fetch():
+    def fetch(slot):
         with torch.cuda.stream(copy_stream):
-            d = to_device(host, device, TRAIN_KEYS)
+            if done[slot] is not None:
+                copy_stream.wait_event(done[slot])       # the step that last read this buffer set has finished
+            for k_ in TRAIN_KEYS:
+                bufs[slot][k_].copy_(host[k_], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        pending["next"] = (d, ev)
+        return ev
 
     def e2e_run(steps):
-        fetch()
+        ev = fetch(0)
         for i in range(steps):
-            d, ev = pending.pop("next")
+            slot = i % 2
             compute_stream.wait_event(ev)
-            for t_ in d.values():
-                t_.record_stream(compute_stream)
             if i + 1 < steps:
-                fetch()
-            loss = train_step(d)
+                ev = fetch((i + 1) % 2)
+            loss = train_step(bufs[slot])
             float(loss.item())             # D2H read of the step's result
+            done[slot] = torch.cuda.Event()
+            done[slot].record(compute_stream)
 
     e2e_run(2)
     ms_e2e = timed(lambda: e2e_run(K), 1) / K
