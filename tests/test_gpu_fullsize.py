@@ -147,3 +147,44 @@ def test_score_argmax_1m_properties(full):
     m = ep[0] < 50_000
     seg_r, sim_r, _ = predict_scores_ref(e_tx[:50_000].cpu(), e_bd.cpu(), ep[:, m].cpu(), bd_index.cpu())
     assert float((seg[:50_000].cpu() == seg_r).float().mean()) >= 0.9999
+
+
+def test_points_in_polygons_1m_properties(full):
+    """N2 at BASELINE size: 1M transcripts x 10k buffered cell outlines.  Pair list point-major / polygon-ascending
+    and duplicate-free, every pair inside the polygon's circumscribed circle and every point inside an inscribed
+    circle present, bit-reproducible, and identical to the oracle on the pairs of 25 sampled polygons."""
+    from oracle.geometry_ref import points_in_polygons_ref
+    from segger_b200.geometry import PackedPolygons, pack_rings, points_in_polygons
+    ts, _ = full
+    r = 6.5 * 1.05
+    ang = np.linspace(0, 2 * np.pi, 16, endpoint=False)
+    c = ts.bd_pos.astype(np.float64)
+    rings = [np.stack([x + r * np.cos(ang), y + r * np.sin(ang)], 1) for x, y in c]
+    verts, off = pack_rings(rings)
+    polys = PackedPolygons(verts, off)
+    pts = torch.from_numpy(ts.tx_pos).cuda()
+    e = points_in_polygons(pts, polys, device_output=True)
+    e2 = points_in_polygons(pts, polys, device_output=True)
+    assert torch.equal(e, e2)
+    p, g = e[0].long(), e[1].long()
+    key = p * N_CELLS + g
+    assert bool((key[1:] > key[:-1]).all())                                    # sorted, no duplicates
+    d = (pts.double()[p] - torch.from_numpy(c).cuda()[g]).norm(dim=1)
+    assert float(d.max()) <= r + 1e-9                                            # inside the circumscribed circle
+    # every (transcript, own cell) with the transcript well inside the inscribed circle must be listed
+    own = torch.from_numpy(ts.tx_cell).cuda()
+    has = own >= 0
+    d_own = (pts.double()[has] - torch.from_numpy(c).cuda()[own[has]]).norm(dim=1)
+    deep = torch.nonzero(has).squeeze(1)[d_own < r * np.cos(np.pi / 16) - 1e-6]
+    want = deep * N_CELLS + own[deep]
+    pos = torch.searchsorted(key, want)
+    assert bool((key[pos.clamp_max(key.numel() - 1)] == want).all())
+    # oracle on sampled polygons
+    sel = np.random.default_rng(0).choice(N_CELLS, 25, replace=False)
+    sub_verts, sub_off = pack_rings([rings[i] for i in sel])
+    ref = points_in_polygons_ref(ts.tx_pos, sub_verts, sub_off)
+    ref_pairs = set((int(a), int(sel[b])) for a, b in ref.T)
+    sel_t = torch.from_numpy(sel).cuda()
+    m = torch.isin(g, sel_t)
+    got_pairs = set(zip(p[m].tolist(), g[m].tolist()))
+    assert got_pairs == ref_pairs and len(ref_pairs) > 1000
