@@ -82,6 +82,10 @@ SGB_API int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, int6
                   float* out_act /*or NULL*/, int64_t ld_act, float* stat_max, float* stat_den,
                   void* stream);
 
+/* 1 iff (H, C) is covered by the sub-warp-per-row kernels (needed for the one-source-per-edge form of sgb_gatv2_bwd:
+ * src_rowptr == NULL, n_src == E, dst_col a permutation of [0, E) -- grad_x_l is then written by the dst pass). */
+SGB_API int sgb_gatv2_quad_supported(int H, int C);
+
 /* attention coefficients alpha [E,H] in ORIGINAL edge order (return_attention_weights=True path of
  * GATv2Conv; SkipGAT.attention_weights, models/ist_encoder.py:192-211).  Pre-dropout alpha. */
 SGB_API int sgb_gatv2_alpha(const float* x_l, int64_t ld_l, const float* x_r, int64_t ld_r, const float* att,

@@ -78,6 +78,7 @@ _PROTOS = {
     "sgb_pip_fill_scratch_bytes": (c_sz, [c_i64]),
     "sgb_pip_fill": (c_int, [c_vp, c_vp, c_i64, c_i64, C.c_double, C.c_double, C.c_double, c_int, c_int, c_i64, c_vp, c_i64,
                              c_vp, c_sz, c_vp, c_sz, c_vp]),
+    "sgb_gatv2_quad_supported": (c_int, [c_int, c_int]),
     "sgb_l2norm_fwd": (c_int, [c_vp, c_i64, c_i64, c_int, c_f32, c_vp, c_i64, c_vp, c_vp]),
     "sgb_l2norm_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_f32, c_vp, c_i64, c_vp]),
     "sgb_score_argmax": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp,

@@ -723,6 +723,12 @@ extern "C" int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, i
   return check_launch("gatv2_fwd");
 }
 
+extern "C" int sgb_gatv2_quad_supported(int H, int C) {
+  GatParams p{};
+  p.H = H; p.C = C; p.slope = 0.2f;
+  return quad_supported(p) ? 1 : 0;
+}
+
 extern "C" int sgb_gatv2_alpha(const float* x_l, int64_t ld_l, const float* x_r, int64_t ld_r, const float* att,
                                const int32_t* dst_rowptr, const int32_t* dst_col, const int32_t* dst_eid,
                                int64_t n_dst, int64_t E, int H, int C, float negative_slope, const float* stat_max,
@@ -772,7 +778,11 @@ extern "C" int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, i
   SGB_REQUIRE(n_src >= 0 && n_src < (int64_t(1) << 31), SGB_ERR_RANGE, "gatv2_bwd: n_src out of range");
   SGB_REQUIRE(grad_att && (n_src == 0 || grad_x_l) && (n_dst == 0 || (grad_x_r && out && grad_out && stat_max && stat_den)),
               SGB_ERR_ARG, "gatv2_bwd: null argument");
-  SGB_REQUIRE(dst_rowptr && src_rowptr && (E == 0 || (dst_col && src_dst && src_pos)), SGB_ERR_ARG, "gatv2_bwd: null CSR");
+  // src_rowptr == NULL: "one source per edge" -- dst_col is a permutation of [0, E) (n_src == E), so every grad_x_l row has
+  // exactly one contribution and the dst pass writes it directly (no transposed pass, no per-edge records read back)
+  const bool direct_src = src_rowptr == nullptr;
+  SGB_REQUIRE(dst_rowptr && (E == 0 || dst_col) && (direct_src ? n_src == E : (E == 0 || (src_dst && src_pos))), SGB_ERR_ARG,
+              "gatv2_bwd: null CSR");
   SGB_REQUIRE(!gelu_fused || g_buf, SGB_ERR_ARG, "gatv2_bwd: gelu_fused requires g_buf");
   SGB_REQUIRE(ws && ws_bytes >= sgb_gatv2_bwd_workspace_bytes(n_dst, E, H, C), SGB_ERR_WORKSPACE, "gatv2_bwd: workspace too small");
   const bool train = training && p_drop > 0.f;
@@ -801,6 +811,8 @@ extern "C" int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, i
 
   if (n_dst > 0 && aligned && !legacy_path() && quad_bwd_launch(p, grad_att, grad_bias, stream))
     return check_launch("gatv2_bwd(quad)");
+  SGB_REQUIRE(!direct_src, SGB_ERR_ARG, "gatv2_bwd: the one-source-per-edge form (src_rowptr == NULL) needs a shape covered by "
+              "the sub-warp kernels (sgb_gatv2_quad_supported)");
   if (n_dst == 0) {
     cudaMemsetAsync(grad_att, 0, sizeof(float) * F, stream);
     if (grad_bias) cudaMemsetAsync(grad_bias, 0, sizeof(float) * F, stream);

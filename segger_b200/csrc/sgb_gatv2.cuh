@@ -56,5 +56,6 @@ static inline __host__ __device__ int rec_stride(int H) { return (2 * H + 3) / 4
 bool quad_fwd_launch(const GatParams& p, cudaStream_t stream);
 size_t quad_bwd_partial_floats(int H, int C);
 bool quad_bwd_launch(const GatParams& p, float* grad_att, float* grad_bias, cudaStream_t stream);
+bool quad_supported(const GatParams& p);   // shape (H, C) and slope covered by the sub-warp kernels
 
 }  // namespace sgb

@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
   }
   const float slope = p.slope;
   const bool training = p.training != 0;
+  const bool direct_src = p.t_rowptr == nullptr;   // one source per edge: this pass also writes grad_x_l
 
   for (int64_t chunk = static_cast<int64_t>(blockIdx.x) * kQW + warp; chunk < nchunks;
        chunk += static_cast<int64_t>(gridDim.x) * kQW) {
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
         pipe.consumed();
         const int e = eid_next;
         if (training && k + 1 < c_deg) eid_next = __ldg(p.eid + c_beg + k + 1);
+        const int jcol = (direct_src && act) ? __ldg(p.col + c_beg + k) : 0;
         uint32_t eh = 0;
         if (training) eh = rng_edge(p.seed, static_cast<uint32_t>(e));
         float delta[H], alk[H];
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
           delta[h] = alpha * (dd[h] * ks - cdot[h]);
           alk[h] = alpha * ks;
         }
-        if (act && s < SH / 4) {
+        if (act && !direct_src && s < SH / 4) {
           // record: [delta_0..delta_{H-1}, alpha'_0..alpha'_{H-1}, pad]
           float rec[SH];
 #pragma unroll
@@ -456,8 +458,19 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
         for (int t = 0; t < V; ++t) {
           const float d = delta[t / VPH], ds = d * slope;     // delta * lrelu'(z): d where z > 0, d * slope elsewhere
           const float4 zz = z[t];
-          gr[t].x = fmaf(zz.x > 0.f ? d : ds, a[t].x, gr[t].x); gr[t].y = fmaf(zz.y > 0.f ? d : ds, a[t].y, gr[t].y);
-          gr[t].z = fmaf(zz.z > 0.f ? d : ds, a[t].z, gr[t].z); gr[t].w = fmaf(zz.w > 0.f ? d : ds, a[t].w, gr[t].w);
+          if (!direct_src) {           // (warp-uniform) the common form: accumulate dL/dz_e into grad_x_r with FMAs
+            gr[t].x = fmaf(zz.x > 0.f ? d : ds, a[t].x, gr[t].x); gr[t].y = fmaf(zz.y > 0.f ? d : ds, a[t].y, gr[t].y);
+            gr[t].z = fmaf(zz.z > 0.f ? d : ds, a[t].z, gr[t].z); gr[t].w = fmaf(zz.w > 0.f ? d : ds, a[t].w, gr[t].w);
+          } else {                     // one source per edge: grad_x_l[j] = dL/dz_e + alpha'_e g_i is written here too
+            const float4 dz = make_float4((zz.x > 0.f ? d : ds) * a[t].x, (zz.y > 0.f ? d : ds) * a[t].y,
+                                          (zz.z > 0.f ? d : ds) * a[t].z, (zz.w > 0.f ? d : ds) * a[t].w);
+            gr[t] = add4(gr[t], dz);
+            if (act) {
+              const float ak = alk[t / VPH];
+              st4(p.grad_x_l + static_cast<int64_t>(jcol) * p.ld_gl + (t * LPR + s) * 4,
+                  make_float4(fmaf(ak, g4[t].x, dz.x), fmaf(ak, g4[t].y, dz.y), fmaf(ak, g4[t].z, dz.z), fmaf(ak, g4[t].w, dz.w)));
+            }
+          }
           fma4(gatt[t], d, zz);
         }
       }
@@ -692,6 +705,11 @@ bool set_smem(K kernel, size_t bytes) {
 // max(z, slope*z) and the sign test on lrelu(z) in the backward need 0 <= slope <= 1
 static bool quad_slope_ok(float slope) { return slope >= 0.f && slope <= 1.f; }
 
+bool quad_supported(const GatParams& p) {
+  QShape qs;
+  return quad_slope_ok(p.slope) && quad_shape(p.H, p.C, qs);
+}
+
 bool quad_fwd_launch(const GatParams& p, cudaStream_t stream) {
   QShape qs;
   if (!quad_slope_ok(p.slope) || !quad_shape(p.H, p.C, qs)) return false;
@@ -761,7 +779,7 @@ bool quad_bwd_launch(const GatParams& p, float* grad_att, float* grad_bias, cuda
     quad_colsum_kernel<<<static_cast<unsigned>(ceil_div(2 * F, 32)), dim3(32, 8), 0, stream>>>(p.partial, nb, 2 * F, F,
                                                                                                grad_att, grad_bias);
   }
-  if (p.n_src > 0) {
+  if (p.n_src > 0 && p.t_rowptr != nullptr) {
     const int rpw = pick_rpw(p.n_src, G);
     const int64_t nchunks = ceil_div(p.n_src, rpw);
     const unsigned blocks = static_cast<unsigned>(ceil_div(nchunks, kQW));

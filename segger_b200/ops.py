@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -73,6 +74,7 @@ class EdgeCSR:
     src_index: Optional[Tensor] = None      # row 0 of the edge_index this CSR was built from (a view, kept alive)
     _src_unique: Optional[bool] = None      # lazily computed: source ids strictly increasing (each source once)
     _virtual: Optional["EdgeCSR"] = None
+    one_source_per_edge: bool = False       # col is a permutation of [0, E): the backward needs no transposed pass
 
     def sources_unique_increasing(self) -> bool:
         """True iff the edge list names every source at most once, in increasing order (what setup_heterodata emits
@@ -99,7 +101,7 @@ class EdgeCSR:
             if self.t_rowptr is not None:
                 t_rowptr = torch.arange(self.E + 1, dtype=torch.int32, device=self.rowptr.device)
             self._virtual = EdgeCSR(self.rowptr, self.eid, self.eid, t_rowptr, self.t_dst, self.t_pos, self.E, self.n_dst,
-                                    self.E, self.status, self.src_index)
+                                    self.E, self.status, self.src_index, one_source_per_edge=True)
         return self._virtual
 
 
@@ -361,9 +363,14 @@ def gatv2_bwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], out
     lib = _lib.load()
     ws = _ws(lib.sgb_gatv2_bwd_workspace_bytes(n_dst, csr.E, H, C), dev)
     att, bias = _vec(att.reshape(-1)), _vec(bias)
+    # one virtual source per edge: the dst pass writes grad_x_l itself (NULL transposed CSR) where the sub-warp kernels apply
+    direct = (csr.one_source_per_edge and n_dst > 0 and csr.E > 0 and bool(lib.sgb_gatv2_quad_supported(H, C))
+              and os.environ.get("SEGGER_B200_GAT") != "legacy" and os.environ.get("SEGGER_B200_GAT_DIRECT", "1") != "0"
+              and all(t.data_ptr() % 16 == 0 and _ld(t) % 4 == 0 for t in (x_l, x_r, out_pre, grad_out, grad_x_l, grad_x_r)))
+    t_rowptr, t_dst, t_pos = (None, None, None) if direct else (csr.t_rowptr, csr.t_dst, csr.t_pos)
     check(lib.sgb_gatv2_bwd(ptr(x_l), _ld(x_l), ptr(x_r), _ld(x_r), ptr(att), ptr(bias), ptr(out_pre), _ld(out_pre),
                             ptr(grad_out), _ld(grad_out), int(gelu_fused), ptr(g_buf), ptr(csr.rowptr), ptr(csr.col),
-                            ptr(csr.eid), ptr(csr.t_rowptr), ptr(csr.t_dst), ptr(csr.t_pos), n_src, n_dst, csr.E,
+                            ptr(csr.eid), ptr(t_rowptr), ptr(t_dst), ptr(t_pos), n_src, n_dst, csr.E,
                             H, C, slope, p_drop, seed, int(training), ptr(smax), ptr(sden), ptr(grad_x_l),
                             _ld(grad_x_l), ptr(grad_x_r), _ld(grad_x_r), ptr(g_att), ptr(g_bias), ptr(ws),
                             ws.numel(), stream_ptr(dev)), "gatv2_bwd")

@@ -397,3 +397,31 @@ def test_gatv2_fwd_activated_output_only(H, C):
     none, act2, m2, s2 = ops.gatv2_fwd(x_l, x_r, att, bias, csr, H, C, 0.2, 0.0, False, 0, True, want_pre=False)
     assert none is None and torch.equal(act, act2) and torch.equal(m1, m2) and torch.equal(s1, s2)
     assert rel_err(act, torch.nn.functional.gelu(pre.double())) < 1e-6
+
+
+@pytest.mark.parametrize("H,C", [(2, 64), (3, 32), (4, 128)])
+def test_gatv2_bwd_one_source_per_edge_form(H, C):
+    """tx-belongs-bd with one virtual source per edge (EdgeCSR.per_edge_sources): the dst pass writes grad_x_l itself
+    (NULL transposed CSR in the C ABI); must equal the two-pass backward on the same virtual graph (to rounding: the
+    one-pass form adds the rounded product where the two-pass form uses an FMA)."""
+    F = H * C
+    g = torch.Generator().manual_seed(C)
+    n_src, n_dst, E = 5000, 300, 2100
+    src = torch.sort(torch.randperm(n_src, generator=g)[:E]).values
+    ei = torch.stack([src, torch.randint(0, n_dst - 20, (E,), generator=g)]).cuda()
+    csr = ops.build_csr(ei, n_src, n_dst)
+    assert csr.sources_unique_increasing()
+    v = csr.per_edge_sources()
+    assert v.one_source_per_edge and v.n_src == E
+    x_l, x_r = torch.randn(E, F, generator=g).cuda(), torch.randn(n_dst, F, generator=g).cuda()
+    att, bias = (torch.randn(F, generator=g) * 0.3).cuda(), (torch.randn(F, generator=g) * 0.1).cuda()
+    go = torch.randn(n_dst, F, generator=g).cuda()
+    out, _, smax, sden = ops.gatv2_fwd(x_l, x_r, att, bias, v, H, C, 0.2, 0.2, True, 5, True)
+    a = ops.gatv2_bwd(x_l, x_r, att, bias, out, go, True, v, H, C, 0.2, 0.2, True, 5, smax, sden)
+    two_pass = ops.EdgeCSR(v.rowptr, v.col, v.eid, v.t_rowptr, v.t_dst, v.t_pos, v.n_src, v.n_dst, v.E, v.status)
+    b = ops.gatv2_bwd(x_l, x_r, att, bias, out, go, True, two_pass, H, C, 0.2, 0.2, True, 5, smax, sden)
+    for u, w in zip(a, b):
+        assert rel_err(u, w) < 1e-6
+    assert torch.equal(a[2], b[2])                     # grad_att: same products, same order
+    a2 = ops.gatv2_bwd(x_l, x_r, att, bias, out, go, True, v, H, C, 0.2, 0.2, True, 5, smax, sden)
+    assert all(torch.equal(u, w) for u, w in zip(a, a2))
