@@ -46,6 +46,27 @@ TB = ("tx", "belongs", "bd")
 PRED = ("tx", "neighbors", "bd")
 
 
+_OUT_FD = None
+
+
+def capture_stdout():
+    """Route file descriptor 1 to stderr for the whole run (NCCL prints its version banner on stdout from C) and keep
+    the real stdout for the single JSON line."""
+    global _OUT_FD
+    if _OUT_FD is None:
+        sys.stdout.flush()
+        _OUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _OUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, data)
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -219,7 +240,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 WORKLOADS_DESC = {
@@ -239,6 +260,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -419,7 +441,7 @@ def main():
         "training_step_with_losses": loss_step,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
