@@ -190,3 +190,38 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+
+
+def test_geometry_host_helpers_pack_and_grid():
+    """pack_rings / PackedPolygons grid (host side of the point-in-polygon join): offsets, tolerated empty rings, a grid
+    that covers every polygon box with cells of about one polygon extent."""
+    from segger_b200.geometry import PackedPolygons, pack_rings
+    rng = np.random.default_rng(0)
+    ang = np.linspace(0, 2 * np.pi, 16, endpoint=False)
+    centers = rng.uniform(0, 500, (300, 2))
+    rings = [np.stack([x + 7 * np.cos(ang), y + 7 * np.sin(ang)], 1) for x, y in centers]
+    rings.insert(5, np.zeros((0, 2)))
+    verts, off = pack_rings(rings)
+    assert verts.shape == (300 * 16, 2) and off[0] == 0 and off[-1] == 300 * 16 and off[6] == off[5]
+    p = PackedPolygons(verts, off)
+    xmin, ymin, cell, nx, ny = p.grid
+    assert p.n_poly == 301 and 13.0 < cell < 15.0
+    assert xmin <= verts[:, 0].min() and ymin <= verts[:, 1].min()
+    assert xmin + nx * cell > verts[:, 0].max() and ymin + ny * cell > verts[:, 1].max()
+    assert nx * ny < 2 ** 26
+    empty = PackedPolygons(*pack_rings([]))
+    assert empty.grid is None and empty.n_poly == 0
+
+
+def test_loss_modules_reject_unsupported_options_without_gpu():
+    from segger_b200.triplet_loss import MetricLoss, TripletLoss
+    sim = torch.eye(4)
+    with pytest.raises(ValueError):
+        TripletLoss(sim.clone(), margin=0.0)
+    with pytest.raises(NotImplementedError):
+        TripletLoss(sim.clone(), margin=0.3, swap=True)
+    lt, lm = TripletLoss(sim.clone(), margin=0.3), MetricLoss(sim.clone())
+    assert lt.forward(torch.zeros(0, 8), torch.zeros(0, dtype=torch.long)) == 0.
+    assert lm.forward(torch.zeros(0, 8), torch.zeros(0, dtype=torch.long)) == 0.
+    with pytest.raises(Exception):                      # CPU tensors: the product path has no CPU fallback
+        lt.forward(torch.randn(10, 8), torch.randint(0, 4, (10,)))
