@@ -52,6 +52,7 @@ def main():
     _, idx = neighbors_ref.kdtree_table(pts, 5, 5.0)
     np.savez(os.path.join(HERE, "knn_small.npz"), points=pts, k=5, max_dist=5.0, scipy_idx=idx)
     make_losses()
+    make_pip()
     print("golden fixtures written to", HERE)
 
 
@@ -82,8 +83,30 @@ def make_losses():
                os.path.join(HERE, "losses_small.pt"))
 
 
+def make_pip():
+    """pip_small.npz: freezes oracle/geometry_ref.py on 40 jittered 12-gons (some closed by repeating the first vertex,
+    overlapping) and 3000 float32 points."""
+    from oracle.geometry_ref import points_in_polygons_ref
+    rng = np.random.default_rng(77)
+    rings = []
+    for i in range(40):
+        c = rng.uniform(5, 95, 2)
+        ang = np.linspace(0, 2 * np.pi, 12, endpoint=False)
+        r = 6.0 * (1 + 0.35 * rng.uniform(-1, 1, 12))
+        ring = np.stack([c[0] + r * np.cos(ang), c[1] + r * np.sin(ang)], 1)
+        rings.append(np.concatenate([ring, ring[:1]]) if i % 3 == 0 else ring)
+    off = np.zeros(41, dtype=np.int64)
+    off[1:] = np.cumsum([len(r) for r in rings])
+    verts = np.concatenate(rings)
+    pts = rng.uniform(0, 100, (3000, 2)).astype(np.float32)
+    pairs = points_in_polygons_ref(pts, verts, off)
+    np.savez(os.path.join(HERE, "pip_small.npz"), points=pts, verts=verts, ring_off=off, pairs=pairs)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "losses":
         make_losses()
+    elif len(sys.argv) > 1 and sys.argv[1] == "pip":
+        make_pip()
     else:
         main()

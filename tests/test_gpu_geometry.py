@@ -71,3 +71,10 @@ def test_prediction_graph_on_synthetic_tile_matches_oracle_and_feeds_scoring():
     deep = np.nonzero(own)[0][d < r_buf * np.cos(np.pi / 16) - 1e-6]          # inside the inscribed circle
     pairs = set(map(tuple, got.numpy().T))
     assert all((int(i), int(ts.tx_cell[i])) in pairs for i in deep[::50])
+
+
+def test_points_in_polygons_against_committed_golden_fixture():
+    import os
+    gd = np.load(os.path.join(os.path.dirname(__file__), "golden", "pip_small.npz"))
+    got = points_in_polygons(gd["points"], gd["verts"], gd["ring_off"])
+    assert np.array_equal(got.numpy(), gd["pairs"])

@@ -259,3 +259,10 @@ def test_points_in_polygons_ref_known_answers():
     res = points_in_polygons_ref(p, ring, np.array([0, 16]))
     mask = np.zeros(4000, bool); mask[res[0]] = True
     assert np.array_equal(mask, inside)
+
+
+def test_pip_oracle_reproduces_committed_golden_vectors():
+    from oracle.geometry_ref import points_in_polygons_ref
+    gd = np.load(os.path.join(GOLD, "pip_small.npz"))
+    got = points_in_polygons_ref(gd["points"], gd["verts"], gd["ring_off"])
+    assert np.array_equal(got, gd["pairs"]) and got.shape[1] > 500
