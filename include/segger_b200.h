@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 100
+#define SGB_VERSION 200
 
 #if defined(__GNUC__)
 #define SGB_API __attribute__((visibility("default")))
@@ -298,6 +298,49 @@ SGB_API size_t sgb_pip_fill_scratch_bytes(int64_t E);
 SGB_API int sgb_pip_fill(const double* verts, const int64_t* ring_off, int64_t n_points, int64_t n_poly, double xmin, double ymin,
                  double cell, int nx, int ny, int64_t E, int32_t* edge_index, int64_t ld, void* ws, size_t ws_bytes,
                  void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-side tile slicing and batch assembly and the masked compaction that ends
+ * predict_step.  All selections are order-preserving (flags -> exclusive scan -> scatter), i.e. they equal
+ * torch.nonzero / boolean-mask indexing element for element.  Positions and counts are int32 (n < 2^31).
+ * Workspace for a selection over n items: sgb_select_workspace_bytes(n).  `count` is a device int32.
+ * ---------------------------------------------------------------------------------------- */
+SGB_API size_t sgb_select_workspace_bytes(int64_t n);
+/* sel[0..count) = indices with mask != 0 (ascending); map[i] = rank of i in sel or -1 (either may be NULL). */
+SGB_API int sgb_mask_select(const uint8_t* mask, int64_t n, int32_t* sel, int32_t* map, int32_t* count, void* ws,
+                    size_t ws_bytes, void* stream);
+/* TilePredictDataset._subset (data/tile_dataset.py:218-246): nodes with outer[0] <= x < outer[2] and
+ * outer[1] <= y < outer[3] (the tile grown by the margin), plus predict_mask = inside the closed inner box for the
+ * selected nodes.  pos [n,2] fp32 (bounds are rounded to fp32 first, as torch does) or fp64. */
+SGB_API int sgb_box_select(const void* pos, int pos_f64, int64_t n, const double* outer, const double* inner /*or NULL*/,
+                   int32_t* sel, int32_t* map, uint8_t* inner_mask /*[count]*/, int32_t* count, void* ws,
+                   size_t ws_bytes, void* stream);
+/* dst[k,:] = src[sel[k],:] for k < *count (count == NULL: k < m), rows of row_bytes bytes of any dtype: the node /
+ * edge attribute slicing of HeteroData.subgraph and PartitionDataset._index_select. */
+SGB_API int sgb_gather_rows_bytes(const void* src, int64_t row_bytes, const int32_t* sel, const int32_t* count, int64_t m,
+                          void* dst, void* stream);
+/* PyG bipartite_subgraph(relabel_nodes=True) as HeteroData.subgraph applies it per edge type: keep edges whose
+ * endpoints are both selected (map_* >= 0), relabel them, keep their order; kept_eid (optional) = original edge ids. */
+SGB_API int sgb_edge_subset(const void* edge_index, int idx_bytes, int64_t row_stride, int64_t col_stride, int64_t E,
+                    const int32_t* map_src, int64_t n_src, const int32_t* map_dst, int64_t n_dst, void* out_edge_index,
+                    int64_t ld_out, int32_t* kept_eid, int32_t* count, void* ws, size_t ws_bytes, void* stream);
+/* PartitionDataset.__getitem__ (data/partition/dataset.py:512-579) for K tiles + the DataLoader collate: rows
+ * [starts[k], starts[k] + out_off[k+1] - out_off[k]) of src land at out_off[k] of dst (device int64 arrays). */
+SGB_API int sgb_ranges_gather(const void* src, int64_t row_bytes, const int64_t* starts, const int64_t* out_off, int K,
+                      int64_t total_rows, void* dst, void* stream);
+/* same for edge_index [2, *] (rows ld_in apart): each tile's edges are shifted from tile-local node numbering
+ * (global id - *_starts[k]) to batch numbering (+ *_out_off[k]) for the source and destination node types. */
+SGB_API int sgb_edges_collate(const void* edge_index, int idx_bytes, int64_t ld_in, const int64_t* e_starts,
+                      const int64_t* e_out_off, const int64_t* src_starts, const int64_t* src_out_off,
+                      const int64_t* dst_starts, const int64_t* dst_out_off, int K, int64_t total_edges, void* out,
+                      int64_t ld_out, void* stream);
+/* batch[r] = k for out_off[k] <= r < out_off[k+1] (the PyG Batch.batch vector). */
+SGB_API int sgb_batch_vector(const int64_t* out_off, int K, int64_t total_rows, int64_t* batch, void* stream);
+/* `src_idx[mask], seg_idx[mask], max_sim[mask], gen_idx[mask]` of LitISTEncoder.predict_step
+ * (models/lightning_model.py:294-298) in one pass; outputs sized n, *count rows valid. */
+SGB_API int sgb_compact_predictions(const uint8_t* mask, int64_t n, const int64_t* src_idx, const int64_t* seg_idx,
+                            const float* max_sim, const void* gene, int gene_bytes, int64_t* out_src, int64_t* out_seg,
+                            float* out_sim, void* out_gene, int32_t* count, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

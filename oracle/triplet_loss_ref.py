@@ -32,12 +32,14 @@ class FastTripletSelectorRef:
         self.similarity = cluster_similarity.clamp_min(1e-8)            # :21-23
         self.dissimilarity = (-cluster_similarity).clamp_min(1e-8)      # :24
 
-    def build_index(self, labels: Tensor):
-        """:27-86.  Returns the tuple the sampler reads."""
+    def build_index(self, labels: Tensor, sorted_idx: Optional[Tensor] = None):
+        """:27-86.  Returns the tuple the sampler reads.  ``sorted_idx``: inject the member order the reference's
+        (unstable) ``torch.argsort(labels)`` produced (:41), to compare everything downstream bit for bit."""
         C = self.similarity.size(0)
         counts = torch.bincount(labels, minlength=C).to(torch.long)
         offsets = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])[:-1]
-        sorted_idx = torch.argsort(labels, stable=True)
+        if sorted_idx is None:
+            sorted_idx = torch.argsort(labels, stable=True)
         present = torch.nonzero(counts > 0, as_tuple=False).flatten()
         diss = self.dissimilarity[present][:, present]
         cdf_neg = torch.cumsum(diss / diss.sum(dim=1, keepdim=True), dim=1)
@@ -49,9 +51,10 @@ class FastTripletSelectorRef:
         present_idx[present] = torch.arange(present.numel())
         return counts, offsets, sorted_idx, present, cdf_pos, cdf_neg, present_idx
 
-    def sample_triplets(self, labels: Tensor, uniforms: Optional[Sequence[Tensor]] = None):
+    def sample_triplets(self, labels: Tensor, uniforms: Optional[Sequence[Tensor]] = None,
+                        sorted_idx: Optional[Tensor] = None):
         """:88-125 -> (positives, negatives, dists_pos, dists_neg)."""
-        counts, offsets, sorted_idx, present, cdf_pos, cdf_neg, present_idx = self.build_index(labels)
+        counts, offsets, sorted_idx, present, cdf_pos, cdf_neg, present_idx = self.build_index(labels, sorted_idx)
         N = labels.numel()
         u_pos, u2, u_neg, u3 = uniforms if uniforms is not None else [torch.rand(N) for _ in range(4)]
         pres_idx = present_idx[labels]

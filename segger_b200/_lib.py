@@ -90,6 +90,18 @@ _PROTOS = {
     "sgb_knn_coo_workspace_bytes": (c_sz, [c_i64]),
     "sgb_knn_count_edges": (c_int, [c_vp, c_i64, c_vp, C.POINTER(c_i64), c_vp, c_sz, c_vp]),
     "sgb_knn_table_to_coo": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "sgb_select_workspace_bytes": (c_sz, [c_i64]),
+    "sgb_mask_select": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "sgb_box_select": (c_int, [c_vp, c_int, c_i64, C.POINTER(C.c_double), C.POINTER(C.c_double), c_vp, c_vp, c_vp, c_vp,
+                               c_vp, c_sz, c_vp]),
+    "sgb_gather_rows_bytes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "sgb_edge_subset": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp,
+                                c_sz, c_vp]),
+    "sgb_ranges_gather": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
+    "sgb_edges_collate": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_vp]),
+    "sgb_batch_vector": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp]),
+    "sgb_compact_predictions": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                        c_sz, c_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

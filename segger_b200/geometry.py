@@ -99,6 +99,6 @@ def points_in_polygons(points, verts, ring_off=None, device=None, device_output:
 
 
 def setup_prediction_graph(points, verts, ring_off=None, device=None) -> Tensor:
-    """Shape modes of setup_prediction_graph (neighbors.py:226-238) for already-buffered outlines: int32 CPU
-    edge_index [2, E] = (transcript row, boundary row), as the reference returns it."""
+    """Round-1 entry point for already-buffered outlines; the drop-in with the reference's signature is
+    ``segger_b200.neighbors.setup_prediction_graph(tx, bd, max_k, buffer_ratio, mode)``."""
     return points_in_polygons(points, verts, ring_off, device=device, device_output=False)

@@ -56,6 +56,11 @@ class HeteroBatch:
     @property
     def edge_index_dict(self): return {k: s["edge_index"] for k, s in self._edges.items() if "edge_index" in s}
     @property
+    def num_graphs(self) -> int:
+        """Number of tiles in the batch (PyG ``Batch.num_graphs``): set by the collate, else 1."""
+        return int(getattr(self, "_num_graphs", 1))
+
+    @property
     def node_types(self): return list(self._nodes)
     @property
     def edge_types(self): return list(self._edges)

@@ -26,10 +26,30 @@ TB = ("tx", "belongs", "bd")
 BT = ("bd", "contains", "tx")
 
 
-def _num_batches(batch: Optional[Tensor]) -> int:
+def set_num_graphs(batch: Tensor, num_graphs: int) -> Tensor:
+    """Tag a ``batch`` vector with its number of graphs (what a PyG ``Batch`` knows as ``num_graphs``) so that no
+    device read-back is needed to size the per-tile min/max table.  Batches assembled by ``segger_b200.tiles`` are
+    tagged; an untagged vector is measured once (``batch.max()``, one sync, as the reference does at
+    ist_encoder.py:67-68) and tagged with the result."""
+    batch._sgb_num_graphs = (None if batch.is_inference() else batch._version, int(num_graphs))
+    return batch
+
+
+def _known_num_graphs(batch: Optional[Tensor]) -> Optional[int]:
     if batch is None or batch.numel() == 0:
         return 1
-    return int(batch.max()) + 1   # one host sync, as in the reference (ist_encoder.py:67-68)
+    tag = getattr(batch, "_sgb_num_graphs", None)
+    if tag is not None and tag[0] == (None if batch.is_inference() else batch._version):
+        return tag[1]
+    return None
+
+
+def _num_batches(batch: Optional[Tensor]) -> int:
+    n = _known_num_graphs(batch)
+    if n is None:
+        n = int(batch.max()) + 1
+        set_num_graphs(batch, n)
+    return n
 
 
 class Positional2dEmbedder(Module):
@@ -217,6 +237,37 @@ class ISTEncoder(torch.nn.Module):
                 batch_dict: Dict[str, Tensor]) -> Dict[str, Tensor]:
         for k, x in x_dict.items():
             require_cuda(x)
+        with torch.cuda.device(next(iter(x_dict.values())).device):     # launches go to the tensors' device
+            return self._forward(x_dict, edge_index_dict, pos_dict, batch_dict)
+
+    def _resolve_meta(self, csrs, batch_dict) -> None:
+        """Everything the host must know about a NEW batch, fetched with one device->host copy: the CSR status words
+        (out-of-range node ids raise IndexError, as indexing with them would in the reference) and the number of
+        tiles in each ``batch`` vector.  Nothing is read when the batch was seen before / was assembled by
+        ``segger_b200.tiles`` (tagged) -- the forward then runs without any stream synchronisation."""
+        todo = [c for c in csrs if c._src_unique is None] if (ops.VALIDATE and ops._DEFERRED is None) else []
+        if ops._DEFERRED is not None:
+            ops.validate_csrs(*csrs)
+        need = []
+        if self.use_positional_embeddings and batch_dict is not None:
+            need = [b for b in batch_dict.values() if _known_num_graphs(b) is None]
+        if not todo and not need:
+            return
+        parts = [c.status.to(torch.int64) for c in todo] + [b.max().to(torch.int64).reshape(1) for b in need]
+        vals = torch.cat(parts).tolist()
+        for b, v in zip(need, vals[2 * len(todo):]):
+            set_num_graphs(b, v + 1)
+        ops._apply_status(todo, [vals[2 * i:2 * i + 2] for i in range(len(todo))])
+
+    def _forward(self, x_dict, edge_index_dict, pos_dict, batch_dict):
+        fused = (len(self.conv_layers) > 0 and self.conv_layers[0]._fusable(x_dict, edge_index_dict))
+        csr = None
+        if fused:
+            need_t = torch.is_grad_enabled()
+            N, M = x_dict["tx"].size(0), x_dict["bd"].size(0)
+            csr = {TT: ops.CSR_CACHE.get(edge_index_dict[TT], N, N, need_t),
+                   TB: ops.CSR_CACHE.get(edge_index_dict[TB], N, M, need_t)}
+        self._resolve_meta(list(csr.values()) if csr else [], batch_dict)
         # Input stage (ist_encoder.py:312-320)
         h_dict = {
             k: self._input_stage(k, x, pos_dict[k] if self.use_positional_embeddings else None,
@@ -224,12 +275,7 @@ class ISTEncoder(torch.nn.Module):
             for k, x in x_dict.items()
         }
         # Graph convolutions with GATv2 + GELU (ist_encoder.py:323-325)
-        fused = len(self.conv_layers) > 0 and self.conv_layers[0]._fusable(h_dict, edge_index_dict)
         if fused:
-            need_t = torch.is_grad_enabled()
-            N, M = h_dict["tx"].size(0), h_dict["bd"].size(0)
-            csr = {TT: ops.CSR_CACHE.get(edge_index_dict[TT], N, N, need_t),
-                   TB: ops.CSR_CACHE.get(edge_index_dict[TB], N, M, need_t)}
             for conv_layer in self.conv_layers:
                 h_dict = conv_layer.forward_fused(h_dict, edge_index_dict, apply_gelu=True, csr=csr)
         else:

@@ -56,28 +56,52 @@ class LitISTEncoder(_Base):
     def predict_step(self, batch, batch_idx: int = 0, min_similarity: Optional[float] = None):
         """lightning_model.py:263-298: embeddings -> cosine similarity over tx-neighbors-bd candidate
         edges -> per-transcript max / arg-max -> cell id (or -1); returns CPU tensors
-        (tx.index, seg_idx, max_sim, gene id) restricted to ``predict_mask``."""
-        embeddings = self.forward(batch)
+        (tx.index, seg_idx, max_sim, gene id) restricted to ``predict_mask``.
+
+        Two stream synchronisations per batch, both after all kernels are queued: one 4-byte read of the kept-row
+        count (with the CSR status words folded in), one for the four result copies.  Results are staged through a
+        reusable pinned buffer and returned as ordinary pageable tensors (Lightning keeps every batch's outputs
+        until the predict loop ends -- they must not stay page-locked)."""
         edge_index = batch[PRED].edge_index
-        max_sim, max_idx, seg_idx = ops.score_argmax(
-            embeddings["tx"], embeddings["bd"], edge_index, batch["bd"]["index"], min_similarity)
-        src_idx = batch["tx"]["index"]
-        gen_idx = batch["tx"]["x"]
-        mask = batch["tx"]["predict_mask"]
-        # To cpu, else gpu is held until end of predict loop (reference comment, :296).  Same four CPU tensors as
-        # the reference's `x[mask].cpu()` x 4, produced with one mask scan, four gathers and four asynchronous
-        # copies into pinned host memory behind a single stream synchronisation (instead of four
-        # nonzero + sync + pageable-copy round trips).
-        n_keep = int(mask.sum())
-        idx = None if n_keep == mask.numel() else torch.nonzero(mask).squeeze(1)
-        outs = []
-        for t in (src_idx, seg_idx, max_sim, gen_idx):
-            sel = t if idx is None else t.index_select(0, idx)
-            host = torch.empty(sel.shape, dtype=sel.dtype, device="cpu", pin_memory=True)
-            host.copy_(sel, non_blocking=True)
-            outs.append(host)
-        torch.cuda.current_stream(max_sim.device).synchronize()
-        return tuple(outs)
+        with ops.deferred_validation() as pending:
+            embeddings = self.forward(batch)
+            n_tx, n_bd = embeddings["tx"].size(0), embeddings["bd"].size(0)
+            csr = ops.candidate_csr(edge_index, n_tx, n_bd)
+            pending.append(csr)
+            max_sim, max_idx, seg_idx = ops.score_argmax(
+                embeddings["tx"], embeddings["bd"], edge_index, batch["bd"]["index"], min_similarity, csr=csr)
+            o_src, o_seg, o_sim, o_gene, count = ops.compact_predictions(
+                batch["tx"]["predict_mask"], batch["tx"]["index"], seg_idx, max_sim, batch["tx"]["x"])
+            status = ops.pending_status(pending)
+            head = count.to(torch.int64) if status is None else torch.cat([count.to(torch.int64), status.flatten().to(torch.int64)])
+            head = head.tolist()                                           # sync 1
+            if status is not None:
+                ops.finish_validation(pending, [head[1 + 2 * i:3 + 2 * i] for i in range((len(head) - 1) // 2)])
+        n_keep = head[0]
+        dev = max_sim.device
+        parts = (o_src[:n_keep], o_seg[:n_keep], o_sim[:n_keep], o_gene[:n_keep])
+        nbytes = sum(t.numel() * t.element_size() for t in parts)
+        stage = self._pinned_stage(nbytes)
+        outs, off = [], 0
+        for t in parts:
+            nb = t.numel() * t.element_size()
+            view = stage[off:off + nb].view(t.dtype)
+            view.copy_(t, non_blocking=True)
+            outs.append(view)
+            off += (nb + 15) // 16 * 16
+        torch.cuda.current_stream(dev).synchronize()                       # sync 2
+        # gene ids come back in the dtype the batch holds them in (int32 from setup_heterodata), like `x[mask].cpu()`
+        return tuple(v.clone() for v in outs)
+
+    def _pinned_stage(self, nbytes: int) -> torch.Tensor:
+        """One reusable page-locked staging buffer (grown geometrically), private to this module instance."""
+        need = nbytes + 64
+        buf = getattr(self, "_stage_buf", None)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(max(need, 1 << 20, 2 * (buf.numel() if buf is not None else 0)), dtype=torch.uint8,
+                              pin_memory=True)
+            object.__setattr__(self, "_stage_buf", buf)
+        return buf
 
     # ---- losses (lightning_model.py:86-125,136-262) ---------------------------------------------
     def setup_losses(self, tx_similarity: torch.Tensor, bd_similarity: torch.Tensor) -> None:
@@ -89,10 +113,36 @@ class LitISTEncoder(_Base):
         self.loss_tx = TripletLoss(tx_similarity, margin=self._tx_margin)
         self.loss_bd = MetricLoss(bd_similarity)
 
+    def setup_gene_embedding(self, gene_embedding) -> None:
+        """The embedding part of ``setup`` (:95-106): replace ``model.lin_first['tx']`` by
+        ``Embedding.from_pretrained(weights, freeze=not update_gene_embedding)``.  ``gene_embedding`` is the
+        datamodule's frame (anything with ``.drop(feature_column).to_torch()``), a tensor or an array."""
+        if hasattr(gene_embedding, "drop") and hasattr(gene_embedding, "columns"):
+            feature = "feature_name"                         # StandardTranscriptFields.feature (io/fields.py:110)
+            if feature in list(gene_embedding.columns):
+                gene_embedding = gene_embedding.drop(feature)
+        if hasattr(gene_embedding, "to_torch"):
+            gene_embedding = gene_embedding.to_torch()
+        weights = torch.as_tensor(gene_embedding).to(torch.float)
+        old = self.model.lin_first["tx"]
+        new = torch.nn.Embedding.from_pretrained(weights, freeze=self._freeze_gene_embedding)
+        self.model.lin_first["tx"] = new.to(old.weight.device)
+
     def setup(self, stage=None):
+        """:86-125.  Needs the supplementary data of the data module, like the reference (which raises TypeError for
+        anything but an ISTDataModule): a missing data module or missing similarity matrices are an error here, not
+        a silent skip that would surface later as an AttributeError in get_losses."""
         dm = getattr(getattr(self, "trainer", None), "datamodule", None)
-        if dm is not None and hasattr(dm, "tx_similarity") and hasattr(dm, "bd_similarity"):
-            self.setup_losses(dm.tx_similarity, dm.bd_similarity)
+        if dm is None:
+            raise TypeError("Expected a data module with `tx_similarity` / `bd_similarity` (segger's ISTDataModule) "
+                            "but the trainer has none.")
+        # Only set gene embeddings if exist in data module (:95)
+        if hasattr(dm, "gene_embedding"):
+            self.setup_gene_embedding(dm.gene_embedding)
+        missing = [a for a in ("tx_similarity", "bd_similarity") if not hasattr(dm, a)]
+        if missing:
+            raise TypeError(f"Expected data module to be `ISTDataModule` but {type(dm).__name__} lacks {missing}.")
+        self.setup_losses(dm.tx_similarity, dm.bd_similarity)
         parent = getattr(super(), "setup", None)
         return parent(stage) if callable(parent) else None
 

@@ -120,7 +120,88 @@ def kdtree_neighbors(points: np.ndarray, max_k: int, max_dist: float, chunk_size
     return edge_index, None
 
 
-def setup_transcripts_graph_xy(xy: np.ndarray, max_k: int, max_dist: float) -> Tensor:
-    """neighbors.py:166-180 with the polars frame already reduced to its [N,2] coordinate array."""
-    edge_index, _ = kdtree_neighbors(points=xy, max_k=max_k, max_dist=max_dist)
+def _xy(tx) -> np.ndarray:
+    """[N, 2] coordinates of a transcript table: a frame with 'x' / 'y' columns (polars / pandas: the reference's
+    ``tx[[tx_fields.x, tx_fields.y]].to_numpy()``, neighbors.py:174, TrainingTranscriptFields.x/.y = 'x'/'y'), a
+    mapping of columns, or an [N, 2] array / tensor."""
+    if isinstance(tx, (np.ndarray, Tensor)):
+        return tx
+    if isinstance(tx, dict):
+        return np.stack([np.asarray(tx["x"]), np.asarray(tx["y"])], axis=1)
+    sub = tx[["x", "y"]]
+    return sub.to_numpy() if hasattr(sub, "to_numpy") else np.asarray(sub)
+
+
+def setup_transcripts_graph(tx, max_k: int, max_dist: float) -> Tensor:
+    """neighbors.py:166-180: the tx-neighbors-tx edge_index of a transcript table."""
+    edge_index, _ = kdtree_neighbors(points=_xy(tx), max_k=max_k, max_dist=max_dist)
     return edge_index
+
+
+def setup_transcripts_graph_xy(xy: np.ndarray, max_k: int, max_dist: float) -> Tensor:
+    """Round-1 name of ``setup_transcripts_graph`` for an [N, 2] array; kept as an alias."""
+    return setup_transcripts_graph(xy, max_k, max_dist)
+
+
+def _knn_unbounded(points, query, max_k: int) -> Tensor:
+    """k nearest neighbours without a radius cap on the radius-capped grid kernel: start from the radius that holds
+    ~4k points at the mean density, double it for the queries that found fewer than k until all are full (or the
+    radius covers the whole point set)."""
+    pts = np.asarray(points, dtype=np.float64)
+    n = pts.shape[0]
+    k = min(max_k, n)
+    span = np.maximum(pts.max(0) - pts.min(0), 1e-9)
+    r = float(np.sqrt(4.0 * max(k, 1) * span[0] * span[1] / (np.pi * max(n, 1)))) + 1e-9
+    diag = float(np.hypot(*(np.maximum(pts.max(0), np.asarray(query).max(0)) - np.minimum(pts.min(0), np.asarray(query).min(0))))) + 1.0
+    while True:
+        table, count = knn_table(points, max_k, r, query=query)
+        if r > diag or int((count < k).sum()) == 0:
+            return table
+        r *= 2.0
+
+
+def setup_prediction_graph(tx, bd, max_k: int, buffer_ratio: float, mode: str = "cell", device=None) -> Tensor:
+    """neighbors.py:200-238: the tx-neighbors-bd candidate edges.
+
+    ``mode`` 'cell' / 'nucleus': transcripts strictly inside the outlines of that boundary type, each grown by
+    ``sqrt(area / pi) * buffer_ratio`` -- the point-in-polygon join runs on the GPU (``segger_b200.geometry``);
+    returns int32 CPU ``[2, E]`` = (transcript row, boundary row) like the reference.  ``bd`` is either a
+    GeoDataFrame (buffered on the host with shapely exactly as the reference does, :229-231) or outlines that
+    are buffered already: a ``geometry.PackedPolygons`` or a ``(verts, ring_off)`` pair (``buffer_ratio`` must
+    then be 0 or None).
+    ``mode`` 'uniform': k nearest transcripts of every boundary centroid.  The reference calls
+    ``kdtree_neighbors(points, query, max_k)`` without the mandatory ``max_dist`` there and raises TypeError
+    (SURVEY Appendix B.4); the evident intent -- no radius cap -- is what this does.  ``bd`` may be the
+    GeoDataFrame or an [M, 2] centroid array; rows are (boundary row, transcript row) as that call returns them.
+    """
+    from .geometry import PackedPolygons, pack_rings, points_in_polygons
+    points = _xy(tx)
+    if mode == "uniform":
+        if hasattr(bd, "geometry"):
+            query = bd.geometry.centroid.get_coordinates().values
+        else:
+            query = bd.cpu().numpy() if isinstance(bd, Tensor) else np.asarray(bd)
+        pts = points.cpu().numpy() if isinstance(points, Tensor) else np.asarray(points)
+        table = _knn_unbounded(pts, query, max_k)
+        with torch.no_grad():
+            edge_index, _ = _table_to_coo(table, None, int(pts.shape[0]))
+        return edge_index.cpu()
+    if mode not in ("cell", "nucleus"):
+        raise ValueError(f"setup_prediction_graph: unknown mode '{mode}' (expected 'nucleus', 'cell' or 'uniform')")
+    if isinstance(bd, PackedPolygons):
+        polys = bd
+    elif isinstance(bd, (tuple, list)) and len(bd) == 2:
+        polys = PackedPolygons(*bd)
+    elif hasattr(bd, "geometry"):
+        boundary_type = "cell" if mode == "cell" else "nucleus"          # StandardBoundaryFields (io/fields.py:121-123)
+        polygons = bd[bd["boundary_type"] == boundary_type].geometry
+        buffer_dists = np.sqrt(polygons.area / np.pi) * buffer_ratio
+        polygons = polygons.buffer(buffer_dists).reset_index(drop=True)
+        polys = PackedPolygons(*pack_rings([np.asarray(g.exterior.coords) for g in polygons]))
+        buffer_ratio = 0
+    else:
+        raise TypeError("setup_prediction_graph: `bd` must be a GeoDataFrame, a PackedPolygons or (verts, ring_off)")
+    if buffer_ratio:
+        raise ValueError("setup_prediction_graph: packed outlines are taken as already buffered (pass buffer_ratio=0); "
+                         "buffering is host geometry (shapely), as in the reference")
+    return points_in_polygons(points, polys, device=device, device_output=False)

@@ -276,6 +276,7 @@ class GATv2Conv(torch.nn.Module):
         x_r = self.lin_r(x_dst)
         ei = self._edges(edge_index, x_src.size(0), x_dst.size(0))
         csr = ops.CSR_CACHE.get(ei, x_src.size(0), x_dst.size(0), transpose=torch.is_grad_enabled())
+        ops.validate_csrs(csr)
         training = self.training and self.dropout > 0.0
         seed = ops.new_seed() if training else 0
         out = ops.GATv2AggregateFn.apply(x_l, x_r, self.att, self.bias, csr, H, C, self.negative_slope,

@@ -76,22 +76,18 @@ class EdgeCSR:
     _virtual: Optional["EdgeCSR"] = None
     one_source_per_edge: bool = False       # col is a permutation of [0, E): the backward needs no transposed pass
 
+    def validate(self) -> "EdgeCSR":
+        """One 8-byte D2H read per CSR build (cached): raises IndexError if the edge list held node ids outside
+        [0, n_src) x [0, n_dst) -- what torch / PyG indexing does with such an edge_index -- and records whether
+        the sources are unique and increasing."""
+        if self._src_unique is None:
+            validate_csrs(self, force=True)
+        return self
+
     def sources_unique_increasing(self) -> bool:
         """True iff the edge list names every source at most once, in increasing order (what setup_heterodata emits
-        for tx-belongs-bd).  One 4-byte D2H read per CSR build; cached."""
-        if self._src_unique is None:
-            if self.src_index is None or self.E == 0:
-                self._src_unique = False
-            else:
-                idx = self.src_index
-                flag = torch.empty(1, dtype=torch.int32, device=idx.device)
-                if idx.stride(0) != 1:
-                    idx = idx.contiguous()
-                check(_lib.load().sgb_index_strictly_increasing(ptr(idx), idx.element_size(), idx.numel(), ptr(flag),
-                                                                stream_ptr(idx.device)), "index_strictly_increasing")
-                _count(2)
-                self._src_unique = bool(flag.item())
-        return self._src_unique
+        for tx-belongs-bd)."""
+        return bool(self.validate()._src_unique)
 
     def per_edge_sources(self) -> "EdgeCSR":
         """The same graph with one virtual source node per edge (valid when sources are unique and increasing, so
@@ -122,31 +118,102 @@ def build_csr(edge_index: Tensor, n_src: int, n_dst: int, transpose: bool = True
     t_rowptr = torch.empty(n_src + 1, **i32) if transpose else None
     t_dst = torch.empty(E, **i32) if transpose else None
     t_pos = torch.empty(E, **i32) if transpose else None
-    status = torch.zeros(1, **i32)
+    status = torch.zeros(2, **i32)     # [0]: out-of-range ids seen (set by the build), [1]: sources strictly increasing
     ws = _ws(lib.sgb_csr_workspace_bytes(E), dev)
-    check(lib.sgb_csr_build(ptr(edge_index), edge_index.element_size(), edge_index.stride(0),
-                            edge_index.stride(1), E, n_src, n_dst, ptr(rowptr), ptr(col), ptr(eid),
-                            ptr(t_rowptr), ptr(t_dst), ptr(t_pos), ptr(status), ptr(ws), ws.numel(),
-                            stream_ptr(dev)), "csr_build")
-    _count(12 if transpose else 6)
+    with torch.cuda.device(dev):
+        check(lib.sgb_csr_build(ptr(edge_index), edge_index.element_size(), edge_index.stride(0),
+                                edge_index.stride(1), E, n_src, n_dst, ptr(rowptr), ptr(col), ptr(eid),
+                                ptr(t_rowptr), ptr(t_dst), ptr(t_pos), ptr(status), ptr(ws), ws.numel(),
+                                stream_ptr(dev)), "csr_build")
+        _count(12 if transpose else 6)
+        if E > 0:
+            idx = edge_index[0]
+            if idx.stride(0) != 1:
+                idx = idx.contiguous()
+            check(lib.sgb_index_strictly_increasing(ptr(idx), idx.element_size(), idx.numel(), ptr(status[1:]),
+                                                    stream_ptr(dev)), "index_strictly_increasing")
+            _count(2)
     return EdgeCSR(rowptr, col, eid, t_rowptr, t_dst, t_pos, n_src, n_dst, E, status, edge_index[0])
+
+
+_DEFERRED: Optional[list] = None      # CSRs whose validation a caller folds into a later sync (predict_step)
+VALIDATE = os.environ.get("SEGGER_B200_VALIDATE", "1") != "0"
+
+
+class deferred_validation:
+    """``with deferred_validation() as pending:`` -- CSRs built inside the block are not validated on the spot (no
+    stream sync); the caller reads ``pending_status(pending)`` together with its own results and calls
+    ``finish_validation``.  Used by predict_step, whose results need a device->host copy anyway."""
+
+    def __enter__(self):
+        global _DEFERRED
+        self.prev, _DEFERRED = _DEFERRED, []
+        return _DEFERRED
+
+    def __exit__(self, *exc):
+        global _DEFERRED
+        _DEFERRED = self.prev
+        return False
+
+
+def pending_status(pending: list) -> Optional[Tensor]:
+    todo = [c for c in pending if c._src_unique is None]
+    return torch.stack([c.status for c in todo]) if todo else None
+
+
+def finish_validation(pending: list, flags) -> None:
+    todo = [c for c in pending if c._src_unique is None]
+    _apply_status(todo, flags)
+
+
+def _apply_status(todo, flags) -> None:
+    for c, (bad, inc) in zip(todo, flags):
+        if bad:
+            raise IndexError(f"edge_index holds node ids outside [0, {c.n_src}) x [0, {c.n_dst}) "
+                             f"(E={c.E}); PyG / torch indexing would fail on it")
+        c._src_unique = bool(inc) and c.E > 0
+
+
+def validate_csrs(*csrs: "EdgeCSR", force: bool = False) -> None:
+    """Read the status words of several freshly built CSRs with ONE device->host copy (one stream sync per new
+    graph, none once a CSR has been validated).  Out-of-range node ids raise IndexError: the kernels clamp such ids
+    so they never fault, but a malformed edge_index must not train or predict silently.
+    ``SEGGER_B200_VALIDATE=0`` turns the check (and its sync) off."""
+    todo = [c for c in csrs if c is not None and c._src_unique is None]
+    if not todo:
+        return
+    if not force:
+        if _DEFERRED is not None:
+            _DEFERRED.extend(todo)
+            return
+        if not VALIDATE:
+            return
+    _apply_status(todo, torch.stack([c.status for c in todo]).tolist())
 
 
 class _CsrCache:
     """Tiny LRU so that the layers of one forward (and repeated forwards over a static graph) share
     one CSR build per edge type.  Keyed on storage identity + version; holds the tensor alive."""
 
-    def __init__(self, size: int = 8):
+    def __init__(self, size: int = 4):
+        # one forward touches two edge types (+ the candidate edges of predict_step): 4 entries = the current batch
+        # and nothing older; per-tile batches never hit across steps, so a larger cache would only pin dead graphs
         self.size = size
         self.items = []
 
     def get(self, edge_index: Tensor, n_src: int, n_dst: int, transpose: bool) -> EdgeCSR:
-        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index.stride(), edge_index.dtype,
-               edge_index._version, n_src, n_dst)
+        # inference tensors (Lightning's predict / validation loops run under torch.inference_mode) carry no version
+        # counter; they cannot be mutated in place outside inference mode, so identity + layout is the whole key
+        ver = None if edge_index.is_inference() else edge_index._version
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index.stride(), edge_index.dtype, ver, n_src, n_dst,
+               edge_index.device)
         for i, (k, t, csr) in enumerate(self.items):
-            if k == key and (csr.t_rowptr is not None or not transpose):
-                self.items.append(self.items.pop(i))
-                return csr
+            if k == key:
+                if csr.t_rowptr is not None or not transpose:
+                    self.items.append(self.items.pop(i))
+                    return csr
+                self.items.pop(i)          # built without the transpose: replaced below, not kept beside the new one
+                break
         csr = build_csr(edge_index, n_src, n_dst, transpose)
         self.items.append((key, edge_index, csr))
         if len(self.items) > self.size:
@@ -488,7 +555,10 @@ class SkipGATLayerFn(torch.autograd.Function):
         dev = x_tx.device
         # tx-belongs-bd sources only: when the belongs edge list names each source once (increasing), project just
         # those E_tb rows through tb.lin_l instead of all N transcripts (a third of the layer's projection GEMMs)
-        subset = (F % 4 == 0 and x_tx.size(1) % 4 == 0 and 0 < csr_tb.E <= (3 * N) // 4 and csr_tb.sources_unique_increasing())
+        # (the backward adds the row gradients back with a non-atomic rows_add and walks the transposed arrays in
+        # edge order, hence "unique, increasing" -- without autograd any edge list qualifies and nothing is read back)
+        subset = (F % 4 == 0 and x_tx.size(1) % 4 == 0 and 0 < csr_tb.E <= (3 * N) // 4
+                  and (not exact or csr_tb.sources_unique_increasing()))
         if subset:
             w_cat = torch.cat([wl_tt, wr_tt], 0)
             b_cat = torch.cat([bl_tt, br_tt], 0)
@@ -760,8 +830,13 @@ class OutputStageFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # scoring
 # ------------------------------------------------------------------------------------------------
+def candidate_csr(edge_index: Tensor, n_tx: int, n_bd: int) -> EdgeCSR:
+    """Candidate CSR over transcripts for ``score_argmax``: the "destination" of the sort is the transcript row."""
+    return build_csr(edge_index.flip(0), n_bd, n_tx, transpose=False)
+
+
 def score_argmax(emb_tx: Tensor, emb_bd: Tensor, edge_index: Tensor, bd_index: Optional[Tensor],
-                 min_similarity: Optional[float] = None, eps: float = 1e-8):
+                 min_similarity: Optional[float] = None, eps: float = 1e-8, csr: Optional[EdgeCSR] = None):
     """Fused cosine-similarity / scatter-max / cell lookup over candidate edges [2,E] (tx -> bd).
 
     Returns (max_sim fp32 [N_tx], max_idx int64 [N_tx] (E where a transcript has no candidate),
@@ -772,8 +847,9 @@ def score_argmax(emb_tx: Tensor, emb_bd: Tensor, edge_index: Tensor, bd_index: O
     n_tx, D = emb_tx.shape
     dev = emb_tx.device
     E = edge_index.size(1)
-    # candidate CSR over transcripts: the "destination" of the sort is the transcript row
-    csr = build_csr(edge_index.flip(0), emb_bd.size(0), n_tx, transpose=False)
+    if csr is None:
+        csr = candidate_csr(edge_index, n_tx, emb_bd.size(0))
+        validate_csrs(csr)
     max_sim = torch.empty(n_tx, dtype=torch.float32, device=dev)
     arg = torch.empty(n_tx, dtype=torch.int64, device=dev)
     seg = torch.empty(n_tx, dtype=torch.int64, device=dev)
@@ -788,3 +864,29 @@ def score_argmax(emb_tx: Tensor, emb_bd: Tensor, edge_index: Tensor, bd_index: O
                                        ptr(arg), ptr(seg), stream_ptr(dev)), "score_argmax")
     _count(1)
     return max_sim, arg, seg
+
+
+def compact_predictions(mask: Tensor, src_idx: Tensor, seg_idx: Tensor, max_sim: Tensor, gene: Tensor):
+    """(src_idx[mask], seg_idx[mask], max_sim[mask], gene[mask]) in one pass: -> (out_src, out_seg, out_sim, out_gene,
+    count) with the outputs sized like the inputs (``count`` rows valid, device int32 scalar).  The index plumbing
+    at the end of predict_step (models/lightning_model.py:294-298)."""
+    require_cuda(mask, src_idx, seg_idx, max_sim, gene)
+    n = mask.numel()
+    dev = mask.device
+    m8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else (mask != 0).contiguous().view(torch.uint8)
+    src_idx = src_idx.to(torch.int64).contiguous()
+    seg_idx = seg_idx.to(torch.int64).contiguous()
+    max_sim = max_sim.to(torch.float32).contiguous()
+    if gene.dtype not in (torch.int32, torch.int64):
+        gene = gene.to(torch.int64)
+    gene = gene.contiguous()
+    o_src, o_seg = torch.empty_like(src_idx), torch.empty_like(seg_idx)
+    o_sim, o_gene = torch.empty_like(max_sim), torch.empty_like(gene)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    ws = _ws(lib.sgb_select_workspace_bytes(n), dev)
+    check(lib.sgb_compact_predictions(ptr(m8), n, ptr(src_idx), ptr(seg_idx), ptr(max_sim), ptr(gene), gene.element_size(),
+                                      ptr(o_src), ptr(o_seg), ptr(o_sim), ptr(o_gene), ptr(count), ptr(ws), ws.numel(),
+                                      stream_ptr(dev)), "compact_predictions")
+    _count(5)
+    return o_src, o_seg, o_sim, o_gene, count

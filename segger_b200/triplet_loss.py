@@ -142,8 +142,10 @@ class FastTripletSelector:
         self._index_built = False
 
     @torch.no_grad()
-    def _build_index(self, labels: Tensor) -> None:
-        """:27-86.  Members of a cluster are listed in index order (stable sort through the CSR builder)."""
+    def _build_index(self, labels: Tensor, sorted_idx: Optional[Tensor] = None) -> None:
+        """:27-86.  Members of a cluster are listed in index order (stable sort through the CSR builder); the
+        reference's ``torch.argsort(labels)`` (:41) is not stable, so which member a uniform number selects inside a
+        cluster is pinned only up to that order -- ``sorted_idx`` injects a given order (parity tests)."""
         C = self.similarity.size(0)
         device = labels.device
         N = labels.numel()
@@ -166,7 +168,7 @@ class FastTripletSelector:
         present_idx[present] = torch.arange(present.numel(), device=device)
         self._counts = counts.contiguous()
         self._offsets = offsets_all[:-1].contiguous()
-        self._sorted_idx = csr.eid.to(torch.int64)
+        self._sorted_idx = csr.eid.to(torch.int64) if sorted_idx is None else _i64(sorted_idx).to(device)
         self._present = present.contiguous()
         self._cdf_neg = cdf_neg.contiguous()
         self._cdf_pos = cdf_pos.contiguous()
@@ -175,9 +177,11 @@ class FastTripletSelector:
         self._index_built = True
 
     @torch.no_grad()
-    def sample_triplets(self, labels: Tensor, uniforms=None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    def sample_triplets(self, labels: Tensor, uniforms=None, sorted_idx=None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         require_cuda(labels)
-        self._build_index(labels)
+        if sorted_idx is None:
+            sorted_idx = getattr(self, "_inject_sorted_idx", None)      # parity-test hook (see _build_index)
+        self._build_index(labels, sorted_idx)
         device = labels.device
         N = labels.numel()
         labels = _i64(labels)

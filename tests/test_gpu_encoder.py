@@ -23,6 +23,20 @@ CONFIGS = [  # (in, hidden, out, n_mid, heads)
 ]
 
 
+# Gradients allowed to use the conditioning-relative bar (error vs the fp64 oracle <= 2 x the fp32 oracle's own
+# conditioning noise) instead of the flat 1e-4, each with a hard ceiling; everything else must hold 1e-4 flat.
+# Pattern -> ceiling on the relative error against the fp64 oracle.  Measured table: profiles/r2_grad_parity.json.
+RELAXED = {
+    ".lin_r.weight": 5e-2, ".lin_r.bias": 5e-2, ".lin_l.weight": 2e-2, ".lin_l.bias": 2e-2, ".att": 2e-2,
+    "lin_first": 1e-2, "pos_emb": 1e-2,
+}
+
+
+def _ceiling(name):
+    c = [v for k, v in RELAXED.items() if k in name]
+    return max(c) if c else None
+
+
 def _loss(out, g):
     return sum((out[k] * g[k]).sum() for k in ("tx", "bd"))
 
@@ -83,16 +97,28 @@ def test_istencoder_forward_backward_vs_oracle(cfg):
     ref_grads = {n: p.grad for n, p in ref.named_parameters()}
     ulp_noise = _ulp_perturbed_noise(ref, x, edges, pos, bat, g, grads_64)
     checked = 0
+    table, relaxed = {}, {}
     for n, p in prod.named_parameters():
         if "bd___contains___tx" in n:
             continue
         assert p.grad is not None, n
         noise = max(rel_err(ref_grads[n], grads_64[n]), ulp_noise[n])   # fp32 oracle's own conditioning error
-        assert rel_err(p.grad, grads_64[n]) < max(TOL, 2 * noise), (n, noise)
+        e64, e32 = rel_err(p.grad, grads_64[n]), rel_err(p.grad, ref_grads[n])
+        table[n] = {"err_vs_fp64": e64, "err_vs_fp32_oracle": e32, "oracle_noise": noise}
+        if e64 >= TOL:                                        # needs the relaxed bar: must be on the allow-list
+            relaxed[n] = e64
+            ceil = _ceiling(n)
+            assert ceil is not None, (n, e64, "not on the RELAXED allow-list")
+            assert e64 < min(ceil, max(TOL, 2 * noise)), (n, e64, noise, ceil)
         if noise < TOL / 4:
-            assert rel_err(p.grad, ref_grads[n]) < TOL, n     # well-conditioned: flat 1e-4 vs the fp32 oracle
+            assert e32 < TOL, n                               # well-conditioned: flat 1e-4 vs the fp32 oracle
         checked += 1
     assert checked == len(ref_grads)
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "r2_grad_parity_%d_%d_%d_%d_%d.json" % cfg), "w") as f:
+        json.dump({"config": cfg, "tolerance": TOL, "n_tensors": checked, "relaxed": relaxed, "table": table}, f, indent=1)
+    print(f"cfg {cfg}: {len(relaxed)} of {checked} gradient tensors used the relaxed bar: {relaxed}")
 
 
 def test_istencoder_train_mode_dropout_statistics_and_determinism():

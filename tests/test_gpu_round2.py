@@ -1,0 +1,196 @@
+"""Round-2 GPU tests: Lightning-style inference mode, malformed edge lists, encoder-level dropout parity with the
+kernels' own masks injected into the oracle, and parity at BASELINE.json's own sizes (configs[0] in full, the
+configs[3] model on a 20k-transcript tile)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.ist_encoder_ref import TB, TT, predict_scores_ref
+from segger_b200 import ops
+from segger_b200.hetero import HeteroBatch
+from segger_b200.lightning_model import LitISTEncoder
+from tests.util import PRED, make_models, rel_err, synth_batch, to_dev
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _batch(ts, x, edges, pos, bat):
+    b = HeteroBatch()
+    for k in ("tx", "bd"):
+        b[k]["x"], b[k]["pos"], b[k]["batch"] = x[k], pos[k], bat[k]
+    b["tx"]["index"] = torch.from_numpy(ts.tx_index)
+    b["bd"]["index"] = torch.from_numpy(ts.bd_index)
+    b["tx"]["predict_mask"] = torch.ones(x["tx"].size(0), dtype=torch.bool)
+    for et in (TT, TB, PRED):
+        b[et]["edge_index"] = edges[et]
+    return b
+
+
+def test_forward_and_predict_step_under_inference_mode():
+    """Lightning's predict / validation loops run under torch.inference_mode(): batches moved to the GPU inside it are
+    inference tensors (no version counter).  Forward, predict_step and the generic conv path must all work."""
+    ts, x, edges, pos, bat = synth_batch(3000, 30, seed=11, train_edges=False)
+    torch.manual_seed(0)
+    lit = LitISTEncoder(ts.n_genes, in_channels=32, n_mid_layers=0).cuda().eval()
+    b = _batch(ts, x, edges, pos, bat)
+    with torch.no_grad():
+        want = lit.predict_step(b.cuda(), 0)
+    ops.CSR_CACHE.clear()
+    with torch.inference_mode():
+        bi = b.cuda()
+        assert bi[TT]["edge_index"].is_inference()
+        got = lit.predict_step(bi, 0)
+        emb = lit(bi)
+        again = lit(bi)                                   # second call: CSR cache hit on an inference tensor
+        generic = lit.model.conv_layers[0].conv(
+            {"tx": torch.randn(3000, 64, device="cuda"), "bd": torch.randn(30, 64, device="cuda")},
+            {TT: bi[TT]["edge_index"], TB: bi[TB]["edge_index"]})
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+    assert torch.equal(emb["tx"], again["tx"]) and generic["tx"].shape == (3000, 128)
+    for t in got:
+        assert not t.is_pinned()                          # results are pageable (the predict loop keeps all of them)
+
+
+def test_malformed_edge_index_raises_index_error():
+    """Out-of-range / negative node ids must raise like torch / PyG indexing does, not train on clamped edges."""
+    ts, x, edges, pos, bat = synth_batch(2000, 20, seed=12)
+    torch.manual_seed(0)
+    _, prod = make_models(ts.n_genes, ts.bd_x.shape[1], 32, 64, 64, 0, 2, seed=0)
+    prod.eval()
+    args = lambda e: (to_dev(x), to_dev(e), to_dev(pos), to_dev(bat))
+    prod(*args(edges))                                   # well-formed: fine
+    for bad_val, et, row in ((-1, TT, 0), (2000, TT, 1), (20, TB, 1)):
+        e = {k: v.clone() for k, v in edges.items()}
+        e[et][row, 3] = bad_val
+        ops.CSR_CACHE.clear()
+        with pytest.raises(IndexError):
+            prod(*args(e))
+    # candidate edges of predict_step are checked too (folded into its result read-back)
+    lit = LitISTEncoder(ts.n_genes, in_channels=32, n_mid_layers=0).cuda().eval()
+    b = _batch(ts, x, edges, pos, bat)
+    e = edges[PRED].clone(); e[1, 0] = 20
+    b[PRED]["edge_index"] = e
+    ops.CSR_CACHE.clear()
+    with pytest.raises(IndexError), torch.no_grad():
+        lit.predict_step(b.cuda(), 0)
+    # a standalone CSR reports through validate()
+    csr = ops.build_csr(torch.tensor([[0, 5], [1, 9]]).cuda(), 6, 9)
+    with pytest.raises(IndexError):
+        csr.validate()
+
+
+def test_forward_is_sync_free_on_a_seen_batch():
+    """A batch whose CSRs are validated and whose batch vectors are tagged runs without reading anything back:
+    the forward can be captured in a CUDA graph."""
+    ts, x, edges, pos, bat = synth_batch(4000, 40, seed=13)
+    _, prod = make_models(ts.n_genes, ts.bd_x.shape[1], 32, 64, 64, 0, 2, seed=0)
+    prod.eval()
+    args = (to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
+    with torch.no_grad():
+        want = prod(*args)["tx"].clone()                  # first call: validates + tags (one read-back)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            prod(*args)
+            torch.cuda.current_stream().synchronize()
+            with torch.cuda.graph(g, stream=s):
+                out = prod(*args)["tx"]
+        g.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(out, want)
+
+
+def test_encoder_train_mode_parity_with_the_kernels_own_dropout_masks():
+    """Train mode end to end: the masks the fused kernels regenerate (sgb_dropout_mask of the seeds drawn from torch's
+    generator) are injected into the oracle layer by layer -> outputs and gradients within 1e-4."""
+    in_c, hid, out_c, n_mid, heads = 128, 64, 64, 1, 2
+    ts, x, edges, pos, bat = synth_batch(5000, 50, seed=21)
+    ref, prod = make_models(ts.n_genes, ts.bd_x.shape[1], in_c, hid, out_c, n_mid, heads, seed=4)
+    ref.train(); prod.train()
+    n_layers = n_mid + 2
+    torch.manual_seed(77)
+    seeds = [(ops.new_seed(), ops.new_seed()) for _ in range(n_layers)]      # the order forward_fused draws them in
+    E_tt, E_tb = edges[TT].size(1), edges[TB].size(1)
+    keep = [{TT: ops.dropout_keep_mask(s_tt, E_tt, heads, 0.2, "cuda").cpu(),
+             TB: ops.dropout_keep_mask(s_tb, E_tb, heads, 0.2, "cuda").cpu()} for s_tt, s_tb in seeds]
+    assert 0.15 < 1 - float(keep[0][TT].float().mean()) < 0.25
+    out_r = ref(x, edges, pos, bat, keep_masks=keep)
+    gen = torch.Generator().manual_seed(0)
+    g = {k: torch.randn(v.shape, generator=gen) for k, v in out_r.items()}
+    sum((out_r[k] * g[k]).sum() for k in g).backward()
+    torch.manual_seed(77)
+    out_p = prod(to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
+    sum((out_p[k] * g[k].cuda()).sum() for k in g).backward()
+    for k in ("tx", "bd"):
+        assert rel_err(out_p[k], out_r[k]) < TOL, k
+    rg = dict(ref.named_parameters())
+    errs = {n: rel_err(p.grad, rg[n].grad) for n, p in prod.named_parameters() if p.grad is not None}
+    bad = {n: e for n, e in errs.items() if e >= TOL}
+    assert not bad, bad
+
+
+def _report(name, payload):
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", name), "w") as f:
+        json.dump(payload, f, indent=1)
+
+
+def test_config0_full_size_forward_backward_assignment_vs_oracle():
+    """BASELINE.json configs[0] in full: 50k transcripts / 500 cells, k=5, 2-layer hetero GATv2 hidden=64 heads=2 --
+    kNN graph built by the product, forward + backward + transcript->cell assignment against the CPU oracle."""
+    from oracle import neighbors_ref
+    from segger_b200.neighbors import kdtree_neighbors
+    ts, x, edges, pos, bat = synth_batch(50_000, 500, seed=0, train_edges=False)
+    ei, _ = kdtree_neighbors(ts.tx_pos, 5, 5.0)
+    canon, _, _, _ = neighbors_ref.canonical_knn_table(ts.tx_pos, 5, 5.0)
+    ce, _ = neighbors_ref.knn_to_edge_index(torch.from_numpy(canon), padding_value=50_000)
+    assert torch.equal(ei, ce)                                            # graph edge list bit-exact
+    edges = dict(edges); edges[TT] = ei
+    ref, prod = make_models(ts.n_genes, ts.bd_x.shape[1], 128, 64, 64, 0, 2, seed=0)
+    ref.eval(); prod.eval()
+    out_r = ref(x, edges, pos, bat)
+    gen = torch.Generator().manual_seed(0)
+    g = {k: torch.randn(v.shape, generator=gen) / v.size(0) for k, v in out_r.items()}
+    sum((out_r[k] * g[k]).sum() for k in g).backward()
+    out_p = prod(to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
+    sum((out_p[k] * g[k].cuda()).sum() for k in g).backward()
+    for k in ("tx", "bd"):
+        assert rel_err(out_p[k], out_r[k]) < TOL, k
+    rg = dict(ref.named_parameters())
+    errs = {n: rel_err(p.grad, rg[n].grad) for n, p in prod.named_parameters() if p.grad is not None}
+    _report("r2_cfg0_grad_errors.json", errs)
+    assert max(errs.values()) < TOL, {n: e for n, e in errs.items() if e >= TOL}
+    _, _, seg = ops.score_argmax(out_p["tx"].detach(), out_p["bd"].detach(), edges[PRED].cuda(),
+                                 torch.from_numpy(ts.bd_index).cuda())
+    seg_r, _, _ = predict_scores_ref(out_r["tx"].detach(), out_r["bd"].detach(), edges[PRED], torch.from_numpy(ts.bd_index))
+    agree = float((seg.cpu() == seg_r).float().mean())
+    assert agree >= 0.9999, agree
+
+
+def test_config3_model_on_a_20k_tile_vs_oracle():
+    """The configs[3] model (in=128, hidden=128, heads=4, 3 layers, k=20 neighbours) on a 20k-transcript tile."""
+    ts, x, edges, pos, bat = synth_batch(20_000, 200, seed=3, k=20)
+    ref, prod = make_models(ts.n_genes, ts.bd_x.shape[1], 128, 128, 128, 1, 4, seed=5)
+    ref.eval(); prod.eval()
+    out_r = ref(x, edges, pos, bat)
+    gen = torch.Generator().manual_seed(0)
+    g = {k: torch.randn(v.shape, generator=gen) / v.size(0) for k, v in out_r.items()}
+    sum((out_r[k] * g[k]).sum() for k in g).backward()
+    out_p = prod(to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
+    sum((out_p[k] * g[k].cuda()).sum() for k in g).backward()
+    for k in ("tx", "bd"):
+        assert rel_err(out_p[k], out_r[k]) < TOL, k
+    rg = dict(ref.named_parameters())
+    errs = {n: rel_err(p.grad, rg[n].grad) for n, p in prod.named_parameters() if p.grad is not None}
+    _report("r2_cfg3_grad_errors.json", errs)
+    # fp32-vs-fp32: ill-conditioned tensors are bounded by the allow-list of test_gpu_encoder (they are compared to an
+    # fp64 oracle there); here everything except those must hold the flat bar
+    from tests.test_gpu_encoder import RELAXED
+    bad = {n: e for n, e in errs.items() if e >= TOL and not any(n.endswith(s) or s in n for s in RELAXED)}
+    assert not bad, bad

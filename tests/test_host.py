@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/segger_b200.h but not exported"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS), set(names) ^ set(_lib.EXPORTED_SYMBOLS)
-    assert lib.sgb_version() == 100
+    assert lib.sgb_version() == 200
 
 
 def test_ctypes_prototypes_match_header_arity():
@@ -225,3 +225,42 @@ def test_loss_modules_reject_unsupported_options_without_gpu():
     assert lm.forward(torch.zeros(0, 8), torch.zeros(0, dtype=torch.long)) == 0.
     with pytest.raises(Exception):                      # CPU tensors: the product path has no CPU fallback
         lt.forward(torch.randn(10, 8), torch.randint(0, 4, (10,)))
+
+
+def test_setup_gene_embedding_and_datamodule_contract():
+    """LitISTEncoder.setup (lightning_model.py:86-125): pretrained gene embedding honours update_gene_embedding, and a
+    data module without the similarity matrices is an error at setup time, not an AttributeError in get_losses."""
+    from types import SimpleNamespace
+    from segger_b200.lightning_model import LitISTEncoder
+    w = torch.arange(12, dtype=torch.float64).reshape(4, 3)
+    for update in (True, False):
+        lit = LitISTEncoder(4, in_channels=3, n_mid_layers=0, update_gene_embedding=update)
+        lit.setup_gene_embedding(w.numpy())
+        emb = lit.model.lin_first["tx"]
+        assert isinstance(emb, torch.nn.Embedding) and emb.weight.dtype == torch.float32
+        assert torch.equal(emb.weight.detach(), w.float()) and emb.weight.requires_grad is update
+    lit = LitISTEncoder(4, in_channels=3, n_mid_layers=0, update_gene_embedding=False)
+    sim = torch.eye(3)
+    lit.trainer = SimpleNamespace(datamodule=SimpleNamespace(gene_embedding=w, tx_similarity=sim.clone(),
+                                                             bd_similarity=sim.clone()), max_epochs=2)
+    lit.setup("fit")
+    assert not lit.model.lin_first["tx"].weight.requires_grad and hasattr(lit, "loss_tx") and hasattr(lit, "loss_bd")
+    lit.trainer = SimpleNamespace(datamodule=SimpleNamespace(tx_similarity=sim.clone()), max_epochs=2)
+    with pytest.raises(TypeError):
+        lit.setup("fit")
+    lit.trainer = SimpleNamespace(datamodule=None, max_epochs=2)
+    with pytest.raises(TypeError):
+        lit.setup("fit")
+
+
+def test_graph_setup_drop_ins_accept_frames_and_validate_modes():
+    from segger_b200 import neighbors as nb
+    xy = np.random.default_rng(0).uniform(0, 9, (7, 2)).astype(np.float32)
+    assert np.array_equal(nb._xy({"x": xy[:, 0], "y": xy[:, 1]}), xy)
+    import pandas as pd
+    assert np.array_equal(nb._xy(pd.DataFrame({"x": xy[:, 0], "y": xy[:, 1], "g": 0})), xy)
+    assert nb._xy(xy) is xy
+    with pytest.raises(ValueError):
+        nb.setup_prediction_graph(xy, (np.zeros((0, 2)), np.zeros(1, dtype=np.int64)), 3, 0.0, mode="tile")
+    with pytest.raises(ValueError):          # packed outlines are already buffered
+        nb.setup_prediction_graph(xy, (np.zeros((0, 2)), np.zeros(1, dtype=np.int64)), 3, 0.1, mode="cell")

@@ -65,3 +65,29 @@ def synth_batch(n_tx, n_cells, seed=0, k=5, dist=5.0, train_edges=True):
 
 def to_dev(d, device="cuda"):
     return {k: v.to(device) for k, v in d.items()}
+
+
+class replay_random:
+    """Replay recorded ``torch.rand`` / ``torch.randint`` results (tests/golden/make_reference_golden.py records the
+    draws the reference made) so the product consumes the very same numbers, in the same order, on its own device."""
+
+    def __init__(self, draws):
+        self.draws = list(draws)
+
+    def __enter__(self):
+        self._rand, self._randint = torch.rand, torch.randint
+
+        def take(kind, kwargs):
+            assert self.draws, f"the product drew more random tensors than the reference ({kind})"
+            k, t = self.draws.pop(0)
+            assert k == kind, (k, kind)
+            dev = kwargs.get("device")
+            return t.to(dev) if dev is not None else t.clone()
+
+        torch.rand = lambda *a, **k: take("rand", k)
+        torch.randint = lambda *a, **k: take("randint", k)
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand, torch.randint = self._rand, self._randint
+        return False
