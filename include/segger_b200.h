@@ -134,6 +134,14 @@ SGB_API size_t sgb_linear_workspace_bytes(int64_t N, int64_t K);
 SGB_API int sgb_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b /*or NULL*/,
                    int64_t M, int64_t N, int64_t K, float* y, int64_t ldy, int act,
                    float* y_act /*or NULL*/, int64_t ldya, int exact, void* ws, size_t ws_bytes, void* stream);
+/* y = x W^T + b + table[ids]: forward projection of an input whose leading columns are a row of a small table
+ * selected by an integer id -- ISTEncoder's first layer input is cat(GELU(Embedding[gene]), GELU(pos MLP))
+ * (models/ist_encoder.py:312-320), so that half of the product is table = GELU(Embedding) W_first^T (n_genes rows,
+ * computed once per step) looked up per transcript in the GEMM epilogue instead of K more columns of GEMM.
+ * x [M,K] = the remaining dense columns, w [N,K] the matching weight columns, ids [M] int32|int64, table [*,N]. */
+SGB_API int sgb_linear_fwd_gather(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b /*or NULL*/,
+                          int64_t M, int64_t N, int64_t K, float* y, int64_t ldy, const void* ids, int idx_bytes,
+                          const float* table, int64_t ld_table, int exact, void* ws, size_t ws_bytes, void* stream);
 /* dx = dy W (+ dx if accumulate) ; if act_pre != NULL: dx *= act'(act_pre) (GELU/SiLU backward
  * fused as epilogue).  dy [M,N], w [N,K], dx [M,K]. */
 SGB_API int sgb_linear_dgrad(const float* dy, int64_t ldy, const float* w, int64_t ldw, int64_t M, int64_t N,

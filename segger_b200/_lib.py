@@ -46,6 +46,8 @@ _PROTOS = {
     "sgb_linear_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "sgb_linear_fwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_vp,
                                c_i64, c_int, c_vp, c_sz, c_vp]),
+    "sgb_linear_fwd_gather": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_vp,
+                                      c_i64, c_int, c_vp, c_sz, c_vp]),
     "sgb_linear_dgrad": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_int,
                                  c_vp, c_i64, c_vp, c_sz, c_vp]),
     "sgb_linear_wgrad_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),

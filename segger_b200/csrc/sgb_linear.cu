@@ -38,6 +38,45 @@ extern "C" int sgb_linear_fwd(const float* x, int64_t ldx, const float* w, int64
   return simt_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, act, y_act, ldya, st);
 }
 
+// y = x w^T + b + table[ids]: the forward projection of an input whose first columns are a row of a small table
+// selected by an integer id (ISTEncoder: GELU(Embedding[gene id]), /root/reference/src/segger/models/ist_encoder.py:312-320).
+// x holds only the remaining (dense) columns; table = act(Embedding) w_first^T is computed once per call by the caller.
+namespace {
+template <typename IdxT>
+__global__ void rows_gather_add_kernel(float* __restrict__ y, int64_t ldy, int64_t M, int64_t N, const IdxT* __restrict__ ids,
+                                       const float* __restrict__ tab, int64_t ldt) {
+  const int64_t total = M * N;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t m = t / N, n = t - m * N;
+    y[m * ldy + n] += __ldg(tab + static_cast<int64_t>(ids[m]) * ldt + n);
+  }
+}
+}  // namespace
+
+extern "C" int sgb_linear_fwd_gather(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b, int64_t M,
+                                     int64_t N, int64_t K, float* y, int64_t ldy, const void* ids, int idx_bytes,
+                                     const float* table, int64_t ld_table, int exact, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  int rc = check_dims("linear_fwd_gather", M, N, K);
+  if (rc != SGB_OK) return rc;
+  if (M == 0 || N == 0) return SGB_OK;
+  SGB_REQUIRE(y && x && w && ids && table && K > 0, SGB_ERR_ARG, "linear_fwd_gather: null tensor");
+  SGB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, SGB_ERR_ARG, "linear_fwd_gather: idx_bytes must be 4 or 8");
+  SGB_REQUIRE(ldx >= K && ldw >= K && ldy >= N && ld_table >= N, SGB_ERR_ARG, "linear_fwd_gather: leading dimension too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (exact != 2 && tc_linear_fwd_ok(x, ldx, w, ldw, M, N, K) && !skinny_linear_fwd_ok(x, ldx, M, N, K, y, ldy, nullptr, 0)) {
+    SGB_REQUIRE(ws && ws_bytes >= tc_linear_workspace_bytes(N, K), SGB_ERR_WORKSPACE, "linear_fwd_gather: workspace too small");
+    return tc_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, SGB_ACT_NONE, nullptr, 0, exact, ws, st, ids, idx_bytes, table, ld_table);
+  }
+  rc = sgb_linear_fwd(x, ldx, w, ldw, b, M, N, K, y, ldy, SGB_ACT_NONE, nullptr, 0, exact, ws, ws_bytes, stream);
+  if (rc != SGB_OK) return rc;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(M * N, 256), static_cast<int64_t>(sm_count()) * 16));
+  if (idx_bytes == 8) rows_gather_add_kernel<int64_t><<<blocks, 256, 0, st>>>(y, ldy, M, N, static_cast<const int64_t*>(ids), table, ld_table);
+  else rows_gather_add_kernel<int32_t><<<blocks, 256, 0, st>>>(y, ldy, M, N, static_cast<const int32_t*>(ids), table, ld_table);
+  return check_launch("linear_fwd_gather");
+}
+
 extern "C" int sgb_linear_dgrad(const float* dy, int64_t ldy, const float* w, int64_t ldw, int64_t M, int64_t N,
                                 int64_t K, float* dx, int64_t ldx, int accumulate, int act, const float* act_pre,
                                 int64_t ld_pre, void* ws, size_t ws_bytes, void* stream) {

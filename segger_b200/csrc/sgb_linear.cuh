@@ -32,7 +32,8 @@ bool tc_enabled();
 bool tc_linear_fwd_ok(const float* x, int64_t ldx, const float* w, int64_t ldw, int64_t M, int64_t N, int64_t K);
 size_t tc_linear_workspace_bytes(int64_t N, int64_t K);   // packed (split + swizzled) weights of one fwd / dgrad call
 int tc_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b, int64_t M, int64_t N, int64_t K,
-                  float* y, int64_t ldy, int act, float* y_act, int64_t ldya, int exact, void* ws, cudaStream_t stream);
+                  float* y, int64_t ldy, int act, float* y_act, int64_t ldya, int exact, void* ws, cudaStream_t stream,
+                  const void* gids = nullptr, int gid_bytes = 0, const float* gtab = nullptr, int64_t ld_gtab = 0);
 bool tc_linear_dgrad_ok(const float* dy, int64_t ldy, const float* w, int64_t ldw, int64_t M, int64_t N, int64_t K);
 int tc_linear_dgrad(const float* dy, int64_t ldy, const float* w, int64_t ldw, int64_t M, int64_t N, int64_t K, float* dx,
                     int64_t ldx, int accumulate, int act, const float* act_pre, int64_t ld_pre, void* ws, cudaStream_t stream);

@@ -74,6 +74,12 @@ struct TcParams {
   int colsum_accumulate;    // splits == 1: add into db
   int dbg;                  // timing experiments only (SEGGER_B200_TC_DBG bitmask): results are wrong when set
   const float* Bp;          // B_PACKED: pre-split weights in the shared-memory tile image [n-tile][k-stage][hi|lo]
+  // forward only: C[m, :] += gtab[gids[m], :] -- the part of the product that depends on the row only through a small
+  // integer id (the gene-embedding half of ISTEncoder's first projection) is a table lookup, not a GEMM
+  const void* gids;
+  int gid_bytes;
+  const float* gtab;
+  int64_t ld_gtab;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -563,6 +569,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
                 for (int e = 0; e < 4; ++e) if (n + e < p.N) v[e] += dst[e];
               }
             }
+            if (p.gtab) {
+              const int64_t id = p.gid_bytes == 8 ? static_cast<const int64_t*>(p.gids)[grow]
+                                                  : static_cast<int64_t>(static_cast<const int32_t*>(p.gids)[grow]);
+              const float* tp = p.gtab + id * p.ld_gtab + n;
+              if (whole && (p.ld_gtab % 4 == 0) && aligned16(p.gtab) && (n % 4 == 0)) {
+                const float4 o = ldg4(tp);
+                v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (n + e < p.N) v[e] += __ldg(tp + e);
+              }
+            }
             if (p.act_pre) {
               const float* pp = p.act_pre + grow * p.ld_pre + n;
               float u[4] = {0.f, 0.f, 0.f, 0.f};
@@ -735,8 +753,10 @@ bool tc_linear_fwd_ok(const float* x, int64_t ldx, const float* w, int64_t ldw, 
   return tc_enabled() && M >= 1 && N >= 8 && K >= 8 && K % 4 == 0 && ok_ptr(x, ldx);
 }
 int tc_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* b, int64_t M, int64_t N, int64_t K,
-                  float* y, int64_t ldy, int act, float* y_act, int64_t ldya, int exact, void* ws, cudaStream_t stream) {
+                  float* y, int64_t ldy, int act, float* y_act, int64_t ldya, int exact, void* ws, cudaStream_t stream,
+                  const void* gids, int gid_bytes, const float* gtab, int64_t ld_gtab) {
   TcParams p{};
+  p.gids = gids; p.gid_bytes = gid_bytes; p.gtab = gtab; p.ld_gtab = ld_gtab;
   p.A = x; p.lda = ldx; p.B = w; p.ldb = ldw; p.M = M; p.N = N; p.K = K; p.splits = 1;
   p.k_per_split = ceil_div(K, BK) * BK;
   p.C = y; p.ldc = ldy; p.bias = b; p.act = act; p.C_act = y_act; p.ldca = ldya;

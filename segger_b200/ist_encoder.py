@@ -8,6 +8,7 @@ schedule launches.
 from __future__ import annotations
 
 import logging
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -138,12 +139,16 @@ class SkipGAT(Module):
         return all(isinstance(x_dict[k], Tensor) and x_dict[k].is_cuda for k in ("tx", "bd"))
 
     def forward_fused(self, x_dict: Dict[str, Tensor], edge_index_dict, apply_gelu: bool = False,
-                      csr: Optional[dict] = None) -> Dict[str, Tensor]:
+                      csr: Optional[dict] = None, tx_factor: Optional[Tuple[Tensor, Tensor]] = None) -> Dict[str, Tensor]:
+        """``tx_factor = (ids, table)``: the transcript features are cat(table[ids], x_dict['tx']) in factored form
+        (first layer of ISTEncoder: table = GELU(gene embedding)); see ops.SkipGATLayerFn."""
         tt, tb = self.conv.convs[TT], self.conv.convs[TB]
         x_tx, x_bd = x_dict["tx"].to(torch.float32), x_dict["bd"].to(torch.float32)
-        tt.lin_l.materialize(x_tx.size(-1), x_tx)
-        tt.lin_r.materialize(x_tx.size(-1), x_tx)
-        tb.lin_l.materialize(x_tx.size(-1), x_tx)
+        tx_ids, tx_table = tx_factor if tx_factor is not None else (None, None)
+        in_tx = x_tx.size(-1) + (tx_table.size(-1) if tx_table is not None else 0)
+        tt.lin_l.materialize(in_tx, x_tx)
+        tt.lin_r.materialize(in_tx, x_tx)
+        tb.lin_l.materialize(in_tx, x_tx)
         tb.lin_r.materialize(x_bd.size(-1), x_bd)
         need_t = torch.is_grad_enabled()
         if csr is None:
@@ -160,7 +165,7 @@ class SkipGAT(Module):
             tt.lin_l.weight, tt.lin_l.bias, tt.lin_r.weight, tt.lin_r.bias, tt.att, tt.bias,
             tb.lin_l.weight, tb.lin_l.bias, tb.lin_r.weight, tb.lin_r.bias, tb.att, tb.bias,
             csr_tt, csr_tb, tt.heads, tt.out_channels, tt.negative_slope, tt.dropout, training,
-            seed_tt, seed_tb, apply_gelu, torch.is_grad_enabled())
+            seed_tt, seed_tb, apply_gelu, torch.is_grad_enabled(), tx_ids, tx_table)
         return {"tx": h_tx, "bd": h_bd}
 
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict: Dict[str, Tensor]) -> Dict[str, Tensor]:
@@ -218,7 +223,8 @@ class ISTEncoder(torch.nn.Module):
         logger.debug(f"ISTEncoder: n_genes={n_genes}, in={in_channels}, hidden={hidden_channels}, "
                      f"out={out_channels}, layers={n_mid_layers + 2}")
 
-    def _input_stage(self, k: str, x: Tensor, pos: Optional[Tensor], batch: Optional[Tensor]) -> Tensor:
+    def _input_stage(self, k: str, x: Tensor, pos: Optional[Tensor], batch: Optional[Tensor],
+                     skip_first: bool = False) -> Tensor:
         first = self.lin_first[k]
         feat = w0 = b0 = w2 = b2 = coef = None
         if self.use_positional_embeddings:
@@ -228,7 +234,7 @@ class ISTEncoder(torch.nn.Module):
             w2, b2 = self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias
         if isinstance(first, Embedding):
             return ops.InputStageFn.apply(x, first.weight, None, feat, w0, b0, w2, b2, True, torch.is_grad_enabled(),
-                                          coef)
+                                          coef, skip_first)
         first.materialize(x.size(-1), x)
         return ops.InputStageFn.apply(x, first.weight, first.bias, feat, w0, b0, w2, b2, False,
                                       torch.is_grad_enabled(), coef)
@@ -268,16 +274,29 @@ class ISTEncoder(torch.nn.Module):
             csr = {TT: ops.CSR_CACHE.get(edge_index_dict[TT], N, N, need_t),
                    TB: ops.CSR_CACHE.get(edge_index_dict[TB], N, M, need_t)}
         self._resolve_meta(list(csr.values()) if csr else [], batch_dict)
+        # The transcript input is cat(GELU(Embedding[gene]), GELU(pos MLP)): its first half takes only n_genes distinct
+        # values, so the first layer consumes it in factored form (ids + a [n_genes, in] table) and that half of its
+        # projections becomes a table lookup instead of half the GEMM (ops.SkipGATLayerFn).  SEGGER_B200_FACTOR=0 turns
+        # the factorisation off (A/B and parity of the two forms).
+        first_tx = self.lin_first["tx"] if "tx" in self.lin_first else None
+        factor = (fused and self.use_positional_embeddings and isinstance(first_tx, Embedding)
+                  and first_tx.weight.size(1) % 4 == 0 and x_dict["tx"].dtype in (torch.int32, torch.int64)
+                  and os.environ.get("SEGGER_B200_FACTOR", "1") != "0")
         # Input stage (ist_encoder.py:312-320)
         h_dict = {
             k: self._input_stage(k, x, pos_dict[k] if self.use_positional_embeddings else None,
-                                 batch_dict.get(k) if self.use_positional_embeddings and batch_dict is not None else None)
+                                 batch_dict.get(k) if self.use_positional_embeddings and batch_dict is not None else None,
+                                 skip_first=(factor and k == "tx"))
             for k, x in x_dict.items()
         }
+        tx_factor = None
+        if factor:
+            tx_factor = (x_dict["tx"].contiguous(), _GeluFn.apply(first_tx.weight))
         # Graph convolutions with GATv2 + GELU (ist_encoder.py:323-325)
         if fused:
-            for conv_layer in self.conv_layers:
-                h_dict = conv_layer.forward_fused(h_dict, edge_index_dict, apply_gelu=True, csr=csr)
+            for li, conv_layer in enumerate(self.conv_layers):
+                h_dict = conv_layer.forward_fused(h_dict, edge_index_dict, apply_gelu=True, csr=csr,
+                                                  tx_factor=tx_factor if li == 0 else None)
         else:
             for conv_layer in self.conv_layers:
                 h_dict = conv_layer(h_dict, edge_index_dict)

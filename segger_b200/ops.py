@@ -237,7 +237,8 @@ def new_seed() -> int:
 # ------------------------------------------------------------------------------------------------
 def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE,
                y: Optional[Tensor] = None, y_act: Optional[Tensor] = None,
-               want_pre: bool = True, exact: Optional[bool] = None) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+               want_pre: bool = True, exact: Optional[bool] = None,
+               gather: Optional[Tuple[Tensor, Tensor]] = None) -> Tuple[Optional[Tensor], Optional[Tensor]]:
     """(y, act(y)) with y = x w^T + b.  y / y_act may be preallocated (strided) views.
 
     ``exact``: 0/False = 3-product split-TF32, 1/True = 4 products (fp32-exact operand products);
@@ -260,6 +261,19 @@ def linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE,
     b = _vec(b)
     lib = _lib.load()
     ws = _ws(lib.sgb_linear_workspace_bytes(N, K), dev)
+    if gather is not None:          # y = x w^T + b + table[ids]   (ids [M] int32/int64, table [*, N])
+        if act != ACT_NONE:
+            raise ValueError("linear_fwd: gather cannot be combined with an activation epilogue")
+        ids, table = gather
+        ids = ids if ids.stride(0) == 1 else ids.contiguous()
+        table = _rowmajor(table)
+        if table.size(1) != N or ids.numel() != M:
+            raise ValueError("linear_fwd: gather table / ids do not match the output shape")
+        check(lib.sgb_linear_fwd_gather(ptr(x), _ld(x), ptr(w), _ld(w), ptr(b), M, N, K, ptr(y), _ld(y), ptr(ids),
+                                        ids.element_size(), ptr(table), _ld(table), int(exact), ptr(ws), ws.numel(),
+                                        stream_ptr(dev)), "linear_fwd_gather")
+        _count(2)
+        return y, None
     check(lib.sgb_linear_fwd(ptr(x), _ld(x), ptr(w), _ld(w), ptr(b), M, N, K, ptr(y), _ld(y), act,
                              ptr(y_act), _ld(y_act) if y_act is not None else 0, int(exact),
                              ptr(ws), ws.numel(), stream_ptr(dev)),
@@ -324,6 +338,21 @@ def rows_add(dst: Tensor, ids: Tensor, src: Tensor) -> Tensor:
                                    ptr(src), _ld(src), stream_ptr(dst.device)), "rows_add")
     _count(1)
     return dst
+
+
+def segment_sum_rows(g: Tensor, idx: Tensor, n_rows: int) -> Tensor:
+    """out[r, :] = sum of g[k, :] over k with idx[k] == r, in a fixed order (sort by id + chunked segment sums + ordered
+    merge: deterministic, no atomics).  The backward of a row gather."""
+    g = _rowmajor(g)
+    idx = idx if idx.stride(0) == 1 else idx.contiguous()
+    lib = _lib.load()
+    T, D = g.shape
+    out = torch.empty(n_rows, D, dtype=torch.float32, device=g.device)
+    ws = _ws(lib.sgb_embedding_bwd_workspace_bytes(T, D, n_rows), g.device)
+    check(lib.sgb_embedding_bwd(ptr(g), _ld(g), ptr(idx), idx.element_size(), T, D, n_rows, None, 0, ptr(out), ptr(ws),
+                                ws.numel(), stream_ptr(g.device)), "segment_sum_rows")
+    _count(10)
+    return out
 
 
 class SelectRowsFn(torch.autograd.Function):
@@ -548,29 +577,47 @@ class SkipGATLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_tx, x_bd, wl_tt, bl_tt, wr_tt, br_tt, att_tt, bias_tt, wl_tb, bl_tb, wr_tb, br_tb,
-                att_tb, bias_tb, csr_tt, csr_tb, H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu, exact):
+                att_tb, bias_tb, csr_tt, csr_tb, H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu, exact,
+                tx_ids=None, tx_table=None):
+        """``tx_ids`` / ``tx_table`` (first layer only): the transcript input is cat(tx_table[tx_ids], x_tx) without that
+        concatenation ever being built -- the table half of every tx-side projection is ``tx_table @ W[:, :D1]^T``
+        ([n_genes, .], once per step) looked up per transcript in the GEMM epilogue, its weight gradient is a
+        segment sum of the output gradient by gene id followed by an [n_genes]-row GEMM.  Half the reduction depth of
+        the three largest GEMMs of the step."""
         require_cuda(x_tx, x_bd)
         F = H * C
         N, M = x_tx.size(0), x_bd.size(0)
         dev = x_tx.device
+        D1 = tx_table.size(1) if tx_table is not None else 0
         # tx-belongs-bd sources only: when the belongs edge list names each source once (increasing), project just
         # those E_tb rows through tb.lin_l instead of all N transcripts (a third of the layer's projection GEMMs)
         # (the backward adds the row gradients back with a non-atomic rows_add and walks the transposed arrays in
         # edge order, hence "unique, increasing" -- without autograd any edge list qualifies and nothing is read back)
         subset = (F % 4 == 0 and x_tx.size(1) % 4 == 0 and 0 < csr_tb.E <= (3 * N) // 4
                   and (not exact or csr_tb.sources_unique_increasing()))
+        ids_s = None
+
+        def project(x, w, b, ids):
+            """x w[:, D1:]^T + b (+ the table half, looked up by id)."""
+            if D1 == 0:
+                return linear_fwd(x, w, b, exact=exact)[0]
+            tab, _ = linear_fwd(tx_table, w[:, :D1], None, exact=2)          # [n_genes, rows of w]: fp32 SIMT, tiny
+            return linear_fwd(x, w[:, D1:], b, exact=exact, gather=(ids, tab))[0]
+
         if subset:
             w_cat = torch.cat([wl_tt, wr_tt], 0)
             b_cat = torch.cat([bl_tt, br_tt], 0)
             xs = gather_rows(x_tx, csr_tb.src_index)
-            y_tb, _ = linear_fwd(xs, wl_tb, bl_tb, exact=exact)
+            if D1:
+                ids_s = tx_ids.index_select(0, csr_tb.src_index.long())     # index plumbing: ids of the belongs sources
+            y_tb = project(xs, wl_tb, bl_tb, ids_s)
             csr_tb_run = csr_tb.per_edge_sources()
         else:
             w_cat = torch.cat([wl_tt, wr_tt, wl_tb], 0)
             b_cat = torch.cat([bl_tt, br_tt, bl_tb], 0)
             xs = None
             csr_tb_run = csr_tb
-        y_tx, _ = linear_fwd(x_tx, w_cat, b_cat, exact=exact)
+        y_tx = project(x_tx, w_cat, b_cat, tx_ids)
         if not subset:
             y_tb = y_tx[:, 2 * F:]
         y_bd, _ = linear_fwd(x_bd, wr_tb, br_tb, exact=exact)
@@ -582,8 +629,10 @@ class SkipGATLayerFn(torch.autograd.Function):
         ctx.csr = (csr_tt, csr_tb, csr_tb_run)
         ctx.cfg = (H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu, subset)
         ctx.att_shape = att_tt.shape
+        ctx.D1 = D1
         ctx.save_for_backward(x_tx, x_bd, w_cat, wr_tb, y_tx, y_bd, v_tx, v_bd, att_tt, bias_tt, att_tb, bias_tb,
-                              smax_tt, sden_tt, smax_tb, sden_tb, xs, y_tb if subset else None, wl_tb if subset else None)
+                              smax_tt, sden_tt, smax_tb, sden_tb, xs, y_tb if subset else None, wl_tb if subset else None,
+                              tx_ids, tx_table, ids_s)
         if apply_gelu:
             return h_tx, h_bd
         return v_tx, v_bd
@@ -591,7 +640,8 @@ class SkipGATLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_tx, d_bd):
         (x_tx, x_bd, w_cat, wr_tb, y_tx, y_bd, v_tx, v_bd, att_tt, bias_tt, att_tb, bias_tb, smax_tt, sden_tt,
-         smax_tb, sden_tb, xs, y_tb, wl_tb) = ctx.saved_tensors
+         smax_tb, sden_tb, xs, y_tb, wl_tb, tx_ids, tx_table, ids_s) = ctx.saved_tensors
+        D1 = ctx.D1
         csr_tt, csr_tb, csr_tb_run = ctx.csr
         H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu, subset = ctx.cfg
         F = H * C
@@ -613,20 +663,37 @@ class SkipGATLayerFn(torch.autograd.Function):
         _, _, ga_tb, gb_tb = gatv2_bwd(y_tb, y_bd, att_tb, bias_tb, v_bd, d_bd.contiguous(), apply_gelu,
                                        csr_tb_run, H, C, slope, p_drop, training, seed_tb, smax_tb, sden_tb,
                                        grad_x_l=g_tb, grad_x_r=g_bd)
-        dx_tx = linear_dgrad(g_tx, w_cat) if ctx.needs_input_grad[0] else None
+        d_table = None
+        n_genes = tx_table.size(0) if D1 else 0
+        want_table = D1 > 0 and ctx.needs_input_grad[26]
+
+        def back(g, x, w, ids):
+            """-> (dx of the dense columns, dw [rows, D1 + D2], db) of y = x w[:, D1:]^T + table[ids] + b."""
+            nonlocal d_table
+            dx = linear_dgrad(g, w[:, D1:] if D1 else w) if ctx.needs_input_grad[0] else None
+            dw_dense, db = linear_wgrad(g, x)
+            if D1 == 0:
+                return dx, dw_dense, db
+            seg = segment_sum_rows(g, ids, n_genes)                        # [n_genes, rows]: sum of dL/dy by gene
+            dw_tab, _ = linear_wgrad(seg, tx_table, want_db=False)         # [rows, D1]
+            if want_table:
+                dt = linear_dgrad(seg, w[:, :D1])                          # [n_genes, D1]
+                d_table = dt if d_table is None else d_table.add_(dt)
+            return dx, torch.cat([dw_tab, dw_dense], 1), db
+
+        dx_tx, dw_cat, db_cat = back(g_tx, x_tx, w_cat, tx_ids)
         dx_bd = linear_dgrad(g_bd, wr_tb) if ctx.needs_input_grad[1] else None
-        dw_cat, db_cat = linear_wgrad(g_tx, x_tx)
         dwr_tb, dbr_tb = linear_wgrad(g_bd, x_bd)
         if subset:
+            dxs, dwl_tb, dbl_tb = back(g_tb, xs, wl_tb, ids_s)
             if dx_tx is not None:
-                rows_add(dx_tx, csr_tb.src_index, linear_dgrad(g_tb, wl_tb))
-            dwl_tb, dbl_tb = linear_wgrad(g_tb, xs)
+                rows_add(dx_tx, csr_tb.src_index, dxs)
         else:
             dwl_tb, dbl_tb = dw_cat[2 * F:], db_cat[2 * F:]
         return (dx_tx, dx_bd,
                 dw_cat[:F], db_cat[:F], dw_cat[F:2 * F], db_cat[F:2 * F], ga_tt.view(ctx.att_shape), gb_tt,
                 dwl_tb, dbl_tb, dwr_tb, dbr_tb, ga_tb.view(ctx.att_shape), gb_tb,
-                None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, d_table)
 
 
 def sinusoid_freqs(dim: int, max_period: float, device) -> Tensor:
@@ -717,16 +784,20 @@ class InputStageFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, first_w, first_b, feat, w0, b0, w2, b2, is_embedding, exact, coef=None):
+    def forward(ctx, x, first_w, first_b, feat, w0, b0, w2, b2, is_embedding, exact, coef=None, skip_first=False):
+        """``skip_first``: emit only the positional columns (the embedding half is consumed in factored form by the
+        first SkipGAT layer, see SkipGATLayerFn)."""
         dev = first_w.device
         N = x.size(0)
-        D = first_w.size(1) if is_embedding else first_w.size(0)
+        D = 0 if skip_first else (first_w.size(1) if is_embedding else first_w.size(0))
         use_pos = feat is not None
         dim = w2.size(0) if use_pos else 0
         h = torch.empty(N, D + 2 * dim, dtype=torch.float32, device=dev)
         lib = _lib.load()
         pre_first = None
-        if is_embedding:
+        if skip_first:
+            saved_x = None
+        elif is_embedding:
             ids = x if x.dtype in (torch.int32, torch.int64) else x.long()
             ids = ids.contiguous()
             tab = first_w.contiguous()
@@ -750,6 +821,7 @@ class InputStageFn(torch.autograd.Function):
                 linear_fwd(a0[d * N:(d + 1) * N], w2, b2, ACT_GELU, y=y2[d * N:(d + 1) * N],
                            y_act=h[:, D + d * dim: D + (d + 1) * dim], exact=exact)
         ctx.is_embedding, ctx.use_pos, ctx.D, ctx.dim, ctx.N = is_embedding, use_pos, D, dim, N
+        ctx.skip_first = skip_first
         ctx.has_first_b = first_b is not None
         ctx.save_for_backward(saved_x, first_w, pre_first, feat, w0, y0, a0, w2, y2, coef)
         return h
@@ -762,7 +834,9 @@ class InputStageFn(torch.autograd.Function):
         dh = _rowmajor(dh)
         lib = _lib.load()
         d_first_w = d_first_b = dw0 = db0 = dw2 = db2 = None
-        if ctx.is_embedding:
+        if ctx.skip_first:
+            pass
+        elif ctx.is_embedding:
             if ctx.needs_input_grad[1]:
                 tab = first_w.contiguous()
                 d_first_w = torch.empty_like(tab)
@@ -787,7 +861,7 @@ class InputStageFn(torch.autograd.Function):
             dw0, db0 = linear_wgrad(dy0, feat.view(2 * N, feat.size(-1)))
             if coef is not None:
                 dw0 = linear_dgrad(dw0, coef)                             # [dim, deg] @ [deg, 256]
-        return None, d_first_w, d_first_b, None, dw0, db0, dw2, db2, None, None, None
+        return None, d_first_w, d_first_b, None, dw0, db0, dw2, db2, None, None, None, None
 
 
 class OutputStageFn(torch.autograd.Function):

@@ -26,9 +26,13 @@ CONFIGS = [  # (in, hidden, out, n_mid, heads)
 # Gradients allowed to use the conditioning-relative bar (error vs the fp64 oracle <= 2 x the fp32 oracle's own
 # conditioning noise) instead of the flat 1e-4, each with a hard ceiling; everything else must hold 1e-4 flat.
 # Pattern -> ceiling on the relative error against the fp64 oracle.  Measured table: profiles/r2_grad_parity.json.
+# Measured on B200 (profiles/r2_grad_parity.json): of the 188 gradient tensors of the four configurations only the six
+# lin_r gradients of the tx-neighbors-tx convs of the configs[3]-shaped model (F = 512) exceed 1e-4 against the fp64
+# oracle (worst 3.7e-3) -- and there the fp32 ORACLE ITSELF is 6.3e-3 away from fp64 (LeakyReLU kink flips) while the
+# kernels sit 4e-6 from the fp32 oracle.
 RELAXED = {
-    ".lin_r.weight": 5e-2, ".lin_r.bias": 5e-2, ".lin_l.weight": 2e-2, ".lin_l.bias": 2e-2, ".att": 2e-2,
-    "lin_first": 1e-2, "pos_emb": 1e-2,
+    "<tx___neighbors___tx>.lin_r.weight": 1e-2,
+    "<tx___neighbors___tx>.lin_r.bias": 1e-2,
 }
 
 

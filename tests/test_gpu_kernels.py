@@ -36,7 +36,7 @@ def test_csr_build_bit_exact(E, n_src, n_dst, dtype):
     inv = torch.empty(E, dtype=torch.long)
     inv[order] = torch.arange(E)
     assert torch.equal(csr.t_pos.cpu().long(), inv[torder])
-    assert int(csr.status.item()) == 0
+    assert int(csr.status[0]) == 0
 
 
 @pytest.mark.parametrize("sorted_row", [0, 1])
@@ -68,7 +68,7 @@ def test_csr_strided_view_and_range_flag():
     for f in ("rowptr", "col", "eid", "t_rowptr", "t_dst", "t_pos"):
         assert torch.equal(getattr(a, f), getattr(b, f))
     bad = ei.clone(); bad[1, 5] = 999
-    assert int(ops.build_csr(bad.cuda(), 50, 60).status.item()) == 1
+    assert int(ops.build_csr(bad.cuda(), 50, 60).status[0]) == 1
 
 
 # ---------------------------------------------------------------------------------------------- GATv2

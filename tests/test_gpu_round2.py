@@ -194,3 +194,35 @@ def test_config3_model_on_a_20k_tile_vs_oracle():
     from tests.test_gpu_encoder import RELAXED
     bad = {n: e for n, e in errs.items() if e >= TOL and not any(n.endswith(s) or s in n for s in RELAXED)}
     assert not bad, bad
+
+
+def test_factored_first_layer_equals_dense_form(monkeypatch):
+    """The gene-embedding half of the first layer consumed as (ids, table) -- a table lookup in the GEMM epilogue and a
+    segment sum in the backward -- against the same model run with the concatenated [N, 2*in] input
+    (SEGGER_B200_FACTOR=0): same math, different summation order."""
+    ts, x, edges, pos, bat = synth_batch(6000, 60, seed=31)
+    ref, prod = make_models(ts.n_genes, ts.bd_x.shape[1], 128, 64, 64, 0, 2, seed=2)
+    prod.eval()
+    args = (to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
+    gen = torch.Generator().manual_seed(0)
+    g = {"tx": torch.randn(6000, 64, generator=gen).cuda(), "bd": torch.randn(60, 64, generator=gen).cuda()}
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SEGGER_B200_FACTOR", flag)
+        prod.zero_grad()
+        out = prod(*args)
+        sum((out[k] * g[k]).sum() for k in g).backward()
+        res[flag] = ({k: v.detach().clone() for k, v in out.items()},
+                     {n: p.grad.clone() for n, p in prod.named_parameters() if p.grad is not None})
+    for k in ("tx", "bd"):
+        assert rel_err(res["1"][0][k], res["0"][0][k]) < 1e-5, k
+    assert res["0"][1].keys() == res["1"][1].keys()
+    for n in res["0"][1]:
+        assert rel_err(res["1"][1][n], res["0"][1][n]) < 2e-5, n
+    # frozen pretrained embedding: no table gradient is computed or returned
+    prod.lin_first["tx"].weight.requires_grad_(False)
+    prod.zero_grad()
+    out = prod(*args)
+    sum((out[k] * g[k]).sum() for k in g).backward()
+    assert prod.lin_first["tx"].weight.grad is None
+    assert rel_err(prod.pos_emb.mlp[0].weight.grad, res["1"][1]["pos_emb.mlp.0.weight"]) < 1e-6
