@@ -160,6 +160,70 @@ embedding_bwd_stage1_kernel(const float* __restrict__ dy, int64_t ldy, const uin
   }
 }
 
+// Vector form of stage 1 for plain segment sums (no activation): D % 4 == 0, 16-byte aligned rows.  The chunk's 64
+// (id, row) pairs are loaded once into registers and broadcast by shuffle, and the rows are gathered U at a time
+// (U x V independent 128-bit loads in flight per lane) instead of one dependent perm -> row chain per iteration;
+// the sum inside a segment still runs in sorted order, so the result is bit-identical to the scalar kernel.
+template <int V, int U>
+__global__ void __launch_bounds__(256)
+segment_sum_stage1_vec_kernel(const float* __restrict__ dy, int64_t ldy, const uint32_t* __restrict__ sid,
+                              const uint32_t* __restrict__ perm, const int32_t* __restrict__ rowptr, int64_t N, int D,
+                              int d_base, float* __restrict__ grad_table, float* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t s0 = chunk * kEmbChunk;
+  if (s0 >= N) return;
+  const int n = static_cast<int>(min(static_cast<int64_t>(kEmbChunk), N - s0));
+  static_assert(kEmbChunk == 64, "two register-resident (id, row) pairs per lane");
+  const uint32_t id_a = lane < n ? sid[s0 + lane] : 0xffffffffu, id_b = 32 + lane < n ? sid[s0 + 32 + lane] : 0xffffffffu;
+  const uint32_t pr_a = lane < n ? perm[s0 + lane] : 0u, pr_b = 32 + lane < n ? perm[s0 + 32 + lane] : 0u;
+  const int D4 = D >> 2;
+  float4 acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t g = __shfl_sync(kFull, id_a, 0);
+  int run_start = 0;
+  auto flush = [&](int s_end) {
+    const int64_t gs = s0 + run_start, ge = s0 + s_end;
+    const bool complete = (rowptr[g] == gs) && (rowptr[g + 1] == ge);
+    float* dst = complete ? grad_table + static_cast<int64_t>(g) * D : part + (chunk * 2 + (run_start == 0 ? 0 : 1)) * D;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int q = (d_base >> 2) + lane + 32 * v;
+      if (q < D4) *reinterpret_cast<float4*>(dst + q * 4) = acc[v];
+      acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  for (int s = 0; s < n; s += U) {
+    float4 x[U][V];
+    uint32_t ids[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = s + u;
+      const uint32_t r = k < 32 ? __shfl_sync(kFull, pr_a, k & 31) : __shfl_sync(kFull, pr_b, k & 31);
+      ids[u] = k < 32 ? __shfl_sync(kFull, id_a, k & 31) : __shfl_sync(kFull, id_b, k & 31);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int q = (d_base >> 2) + lane + 32 * v;
+        x[u][v] = (k < n && q < D4) ? ldg4(dy + static_cast<int64_t>(r) * ldy + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = s + u;
+      if (k >= n) break;
+      if (ids[u] != g) {
+        flush(k);
+        g = ids[u];
+        run_start = k;
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) { acc[v].x += x[u][v].x; acc[v].y += x[u][v].y; acc[v].z += x[u][v].z; acc[v].w += x[u][v].w; }
+    }
+  }
+  flush(n);
+}
+
 // Stage 2: warp per table row; segments spanning several chunks are summed in chunk order.
 __global__ void __launch_bounds__(256)
 embedding_bwd_stage2_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int D, const float* __restrict__ part,
@@ -522,7 +586,7 @@ extern "C" int sgb_embedding_bwd(const float* dy, int64_t ldy, const void* ids, 
                                  size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SGB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, SGB_ERR_ARG, "embedding_bwd: idx_bytes must be 4 or 8");
-  SGB_REQUIRE(N >= 0 && N < (int64_t(1) << 31) && D >= 1 && D <= 512 && n_rows >= 1 && n_rows < (int64_t(1) << 31), SGB_ERR_RANGE,
+  SGB_REQUIRE(N >= 0 && N < (int64_t(1) << 31) && D >= 1 && D <= 8192 && n_rows >= 1 && n_rows < (int64_t(1) << 31), SGB_ERR_RANGE,
               "embedding_bwd: size out of range");
   SGB_REQUIRE(grad_table && ws, SGB_ERR_ARG, "embedding_bwd: null tensor");
   EmbWs e = emb_carve(ws, N, n_rows, D);
@@ -540,8 +604,20 @@ extern "C" int sgb_embedding_bwd(const float* dy, int64_t ldy, const void* ids, 
   rc = rowptr_from_sorted(e.sid, N, e.rowptr, n_rows, stream);
   if (rc != SGB_OK) return rc;
   const int64_t chunks = ceil_div(N, kEmbChunk);
-  embedding_bwd_stage1_kernel<<<static_cast<unsigned>(ceil_div(chunks, 8)), 256, 0, stream>>>(
-      dy, ldy, e.sid, e.perm, e.rowptr, N, D, table, table ? act : SGB_ACT_NONE, grad_table, e.part);
+  const unsigned s1_blocks = static_cast<unsigned>(ceil_div(chunks, 8));
+  if (!table && D % 4 == 0 && ldy % 4 == 0 && aligned16(dy) && aligned16(grad_table)) {
+    // plain segment sum: 128-bit gathers, several rows in flight; 1024 columns per pass
+    for (int d0 = 0; d0 < D; d0 += 1024) {
+      const int w = std::min(D - d0, 1024);
+      if (w <= 128) segment_sum_stage1_vec_kernel<1, 8><<<s1_blocks, 256, 0, stream>>>(dy, ldy, e.sid, e.perm, e.rowptr, N, D, d0, grad_table, e.part);
+      else if (w <= 256) segment_sum_stage1_vec_kernel<2, 4><<<s1_blocks, 256, 0, stream>>>(dy, ldy, e.sid, e.perm, e.rowptr, N, D, d0, grad_table, e.part);
+      else if (w <= 512) segment_sum_stage1_vec_kernel<4, 2><<<s1_blocks, 256, 0, stream>>>(dy, ldy, e.sid, e.perm, e.rowptr, N, D, d0, grad_table, e.part);
+      else segment_sum_stage1_vec_kernel<8, 2><<<s1_blocks, 256, 0, stream>>>(dy, ldy, e.sid, e.perm, e.rowptr, N, D, d0, grad_table, e.part);
+    }
+  } else {
+    embedding_bwd_stage1_kernel<<<s1_blocks, 256, 0, stream>>>(
+        dy, ldy, e.sid, e.perm, e.rowptr, N, D, table, table ? act : SGB_ACT_NONE, grad_table, e.part);
+  }
   embedding_bwd_stage2_kernel<<<static_cast<unsigned>(ceil_div(n_rows, 8)), 256, 0, stream>>>(e.rowptr, n_rows, D, e.part, grad_table);
   return check_launch("embedding_bwd");
 }

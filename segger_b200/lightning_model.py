@@ -10,6 +10,8 @@ be handed to a ``Trainer``; otherwise it is a plain ``torch.nn.Module`` with the
 from __future__ import annotations
 
 import math
+import os
+import weakref
 from typing import Optional
 
 import torch
@@ -24,6 +26,35 @@ except Exception:  # noqa: BLE001
     _Base = torch.nn.Module
 
 PRED = ("tx", "neighbors", "bd")
+
+# Results of predict_step live on the host until the predict loop ends (Lightning keeps every batch's outputs).  They
+# are written by asynchronous device->host copies, which need page-locked memory; a budget of page-locked result
+# memory (default 2 GiB, SEGGER_B200_PINNED_RESULT_BYTES) is handed out batch by batch and returned when the tensors
+# are garbage-collected.  Beyond the budget (very large datasets: ~28 B per transcript) results are staged through one
+# reusable pinned buffer and returned as ordinary pageable copies, so locked memory stays bounded.
+_PINNED_BUDGET = int(os.environ.get("SEGGER_B200_PINNED_RESULT_BYTES", str(2 << 30)))
+_pinned_live = 0
+_stage_buf = None
+
+
+def _release(nbytes: int) -> None:
+    global _pinned_live
+    _pinned_live -= nbytes
+
+
+def _result_buffer(nbytes: int):
+    """-> (uint8 pinned host buffer of >= nbytes, pooled): pooled buffers are owned by the returned tensors."""
+    global _pinned_live, _stage_buf
+    need = max(nbytes, 16)
+    if _pinned_live + need <= _PINNED_BUDGET:
+        buf = torch.empty(need, dtype=torch.uint8, pin_memory=True)
+        _pinned_live += need
+        weakref.finalize(buf, _release, need)       # the result views keep `buf` alive through ._base
+        return buf, True
+    if _stage_buf is None or _stage_buf.numel() < need:
+        _stage_buf = torch.empty(max(need, 1 << 20, 2 * (_stage_buf.numel() if _stage_buf is not None else 0)),
+                                 dtype=torch.uint8, pin_memory=True)
+    return _stage_buf, False
 
 
 class LitISTEncoder(_Base):
@@ -59,9 +90,8 @@ class LitISTEncoder(_Base):
         (tx.index, seg_idx, max_sim, gene id) restricted to ``predict_mask``.
 
         Two stream synchronisations per batch, both after all kernels are queued: one 4-byte read of the kept-row
-        count (with the CSR status words folded in), one for the four result copies.  Results are staged through a
-        reusable pinned buffer and returned as ordinary pageable tensors (Lightning keeps every batch's outputs
-        until the predict loop ends -- they must not stay page-locked)."""
+        count (with the CSR status words folded in), one for the four result copies (see ``_result_buffer`` for how
+        page-locked result memory is bounded)."""
         edge_index = batch[PRED].edge_index
         with ops.deferred_validation() as pending:
             embeddings = self.forward(batch)
@@ -80,28 +110,17 @@ class LitISTEncoder(_Base):
         n_keep = head[0]
         dev = max_sim.device
         parts = (o_src[:n_keep], o_seg[:n_keep], o_sim[:n_keep], o_gene[:n_keep])
-        nbytes = sum(t.numel() * t.element_size() for t in parts)
-        stage = self._pinned_stage(nbytes)
+        sizes = [(t.numel() * t.element_size() + 15) // 16 * 16 for t in parts]
+        host, pooled = _result_buffer(sum(sizes))
         outs, off = [], 0
-        for t in parts:
-            nb = t.numel() * t.element_size()
-            view = stage[off:off + nb].view(t.dtype)
+        for t, nb in zip(parts, sizes):
+            view = host[off:off + t.numel() * t.element_size()].view(t.dtype)
             view.copy_(t, non_blocking=True)
             outs.append(view)
-            off += (nb + 15) // 16 * 16
+            off += nb
         torch.cuda.current_stream(dev).synchronize()                       # sync 2
         # gene ids come back in the dtype the batch holds them in (int32 from setup_heterodata), like `x[mask].cpu()`
-        return tuple(v.clone() for v in outs)
-
-    def _pinned_stage(self, nbytes: int) -> torch.Tensor:
-        """One reusable page-locked staging buffer (grown geometrically), private to this module instance."""
-        need = nbytes + 64
-        buf = getattr(self, "_stage_buf", None)
-        if buf is None or buf.numel() < need:
-            buf = torch.empty(max(need, 1 << 20, 2 * (buf.numel() if buf is not None else 0)), dtype=torch.uint8,
-                              pin_memory=True)
-            object.__setattr__(self, "_stage_buf", buf)
-        return buf
+        return tuple(outs) if pooled else tuple(v.clone() for v in outs)
 
     # ---- losses (lightning_model.py:86-125,136-262) ---------------------------------------------
     def setup_losses(self, tx_similarity: torch.Tensor, bd_similarity: torch.Tensor) -> None:
