@@ -760,8 +760,15 @@ static size_t bwd_edge_bytes(int64_t E, int H) {
   return align_up(static_cast<size_t>(E > 0 ? E : 1) * (rec_stride(H) / 2) * sizeof(float));
 }
 
+// the two per-edge arrays double as the sub-warp path's record array: [E][quad_bwd_record_bytes]
+static size_t bwd_edge_region(int64_t E, int H, int C) {
+  const size_t two = 2 * bwd_edge_bytes(E, H);
+  const size_t quad = align_up(static_cast<size_t>(E > 0 ? E : 1) * quad_bwd_record_bytes(H, C));
+  return two > quad ? two : quad;
+}
+
 extern "C" size_t sgb_gatv2_bwd_workspace_bytes(int64_t n_dst, int64_t E, int H, int C) {
-  return 2 * bwd_edge_bytes(E, H) + align_up(bwd_partial_floats(n_dst, H, C) * sizeof(float));
+  return bwd_edge_region(E, H, C) + align_up(bwd_partial_floats(n_dst, H, C) * sizeof(float));
 }
 
 extern "C" int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, int64_t ld_r, const float* att,
@@ -805,7 +812,7 @@ extern "C" int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, i
   p.stat_max = const_cast<float*>(stat_max); p.stat_den = const_cast<float*>(stat_den);
   p.grad_out = grad_out; p.ld_g = ld_g; p.gelu_fused = gelu_fused; p.g_buf = g_buf;
   p.e_delta = reinterpret_cast<float*>(w); p.e_alpha = reinterpret_cast<float*>(w + edge);
-  p.partial = reinterpret_cast<float*>(w + 2 * edge);
+  p.partial = reinterpret_cast<float*>(w + bwd_edge_region(E, H, C));
   p.grad_x_l = grad_x_l; p.grad_x_r = grad_x_r; p.ld_gl = ld_gl; p.ld_gr = ld_gr;
   p.t_rowptr = src_rowptr; p.t_dst = src_dst; p.t_pos = src_pos;
 

@@ -55,6 +55,7 @@ static inline __host__ __device__ int rec_stride(int H) { return (2 * H + 3) / 4
 // sub-warp-per-row path (sgb_gatv2_quad.cu); each returns false if the shape is not covered
 bool quad_fwd_launch(const GatParams& p, cudaStream_t stream);
 size_t quad_bwd_partial_floats(int H, int C);
+size_t quad_bwd_record_bytes(int H, int C);   // bytes of one per-edge record of the sub-warp backward (0: shape not covered)
 bool quad_bwd_launch(const GatParams& p, float* grad_att, float* grad_bias, cudaStream_t stream);
 bool quad_supported(const GatParams& p);   // shape (H, C) and slope covered by the sub-warp kernels
 

@@ -119,6 +119,19 @@ struct Pipe {
   __device__ __forceinline__ void consumed() { cslot = (cslot + 1 == D) ? 0 : cslot + 1; }
 };
 
+// Per-edge record the dst pass leaves for the src pass (dst-CSR order), RSB bytes:
+//   [delta_0..delta_{H-1}, alpha'_0..alpha'_{H-1}, pad to SH floats][one u16 of lrelu'(z) bits per lane of the row group]
+// Lane s of the group owns bit 4t+c for element c of its float4 t (the same lane layout in both passes), so the src pass
+// recovers lrelu'(z_e) without re-gathering x_r[i] and x_l[j].
+__host__ __device__ constexpr int rec_scalars(int H) { return (2 * H + 3) / 4 * 4; }
+__host__ __device__ constexpr int rec_bytes(int H, int LPR) { return (rec_scalars(H) * 4 + 2 * LPR + 15) / 16 * 16; }
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+
 __device__ __forceinline__ float4 lds4(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -298,7 +311,7 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
 template <int V, int LPR, int H, int D, int MINB>
 __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
   constexpr int G = 32 / LPR, VPH = V / H, F4 = V * LPR;
-  constexpr int SH = (2 * H + 3) / 4 * 4;
+  constexpr int SH = rec_scalars(H), RSB = rec_bytes(H, LPR);
   extern __shared__ float4 q_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s = lane % LPR, g = lane / LPR;
@@ -443,6 +456,7 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
           delta[h] = alpha * (dd[h] * ks - cdot[h]);
           alk[h] = alpha * ks;
         }
+        char* rec_ptr = reinterpret_cast<char*>(p.e_delta) + static_cast<int64_t>(c_beg + k) * RSB;
         if (act && !direct_src && s < SH / 4) {
           // record: [delta_0..delta_{H-1}, alpha'_0..alpha'_{H-1}, pad]
           float rec[SH];
@@ -452,15 +466,18 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
 #pragma unroll
           for (int i = 0; i < SH / 4; ++i)
             if (s == i) out4 = make_float4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
-          st4(p.e_delta + (static_cast<int64_t>(c_beg + k) * SH + s * 4), out4);
+          st4(reinterpret_cast<float*>(rec_ptr) + s * 4, out4);
         }
+        uint32_t zbits = 0;
 #pragma unroll
         for (int t = 0; t < V; ++t) {
           const float d = delta[t / VPH], ds = d * slope;     // delta * lrelu'(z): d where z > 0, d * slope elsewhere
           const float4 zz = z[t];
           if (!direct_src) {           // (warp-uniform) the common form: accumulate dL/dz_e into grad_x_r with FMAs
-            gr[t].x = fmaf(zz.x > 0.f ? d : ds, a[t].x, gr[t].x); gr[t].y = fmaf(zz.y > 0.f ? d : ds, a[t].y, gr[t].y);
-            gr[t].z = fmaf(zz.z > 0.f ? d : ds, a[t].z, gr[t].z); gr[t].w = fmaf(zz.w > 0.f ? d : ds, a[t].w, gr[t].w);
+            const bool px = zz.x > 0.f, py = zz.y > 0.f, pz = zz.z > 0.f, pw = zz.w > 0.f;
+            gr[t].x = fmaf(px ? d : ds, a[t].x, gr[t].x); gr[t].y = fmaf(py ? d : ds, a[t].y, gr[t].y);
+            gr[t].z = fmaf(pz ? d : ds, a[t].z, gr[t].z); gr[t].w = fmaf(pw ? d : ds, a[t].w, gr[t].w);
+            zbits |= (px ? 1u : 0u) << (4 * t) | (py ? 2u : 0u) << (4 * t) | (pz ? 4u : 0u) << (4 * t) | (pw ? 8u : 0u) << (4 * t);
           } else {                     // one source per edge: grad_x_l[j] = dL/dz_e + alpha'_e g_i is written here too
             const float4 dz = make_float4((zz.x > 0.f ? d : ds) * a[t].x, (zz.y > 0.f ? d : ds) * a[t].y,
                                           (zz.z > 0.f ? d : ds) * a[t].z, (zz.w > 0.f ? d : ds) * a[t].w);
@@ -473,6 +490,7 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
           }
           fma4(gatt[t], d, zz);
         }
+        if (act && !direct_src) *reinterpret_cast<uint16_t*>(rec_ptr + SH * 4 + 2 * s) = static_cast<uint16_t>(zbits);
       }
       if (rvalid) {
 #pragma unroll
@@ -537,9 +555,13 @@ __global__ void quad_colsum_kernel(const float* __restrict__ partial, int nb, in
 // ================================================================================================
 template <int V, int LPR, int H, int D>
 __global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
+  // grad_x_l[j] = sum over out-edges e = (j -> i) of  delta_e * att (.) lrelu'(z_e)  +  alpha'_e * g_i
+  // Per edge the ring carries the V float4 of g_i this lane consumes and the edge's record (scalars + lrelu' bits):
+  // neither x_r[i] nor the row's own x_l is read.
   constexpr int G = 32 / LPR, VPH = V / H;
-  constexpr int SH = (2 * H + 3) / 4 * 4;
-  constexpr int SLOTS = 2 * V + 1;
+  constexpr int SH = rec_scalars(H), RSB = rec_bytes(H, LPR), RCH = RSB / 16;
+  constexpr int SLOTS = V + 1;
+  static_assert(RCH <= LPR, "the record of a row group is staged by the lanes of that group");
   extern __shared__ float4 q_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s = lane % LPR, g = lane / LPR;
@@ -548,14 +570,15 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const Gat
   pipe.ring = static_cast<uint32_t>(__cvta_generic_to_shared(q_smem + warp * (D * SLOTS * 32) + lane));
 #pragma unroll
   for (int i = 0; i < D * SLOTS; ++i) sts4(pipe.ring + i * 512, make_float4(0.f, 0.f, 0.f, 0.f));
-  // the scalar record of this lane's group sits at lane (g*LPR + i) of slot 2V, i < SH/4
-  const uint32_t rec_off = static_cast<uint32_t>(2 * V * 512) - static_cast<uint32_t>(s * 16);
+  // the record of this lane's group starts at lane g*LPR of slot V
+  const uint32_t rec_off = static_cast<uint32_t>(V * 512) - static_cast<uint32_t>(s * 16);
 
   float4 a[V];
 #pragma unroll
   for (int t = 0; t < V; ++t) a[t] = ldg4(p.att + (t * LPR + s) * 4);
   const float slope = p.slope;
   const float* gsrc = p.gelu_fused ? p.g_buf : p.grad_out;
+  const char* recs = reinterpret_cast<const char*>(p.e_delta);
 
   for (int64_t chunk = static_cast<int64_t>(blockIdx.x) * kQW + warp; chunk < nchunks;
        chunk += static_cast<int64_t>(gridDim.x) * kQW) {
@@ -566,26 +589,20 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const Gat
     const int rp_e = __ldg(p.t_rowptr + min(wrow0 + lane + 1, p.n_src));
     pipe.start(nq, rp_b, rp_e, g);
 
-    const float *nsrc = nullptr, *nsrc2 = nullptr, *nrec = nullptr;
-    bool nact = false, nedge = false;
+    const float* nsrc = nullptr;
+    const char* nrec = nullptr;
+    bool nact = false;
     auto gen = [&]() {
       nact = false;
-      nedge = false;
       if (pipe.pq < pipe.nq) {
-        if (pipe.pk == 0) {
-          const int64_t row = wrow0 + pipe.pq * G + g;
-          nact = row < p.n_src;
-          nsrc = p.x_l + row * p.ld_l;
-        } else {
+        if (pipe.pk > 0) {                     // step 0 of a quad is an empty header (keeps the cursor arithmetic uniform)
           const int k = pipe.pk - 1;
           if (k < pipe.p_deg) {
             nact = true;
-            nedge = true;
             const int64_t i = __ldg(p.t_dst + pipe.p_beg + k);
             const int64_t pos = __ldg(p.t_pos + pipe.p_beg + k);
-            nsrc = p.x_r + i * p.ld_r;
-            nsrc2 = gsrc + i * p.ld_g;
-            nrec = p.e_delta + pos * SH;
+            nsrc = gsrc + i * p.ld_g;
+            nrec = recs + pos * RSB;
           }
         }
         pipe.advance();
@@ -595,11 +612,7 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const Gat
       if (nact) {
 #pragma unroll
         for (int t = 0; t < V; ++t) cp_async16(pipe.issue_addr(t), nsrc + (t * LPR + s) * 4);
-        if (nedge) {
-#pragma unroll
-          for (int t = 0; t < V; ++t) cp_async16(pipe.issue_addr(V + t), nsrc2 + (t * LPR + s) * 4);
-          if (s < SH / 4) cp_async16(pipe.issue_addr(2 * V), nrec + s * 4);
-        }
+        if (s < RCH) cp_async16(pipe.issue_addr(V), nrec + s * 16);
       }
       pipe.committed();
     };
@@ -613,18 +626,15 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const Gat
       const int64_t row = wrow0 + q * G + g;
       const bool rvalid = row < p.n_src;
 
-      issue(); gen(); cp_wait<D - 1>();
-      float4 l[V], acc[V];
-#pragma unroll
-      for (int t = 0; t < V; ++t) {
-        l[t] = lds4(pipe.read_addr(t));
-        acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      issue(); gen(); cp_wait<D - 1>();        // header step: nothing to read
       pipe.consumed();
+      float4 acc[V];
+#pragma unroll
+      for (int t = 0; t < V; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 
       for (int k = 0; k < c_mx; ++k) {
         issue(); gen(); cp_wait<D - 1>();
-        __syncwarp();   // the (delta, alpha') record was staged by other lanes of the group
+        __syncwarp();   // the record was staged by other lanes of the group
         const bool act = k < c_deg;
         float rec[SH];
 #pragma unroll
@@ -632,18 +642,18 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const Gat
           const float4 v = lds4(pipe.read_addr(0) + rec_off + i * 16);
           rec[4 * i] = v.x; rec[4 * i + 1] = v.y; rec[4 * i + 2] = v.z; rec[4 * i + 3] = v.w;
         }
+        const uint32_t zb = lds_u16(pipe.read_addr(0) + rec_off + SH * 4 + 2 * s);
 #pragma unroll
         for (int t = 0; t < V; ++t) {
-          const float4 xr = lds4(pipe.read_addr(t));
-          const float4 gg = lds4(pipe.read_addr(V + t));
+          const float4 gg = lds4(pipe.read_addr(t));
           const float d = act ? rec[t / VPH] : 0.f;
           const float al = act ? rec[H + t / VPH] : 0.f;
-          const float4 z = add4(l[t], xr);
-          const float4 sel = make_float4(z.x > 0.f ? 1.f : slope, z.y > 0.f ? 1.f : slope,
-                                         z.z > 0.f ? 1.f : slope, z.w > 0.f ? 1.f : slope);
-          acc[t].x = fmaf(d * a[t].x, sel.x, acc[t].x); acc[t].y = fmaf(d * a[t].y, sel.y, acc[t].y);
-          acc[t].z = fmaf(d * a[t].z, sel.z, acc[t].z); acc[t].w = fmaf(d * a[t].w, sel.w, acc[t].w);
-          fma4(acc[t], al, gg);
+          const float ds = d * slope;
+          acc[t].x = fmaf((zb >> (4 * t)) & 1u ? d : ds, a[t].x, acc[t].x);
+          acc[t].y = fmaf((zb >> (4 * t + 1)) & 1u ? d : ds, a[t].y, acc[t].y);
+          acc[t].z = fmaf((zb >> (4 * t + 2)) & 1u ? d : ds, a[t].z, acc[t].z);
+          acc[t].w = fmaf((zb >> (4 * t + 3)) & 1u ? d : ds, a[t].w, acc[t].w);
+          if (act) fma4(acc[t], al, gg);
         }
         pipe.consumed();
         __syncwarp();   // all lanes are done with this step's record before its slot is refilled
@@ -693,7 +703,7 @@ int pick_rpw(int64_t n_rows, int G) {
   return static_cast<int>(rpw);
 }
 
-constexpr int kDFwd = 4, kDDst = 4, kDSrc = 3;
+constexpr int kDFwd = 4, kDDst = 4, kDSrc = 4;
 
 template <typename K>
 bool set_smem(K kernel, size_t bytes) {
@@ -746,6 +756,12 @@ static int quad_dst_blocks(int64_t n_dst, int rpw) {
   return static_cast<int>(want < cap ? want : cap);
 }
 
+size_t quad_bwd_record_bytes(int H, int C) {
+  QShape qs;
+  if (!quad_shape(H, C, qs)) return 0;
+  return static_cast<size_t>(rec_bytes(H, qs.lpr));
+}
+
 size_t quad_bwd_partial_floats(int H, int C) {
   QShape qs;
   if (!quad_shape(H, C, qs)) return 0;
@@ -785,7 +801,7 @@ bool quad_bwd_launch(const GatParams& p, float* grad_att, float* grad_bias, cuda
     const unsigned blocks = static_cast<unsigned>(ceil_div(nchunks, kQW));
 #define X(V, L, Hh)                                                                                   \
   if (qs.v == V && qs.lpr == L && p.H == Hh) {                                                        \
-    const size_t smem = static_cast<size_t>(kQW) * kDSrc * (2 * V + 1) * 512;                         \
+    const size_t smem = static_cast<size_t>(kQW) * kDSrc * (V + 1) * 512;                         \
     auto kern = gatv2_bwd_src_quad_kernel<V, L, Hh, kDSrc>;                                           \
     if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                      \
     kern<<<blocks, kQThreads, smem, stream>>>(p, rpw, nchunks);                                       \

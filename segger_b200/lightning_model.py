@@ -37,24 +37,35 @@ _pinned_live = 0
 _stage_buf = None
 
 
-def _release(nbytes: int) -> None:
-    global _pinned_live
-    _pinned_live -= nbytes
+class _Lease:
+    """Page-locked bytes charged to the budget until every result tensor carved from the buffer has been dropped."""
+
+    def __init__(self, nbytes: int):
+        global _pinned_live
+        self.nbytes, self.refs = nbytes, 0
+        _pinned_live += nbytes
+
+    def attach(self, tensor: torch.Tensor) -> None:
+        self.refs += 1
+        weakref.finalize(tensor, self._drop)
+
+    def _drop(self) -> None:
+        global _pinned_live
+        self.refs -= 1
+        if self.refs == 0:
+            _pinned_live -= self.nbytes
 
 
 def _result_buffer(nbytes: int):
-    """-> (uint8 pinned host buffer of >= nbytes, pooled): pooled buffers are owned by the returned tensors."""
-    global _pinned_live, _stage_buf
+    """-> (uint8 pinned host buffer of >= nbytes, lease | None): a leased buffer is owned by the returned tensors."""
+    global _stage_buf
     need = max(nbytes, 16)
     if _pinned_live + need <= _PINNED_BUDGET:
-        buf = torch.empty(need, dtype=torch.uint8, pin_memory=True)
-        _pinned_live += need
-        weakref.finalize(buf, _release, need)       # the result views keep `buf` alive through ._base
-        return buf, True
+        return torch.empty(need, dtype=torch.uint8, pin_memory=True), _Lease(need)
     if _stage_buf is None or _stage_buf.numel() < need:
         _stage_buf = torch.empty(max(need, 1 << 20, 2 * (_stage_buf.numel() if _stage_buf is not None else 0)),
                                  dtype=torch.uint8, pin_memory=True)
-    return _stage_buf, False
+    return _stage_buf, None
 
 
 class LitISTEncoder(_Base):
@@ -111,7 +122,7 @@ class LitISTEncoder(_Base):
         dev = max_sim.device
         parts = (o_src[:n_keep], o_seg[:n_keep], o_sim[:n_keep], o_gene[:n_keep])
         sizes = [(t.numel() * t.element_size() + 15) // 16 * 16 for t in parts]
-        host, pooled = _result_buffer(sum(sizes))
+        host, lease = _result_buffer(sum(sizes))
         outs, off = [], 0
         for t, nb in zip(parts, sizes):
             view = host[off:off + t.numel() * t.element_size()].view(t.dtype)
@@ -120,7 +131,11 @@ class LitISTEncoder(_Base):
             off += nb
         torch.cuda.current_stream(dev).synchronize()                       # sync 2
         # gene ids come back in the dtype the batch holds them in (int32 from setup_heterodata), like `x[mask].cpu()`
-        return tuple(outs) if pooled else tuple(v.clone() for v in outs)
+        if lease is None:
+            return tuple(v.clone() for v in outs)
+        for v in outs:
+            lease.attach(v)
+        return tuple(outs)
 
     # ---- losses (lightning_model.py:86-125,136-262) ---------------------------------------------
     def setup_losses(self, tx_similarity: torch.Tensor, bd_similarity: torch.Tensor) -> None:

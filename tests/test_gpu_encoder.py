@@ -23,63 +23,7 @@ CONFIGS = [  # (in, hidden, out, n_mid, heads)
 ]
 
 
-# Gradients allowed to use the conditioning-relative bar (error vs the fp64 oracle <= 2 x the fp32 oracle's own
-# conditioning noise) instead of the flat 1e-4, each with a hard ceiling; everything else must hold 1e-4 flat.
-# Pattern -> ceiling on the relative error against the fp64 oracle.  Measured table: profiles/r2_grad_parity.json.
-# Measured on B200 (profiles/r2_grad_parity.json): of the 188 gradient tensors of the four configurations only the six
-# lin_r gradients of the tx-neighbors-tx convs of the configs[3]-shaped model (F = 512) exceed 1e-4 against the fp64
-# oracle (worst 3.7e-3) -- and there the fp32 ORACLE ITSELF is 6.3e-3 away from fp64 (LeakyReLU kink flips) while the
-# kernels sit 4e-6 from the fp32 oracle.
-RELAXED = {
-    "<tx___neighbors___tx>.lin_r.weight": 1e-2,
-    "<tx___neighbors___tx>.lin_r.bias": 1e-2,
-}
-
-
-def _ceiling(name):
-    c = [v for k, v in RELAXED.items() if k in name]
-    return max(c) if c else None
-
-
-def _loss(out, g):
-    return sum((out[k] * g[k]).sum() for k in ("tx", "bd"))
-
-
-def _fp64_truth(ref, x, edges, pos, bat, g):
-    """fp64 copy of the oracle: the conditioning yardstick.  Some gradients (e.g. lin_r of a deep
-    layer, whose true value is a small difference of large terms) are only reproducible to ~1e-2
-    in fp32 *by the reference itself*; for those the bar is "no worse than 2x the fp32 oracle's own
-    distance from the fp64 result" instead of the flat 1e-4."""
-    import copy
-    r64 = copy.deepcopy(ref).double()
-    r64.zero_grad()
-    x64 = {"tx": x["tx"], "bd": x["bd"].double()}
-    out = r64(x64, edges, {k: v.double() for k, v in pos.items()}, bat)
-    _loss(out, {k: v.double() for k, v in g.items()}).backward()
-    return out, {n: p.grad for n, p in r64.named_parameters()}
-
-
-def _ulp_perturbed_noise(ref, x, edges, pos, bat, g, grads_64, trials=3):
-    """Second conditioning yardstick: the fp32 oracle re-run with every weight moved by ~half an
-    ulp (relative 2^-24 * N(0,1), fixed seed).  LeakyReLU has a kink: when some z = x_l[j] + x_r[i]
-    lies within an ulp of 0, ANY fp32 implementation may put it on the other side than the fp64
-    run, which moves one output channel of the affected lin_l/lin_r gradient (and, diluted, every
-    gradient upstream of it) by far more than 1e-4 -- measured: one flipped element = 2e-3 of
-    lin_r.weight of the last tx-tx conv (scripts/debug_mix2.py).  Such a gradient is not pinned by
-    the fp32 reference itself, so the bar for it is what ulp-level perturbation does to the oracle."""
-    import copy
-    gen = torch.Generator().manual_seed(1234)
-    worst = {}
-    for _ in range(trials):
-        r = copy.deepcopy(ref)
-        r.zero_grad()
-        with torch.no_grad():
-            for p in r.parameters():
-                p.mul_(1 + 2.0 ** -24 * torch.randn(p.shape, generator=gen))
-        _loss(r(x, edges, pos, bat), g).backward()
-        for n, p in r.named_parameters():
-            worst[n] = max(worst.get(n, 0.0), rel_err(p.grad, grads_64[n]))
-    return worst
+from tests.util import RELAXED, check_forward_backward  # noqa: E402
 
 
 @pytest.mark.parametrize("cfg", CONFIGS)
@@ -87,42 +31,7 @@ def test_istencoder_forward_backward_vs_oracle(cfg):
     in_c, hid, out_c, n_mid, heads = cfg
     ts, x, edges, pos, bat = synth_batch(6000, 60, seed=1)
     ref, prod = make_models(ts.n_genes, ts.bd_x.shape[1], in_c, hid, out_c, n_mid, heads, seed=3)
-    ref.eval(); prod.eval()
-    out_r = ref(x, edges, pos, bat)
-    gen = torch.Generator().manual_seed(0)
-    g = {k: torch.randn(v.shape, generator=gen) for k, v in out_r.items()}
-    _loss(out_r, g).backward()
-    out_64, grads_64 = _fp64_truth(ref, x, edges, pos, bat, g)
-    out_p = prod(to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
-    _loss(out_p, to_dev(g)).backward()
-    for k in ("tx", "bd"):
-        assert out_p[k].shape == out_r[k].shape
-        assert rel_err(out_p[k], out_r[k]) < TOL, k
-    ref_grads = {n: p.grad for n, p in ref.named_parameters()}
-    ulp_noise = _ulp_perturbed_noise(ref, x, edges, pos, bat, g, grads_64)
-    checked = 0
-    table, relaxed = {}, {}
-    for n, p in prod.named_parameters():
-        if "bd___contains___tx" in n:
-            continue
-        assert p.grad is not None, n
-        noise = max(rel_err(ref_grads[n], grads_64[n]), ulp_noise[n])   # fp32 oracle's own conditioning error
-        e64, e32 = rel_err(p.grad, grads_64[n]), rel_err(p.grad, ref_grads[n])
-        table[n] = {"err_vs_fp64": e64, "err_vs_fp32_oracle": e32, "oracle_noise": noise}
-        if e64 >= TOL:                                        # needs the relaxed bar: must be on the allow-list
-            relaxed[n] = e64
-            ceil = _ceiling(n)
-            assert ceil is not None, (n, e64, "not on the RELAXED allow-list")
-            assert e64 < min(ceil, max(TOL, 2 * noise)), (n, e64, noise, ceil)
-        if noise < TOL / 4:
-            assert e32 < TOL, n                               # well-conditioned: flat 1e-4 vs the fp32 oracle
-        checked += 1
-    assert checked == len(ref_grads)
-    import json, os
-    os.makedirs("gpurun_out", exist_ok=True)
-    with open(os.path.join("gpurun_out", "r2_grad_parity_%d_%d_%d_%d_%d.json" % cfg), "w") as f:
-        json.dump({"config": cfg, "tolerance": TOL, "n_tensors": checked, "relaxed": relaxed, "table": table}, f, indent=1)
-    print(f"cfg {cfg}: {len(relaxed)} of {checked} gradient tensors used the relaxed bar: {relaxed}")
+    check_forward_backward(ref, prod, x, edges, pos, bat, "r2_grad_parity_%d_%d_%d_%d_%d" % cfg)
 
 
 def test_istencoder_train_mode_dropout_statistics_and_determinism():

@@ -12,7 +12,7 @@ from oracle.ist_encoder_ref import TB, TT, predict_scores_ref
 from segger_b200 import ops
 from segger_b200.hetero import HeteroBatch
 from segger_b200.lightning_model import LitISTEncoder
-from tests.util import PRED, make_models, rel_err, synth_batch, to_dev
+from tests.util import PRED, check_forward_backward, make_models, rel_err, synth_batch, to_dev
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -167,19 +167,8 @@ def test_config0_full_size_forward_backward_assignment_vs_oracle():
     assert torch.equal(ei, ce)                                            # graph edge list bit-exact
     edges = dict(edges); edges[TT] = ei
     ref, prod = make_models(ts.n_genes, ts.bd_x.shape[1], 128, 64, 64, 0, 2, seed=0)
-    ref.eval(); prod.eval()
-    out_r = ref(x, edges, pos, bat)
-    gen = torch.Generator().manual_seed(0)
-    g = {k: torch.randn(v.shape, generator=gen) / v.size(0) for k, v in out_r.items()}
-    sum((out_r[k] * g[k]).sum() for k in g).backward()
-    out_p = prod(to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
-    sum((out_p[k] * g[k].cuda()).sum() for k in g).backward()
-    for k in ("tx", "bd"):
-        assert rel_err(out_p[k], out_r[k]) < TOL, k
-    rg = dict(ref.named_parameters())
-    errs = {n: rel_err(p.grad, rg[n].grad) for n, p in prod.named_parameters() if p.grad is not None}
-    _report("r2_cfg0_grad_errors.json", errs)
-    assert max(errs.values()) < TOL, {n: e for n, e in errs.items() if e >= TOL}
+    out_r, out_p = check_forward_backward(ref, prod, x, edges, pos, bat, "r2_grad_parity_cfg0_50k", grad_scale=1e-3,
+                                          noise_trials=2)
     _, _, seg = ops.score_argmax(out_p["tx"].detach(), out_p["bd"].detach(), edges[PRED].cuda(),
                                  torch.from_numpy(ts.bd_index).cuda())
     seg_r, _, _ = predict_scores_ref(out_r["tx"].detach(), out_r["bd"].detach(), edges[PRED], torch.from_numpy(ts.bd_index))
@@ -191,23 +180,7 @@ def test_config3_model_on_a_20k_tile_vs_oracle():
     """The configs[3] model (in=128, hidden=128, heads=4, 3 layers, k=20 neighbours) on a 20k-transcript tile."""
     ts, x, edges, pos, bat = synth_batch(20_000, 200, seed=3, k=20)
     ref, prod = make_models(ts.n_genes, ts.bd_x.shape[1], 128, 128, 128, 1, 4, seed=5)
-    ref.eval(); prod.eval()
-    out_r = ref(x, edges, pos, bat)
-    gen = torch.Generator().manual_seed(0)
-    g = {k: torch.randn(v.shape, generator=gen) / v.size(0) for k, v in out_r.items()}
-    sum((out_r[k] * g[k]).sum() for k in g).backward()
-    out_p = prod(to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
-    sum((out_p[k] * g[k].cuda()).sum() for k in g).backward()
-    for k in ("tx", "bd"):
-        assert rel_err(out_p[k], out_r[k]) < TOL, k
-    rg = dict(ref.named_parameters())
-    errs = {n: rel_err(p.grad, rg[n].grad) for n, p in prod.named_parameters() if p.grad is not None}
-    _report("r2_cfg3_grad_errors.json", errs)
-    # fp32-vs-fp32: ill-conditioned tensors are bounded by the allow-list of test_gpu_encoder (they are compared to an
-    # fp64 oracle there); here everything except those must hold the flat bar
-    from tests.test_gpu_encoder import RELAXED
-    bad = {n: e for n, e in errs.items() if e >= TOL and not any(n.endswith(s) or s in n for s in RELAXED)}
-    assert not bad, bad
+    check_forward_backward(ref, prod, x, edges, pos, bat, "r2_grad_parity_cfg3_20k", grad_scale=1e-3, noise_trials=1)
 
 
 def test_factored_first_layer_equals_dense_form(monkeypatch):
@@ -231,8 +204,15 @@ def test_factored_first_layer_equals_dense_form(monkeypatch):
     for k in ("tx", "bd"):
         assert rel_err(res["1"][0][k], res["0"][0][k]) < 1e-5, k
     assert res["0"][1].keys() == res["1"][1].keys()
-    for n in res["0"][1]:
-        assert rel_err(res["1"][1][n], res["0"][1][n]) < 2e-5, n
+    # both forms are fp32 roundings of the same (partly ill-conditioned) gradients: measured against the fp64 oracle the
+    # factored form must be as close as the dense one
+    import copy
+    r64 = copy.deepcopy(ref).double().eval()
+    o64 = r64({"tx": x["tx"], "bd": x["bd"].double()}, edges, {k: v.double() for k, v in pos.items()}, bat)
+    sum((o64[k] * g[k].cpu().double()).sum() for k in g).backward()
+    for n, p in r64.named_parameters():
+        e_dense, e_fact = rel_err(res["0"][1][n], p.grad), rel_err(res["1"][1][n], p.grad)
+        assert e_fact <= 1.5 * e_dense + 1e-5, (n, e_fact, e_dense)
     # frozen pretrained embedding: no table gradient is computed or returned
     prod.lin_first["tx"].weight.requires_grad_(False)
     prod.zero_grad()

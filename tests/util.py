@@ -91,3 +91,92 @@ class replay_random:
     def __exit__(self, *exc):
         torch.rand, torch.randint = self._rand, self._randint
         return False
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Forward / backward parity of the whole encoder against the oracle (fp32 bar 1e-4 relative, BASELINE north_star).
+#
+# Some reference gradients are themselves ill-conditioned in fp32: LeakyReLU has a kink, and when some z = x_l[j] +
+# x_r[i] of a tx-neighbors-tx conv lies within an ulp of 0, ANY fp32 implementation may put it on the other side than
+# the fp64 run, which moves one output channel of that conv's lin_l / lin_r gradient -- and, diluted, every gradient
+# upstream of it -- by far more than 1e-4.  Such a gradient is not pinned by the fp32 reference itself.  The rule:
+#   * every tensor is compared with an fp64 copy of the oracle; error < 1e-4 -> fine (the overwhelming majority);
+#   * a tensor that exceeds 1e-4 must be ON THE ALLOW-LIST below and stay under min(its ceiling, 2 x the fp32 oracle's
+#     own conditioning noise), where the noise is the larger of (fp32 oracle vs fp64 oracle) and (fp32 oracle with every
+#     weight moved by half an ulp vs fp64 oracle);
+#   * a tensor whose oracle noise is < 2.5e-5 must ALSO hold the flat 1e-4 against the fp32 oracle.
+# The allow-list is exactly the parameters at or upstream of the tx-neighbors-tx attention logits; measured tables
+# (which tensors needed it, how large) are in profiles/r2_grad_parity.json.
+RELAXED = {
+    "<tx___neighbors___tx>.lin_r.weight": 5e-2, "<tx___neighbors___tx>.lin_r.bias": 5e-2,
+    "<tx___neighbors___tx>.lin_l.weight": 5e-3, "<tx___neighbors___tx>.lin_l.bias": 5e-3,
+    "<tx___neighbors___tx>.att": 5e-3, "<tx___neighbors___tx>.bias": 5e-3,
+    "<tx___belongs___bd>.": 5e-3,            # layers above the first see the tt conv's output through tx features
+    "lin_first.": 5e-3, "pos_emb.": 5e-3,
+}
+PARITY_TOL = 1e-4
+
+
+def _ceiling(name):
+    c = [v for k, v in RELAXED.items() if k in name]
+    return max(c) if c else None
+
+
+def _loss(out, g):
+    return sum((out[k] * g[k]).sum() for k in ("tx", "bd"))
+
+
+def check_forward_backward(ref, prod, x, edges, pos, bat, tag, grad_scale=1.0, noise_trials=3):
+    """Outputs within 1e-4 of the fp32 oracle; gradients by the rule above.  Writes gpurun_out/<tag>.json."""
+    import copy
+    import json
+    import os
+    ref.eval(); prod.eval()
+    out_r = ref(x, edges, pos, bat)
+    gen = torch.Generator().manual_seed(0)
+    g = {k: torch.randn(v.shape, generator=gen) * grad_scale for k, v in out_r.items()}
+    _loss(out_r, g).backward()
+    r64 = copy.deepcopy(ref).double()
+    r64.zero_grad()
+    x64 = {"tx": x["tx"], "bd": x["bd"].double()}
+    _loss(r64(x64, edges, {k: v.double() for k, v in pos.items()}, bat), {k: v.double() for k, v in g.items()}).backward()
+    grads_64 = {n: p.grad for n, p in r64.named_parameters()}
+    out_p = prod(to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
+    _loss(out_p, to_dev(g)).backward()
+    for k in ("tx", "bd"):
+        assert out_p[k].shape == out_r[k].shape
+        assert rel_err(out_p[k], out_r[k]) < PARITY_TOL, k
+    ref_grads = {n: p.grad for n, p in ref.named_parameters()}
+    gen = torch.Generator().manual_seed(1234)
+    ulp_noise = {}
+    for _ in range(noise_trials):
+        r = copy.deepcopy(ref)
+        r.zero_grad()
+        with torch.no_grad():
+            for p in r.parameters():
+                p.mul_(1 + 2.0 ** -24 * torch.randn(p.shape, generator=gen))
+        _loss(r(x, edges, pos, bat), g).backward()
+        for n, p in r.named_parameters():
+            ulp_noise[n] = max(ulp_noise.get(n, 0.0), rel_err(p.grad, grads_64[n]))
+    table, relaxed, checked = {}, {}, 0
+    for n, p in prod.named_parameters():
+        if "bd___contains___tx" in n:
+            continue
+        assert p.grad is not None, n
+        noise = max(rel_err(ref_grads[n], grads_64[n]), ulp_noise[n])
+        e64, e32 = rel_err(p.grad, grads_64[n]), rel_err(p.grad, ref_grads[n])
+        table[n] = {"err_vs_fp64": e64, "err_vs_fp32_oracle": e32, "oracle_noise": noise}
+        if e64 >= PARITY_TOL:
+            relaxed[n] = e64
+            ceil = _ceiling(n)
+            assert ceil is not None, (n, e64, "not on the RELAXED allow-list")
+            assert e64 < min(ceil, max(PARITY_TOL, 2 * noise)), (n, e64, noise, ceil)
+        if noise < PARITY_TOL / 4:
+            assert e32 < PARITY_TOL, n
+        checked += 1
+    assert checked == len(ref_grads)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", tag + ".json"), "w") as f:
+        json.dump({"tag": tag, "tolerance": PARITY_TOL, "n_tensors": checked, "relaxed": relaxed, "table": table}, f, indent=1)
+    print(f"{tag}: {len(relaxed)} of {checked} gradient tensors used the relaxed bar: {relaxed}")
+    return out_r, out_p
