@@ -332,6 +332,21 @@ SGB_API int sgb_gather_rows_bytes(const void* src, int64_t row_bytes, const int3
 SGB_API int sgb_edge_subset(const void* edge_index, int idx_bytes, int64_t row_stride, int64_t col_stride, int64_t E,
                     const int32_t* map_src, int64_t n_src, const int32_t* map_dst, int64_t n_dst, void* out_edge_index,
                     int64_t ld_out, int32_t* kept_eid, int32_t* count, void* ws, size_t ws_bytes, void* stream);
+/* PartitionDataset._get_permutation (data/partition/dataset.py:375-401): perm = stable argsort of the node labels
+ * (the reference's torch.argsort is not stable; stable = members of a partition keep their original order) and
+ * rowptr[range+1] = the partition pointers (indptr).  status bit 0: a label was outside [0, range). */
+SGB_API size_t sgb_argsort_workspace_bytes(int64_t n);
+SGB_API int sgb_argsort_stable(const void* labels, int idx_bytes, int64_t n, int64_t range, int32_t* perm, int32_t* rowptr,
+                       int32_t* status, void* ws, size_t ws_bytes, void* stream);
+SGB_API int sgb_invert_permutation(const int32_t* perm, int64_t n, int32_t* inv, void* stream);
+/* PartitionDataset._permute_edge_store (:440-506): edges renumbered through the node permutations, stably sorted by the
+ * partition of their source, edges between different partitions DROPPED (:483-494).  lab_* = labels of the ORIGINAL
+ * node ids, inv_* = inverse node permutations.  edge_rowptr[P+2]: [0..P] partition pointers of the kept edges
+ * (edge_rowptr[P] = number kept).  ws: sgb_argsort_workspace_bytes(E) + 4E bytes. */
+SGB_API int sgb_partition_edges(const void* edge_index, int idx_bytes, int64_t row_stride, int64_t col_stride, int64_t E,
+                        const void* lab_src, const void* lab_dst, int lab_bytes, int64_t n_src, int64_t n_dst, int64_t P,
+                        const int32_t* inv_src, const int32_t* inv_dst, void* out_edge_index, int64_t ld_out,
+                        int32_t* kept_eid, int32_t* edge_rowptr, int32_t* status, void* ws, size_t ws_bytes, void* stream);
 /* PartitionDataset.__getitem__ (data/partition/dataset.py:512-579) for K tiles + the DataLoader collate: rows
  * [starts[k], starts[k] + out_off[k+1] - out_off[k]) of src land at out_off[k] of dst (device int64 arrays). */
 SGB_API int sgb_ranges_gather(const void* src, int64_t row_bytes, const int64_t* starts, const int64_t* out_off, int K,

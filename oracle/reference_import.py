@@ -13,6 +13,7 @@ package (`_segger_ref`), with `sys.modules` stubs for exactly the third-party na
   models/ist_encoder.py      torch_geometric.nn           -> oracle.pyg_stub (PyG API over oracle.pyg_ref math)
   models/triplet_loss.py     torch_geometric.data         -> placeholder classes (imported, never used)
   models/lightning_model.py  lightning, torch_scatter, polars, ..io.fields (the real file), ..data.data_module (stub)
+  data/partition/sampler.py  torch_geometric.loader, .dataset (placeholders): the bin-packing functions are pure Python
   data/utils/neighbors.py    geopandas, polars, cupy, cugraph, cuml, cudf (placeholders); ...geometry.points_in_polygons
                              -> oracle.geometry_ref; scipy.spatial.KDTree is the real one
 
@@ -79,6 +80,7 @@ def load() -> SimpleNamespace:
                                       HeteroDictLinear=pyg_stub.HeteroDictLinear, HeteroConv=pyg_stub.HeteroConv),
         "torch_geometric.data": _module("torch_geometric.data", Data=_Placeholder, Batch=_Placeholder,
                                         HeteroData=_Placeholder),
+        "torch_geometric.loader": _module("torch_geometric.loader", DataLoader=_Placeholder, DynamicBatchSampler=_Placeholder),
         "torch_scatter": _module("torch_scatter", scatter_max=lambda src, index, dim_size=None: scatter_max_ref(
             src, index, int(dim_size))),
         "lightning": _module("lightning", LightningModule=pyg_stub.LightningModule),
@@ -92,6 +94,8 @@ def load() -> SimpleNamespace:
         f"{_PKG}.data": _package(f"{_PKG}.data"),
         f"{_PKG}.data.utils": _package(f"{_PKG}.data.utils"),
         f"{_PKG}.geometry": _module(f"{_PKG}.geometry", points_in_polygons=_points_in_polygons),
+        f"{_PKG}.data.partition": _package(f"{_PKG}.data.partition"),
+        f"{_PKG}.data.partition.dataset": _module(f"{_PKG}.data.partition.dataset", PartitionDataset=_Placeholder),
         f"{_PKG}.data.data_module": _module(f"{_PKG}.data.data_module", ISTDataModule=type("ISTDataModule", (), {})),
     }
     saved = {k: sys.modules.get(k) for k in stubs}
@@ -105,7 +109,8 @@ def load() -> SimpleNamespace:
             setattr(sys.modules[f"{_PKG}.io"], n, getattr(fields, n))
         mods = {}
         for key, rel in (("ist_encoder", "models/ist_encoder.py"), ("triplet_loss", "models/triplet_loss.py"),
-                         ("lightning_model", "models/lightning_model.py"), ("neighbors", "data/utils/neighbors.py")):
+                         ("lightning_model", "models/lightning_model.py"), ("neighbors", "data/utils/neighbors.py"),
+                         ("sampler", "data/partition/sampler.py")):
             name = f"{_PKG}." + rel[:-3].replace("/", ".")
             mods[key] = _exec(name, REF_ROOT / rel)
             added.append(name)

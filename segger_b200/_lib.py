@@ -99,6 +99,11 @@ _PROTOS = {
     "sgb_gather_rows_bytes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "sgb_edge_subset": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp,
                                 c_sz, c_vp]),
+    "sgb_argsort_workspace_bytes": (c_sz, [c_i64]),
+    "sgb_argsort_stable": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "sgb_invert_permutation": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "sgb_partition_edges": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp,
+                                    c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "sgb_ranges_gather": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
     "sgb_edges_collate": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_vp]),
     "sgb_batch_vector": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp]),

@@ -174,6 +174,53 @@ __global__ void compact_predictions_kernel(const int32_t* __restrict__ flags, co
   o_gene[k] = gene[i];
 }
 
+// ---- tile partitioning (PartitionDataset.__init__) ---------------------------------------------------------------
+template <typename IdxT>
+__global__ void labels_to_u32_kernel(const IdxT* __restrict__ labels, int64_t n, int64_t range, uint32_t* __restrict__ keys,
+                                     int32_t* __restrict__ status) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t v = static_cast<int64_t>(labels[i]);
+  if (v < 0 || v >= range) {
+    if (status) atomicOr(status, 1);
+    v = v < 0 ? 0 : range - 1;
+  }
+  keys[i] = static_cast<uint32_t>(v);
+}
+__global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) inv[perm[i]] = static_cast<int32_t>(i);
+}
+// key = partition of the edge's source if both endpoints are in the same partition, else P (sorted to the end, dropped)
+template <typename IdxT, typename LabT>
+__global__ void edge_part_keys_kernel(const IdxT* __restrict__ ei, int64_t row_stride, int64_t col_stride, int64_t E,
+                                      const LabT* __restrict__ lab_src, int64_t n_src, const LabT* __restrict__ lab_dst,
+                                      int64_t n_dst, int64_t P, uint32_t* __restrict__ keys, int32_t* __restrict__ status) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t s = static_cast<int64_t>(ei[e * col_stride]), d = static_cast<int64_t>(ei[row_stride + e * col_stride]);
+  uint32_t k = static_cast<uint32_t>(P);
+  if (s < 0 || s >= n_src || d < 0 || d >= n_dst) {
+    if (status) atomicOr(status, 1);
+  } else {
+    const int64_t ls = static_cast<int64_t>(lab_src[s]), ld = static_cast<int64_t>(lab_dst[d]);
+    if (ls == ld && ls >= 0 && ls < P) k = static_cast<uint32_t>(ls);
+  }
+  keys[e] = k;
+}
+template <typename IdxT>
+__global__ void edge_part_fill_kernel(const IdxT* __restrict__ ei, int64_t row_stride, int64_t col_stride,
+                                      const uint32_t* __restrict__ order, const int32_t* __restrict__ rowptr, int64_t P,
+                                      const int32_t* __restrict__ inv_src, const int32_t* __restrict__ inv_dst,
+                                      IdxT* __restrict__ out, int64_t ld_out, int32_t* __restrict__ kept_eid) {
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= rowptr[P]) return;
+  const int64_t e = order[k];
+  out[k] = static_cast<IdxT>(inv_src[ei[e * col_stride]]);
+  out[ld_out + k] = static_cast<IdxT>(inv_dst[ei[row_stride + e * col_stride]]);
+  if (kept_eid) kept_eid[k] = static_cast<int32_t>(e);
+}
+
 struct SelWs {
   int32_t *flags, *scan;
   void* scan_ws;
@@ -208,6 +255,89 @@ int finish_select(const SelWs& c, int64_t n, int32_t* sel, int32_t* map, int32_t
 using namespace sgb;
 
 extern "C" size_t sgb_select_workspace_bytes(int64_t n) { return carve_sel(nullptr, n).total; }
+
+// workspace: keys + sorted keys + sort scratch
+extern "C" size_t sgb_argsort_workspace_bytes(int64_t n) {
+  return 2 * align_up(static_cast<size_t>(n > 0 ? n : 1) * 4) + sort_pairs_workspace_bytes(n);
+}
+
+extern "C" int sgb_argsort_stable(const void* labels, int idx_bytes, int64_t n, int64_t range, int32_t* perm,
+                                  int32_t* rowptr, int32_t* status, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(idx_bytes == 4 || idx_bytes == 8, SGB_ERR_ARG, "argsort_stable: idx_bytes must be 4 or 8");
+  SGB_REQUIRE(n >= 0 && n < (int64_t(1) << 31) && range >= 1 && range < (int64_t(1) << 31), SGB_ERR_RANGE, "argsort_stable: size out of range");
+  SGB_REQUIRE(ws && ws_bytes >= sgb_argsort_workspace_bytes(n), SGB_ERR_WORKSPACE, "argsort_stable: workspace too small");
+  if (n == 0) {
+    if (rowptr) cudaMemsetAsync(rowptr, 0, static_cast<size_t>(range + 1) * 4, stream);
+    return check_launch("argsort_stable(empty)");
+  }
+  SGB_REQUIRE(labels && perm, SGB_ERR_ARG, "argsort_stable: null argument");
+  const size_t nb = align_up(static_cast<size_t>(n) * 4);
+  uint32_t* keys = static_cast<uint32_t*>(ws);
+  uint32_t* skeys = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + nb);
+  void* sort_ws = static_cast<char*>(ws) + 2 * nb;
+  if (idx_bytes == 8) labels_to_u32_kernel<int64_t><<<blocks_for(n), kT, 0, stream>>>(static_cast<const int64_t*>(labels), n, range, keys, status);
+  else labels_to_u32_kernel<int32_t><<<blocks_for(n), kT, 0, stream>>>(static_cast<const int32_t*>(labels), n, range, keys, status);
+  int rc = sort_pairs(keys, nullptr, skeys, reinterpret_cast<uint32_t*>(perm), n, bits_for(range), sort_ws,
+                      sort_pairs_workspace_bytes(n), stream, true);
+  if (rc != SGB_OK) return rc;
+  if (rowptr) {
+    rc = rowptr_from_sorted(skeys, n, rowptr, range, stream);
+    if (rc != SGB_OK) return rc;
+  }
+  return check_launch("argsort_stable");
+}
+
+extern "C" int sgb_invert_permutation(const int32_t* perm, int64_t n, int32_t* inv, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(n >= 0 && (n == 0 || (perm && inv)), SGB_ERR_ARG, "invert_permutation: bad argument");
+  if (n == 0) return SGB_OK;
+  invert_perm_kernel<<<blocks_for(n), kT, 0, stream>>>(perm, n, inv);
+  return check_launch("invert_permutation");
+}
+
+extern "C" int sgb_partition_edges(const void* edge_index, int idx_bytes, int64_t row_stride, int64_t col_stride, int64_t E,
+                                   const void* lab_src, const void* lab_dst, int lab_bytes, int64_t n_src, int64_t n_dst,
+                                   int64_t P, const int32_t* inv_src, const int32_t* inv_dst, void* out_edge_index,
+                                   int64_t ld_out, int32_t* kept_eid, int32_t* edge_rowptr /*[P+2]*/, int32_t* status,
+                                   void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE((idx_bytes == 4 || idx_bytes == 8) && (lab_bytes == 4 || lab_bytes == 8), SGB_ERR_ARG, "partition_edges: index width must be 4 or 8");
+  SGB_REQUIRE(E >= 0 && E < (int64_t(1) << 31) && P >= 1 && P < (int64_t(1) << 30), SGB_ERR_RANGE, "partition_edges: size out of range");
+  SGB_REQUIRE(edge_rowptr && ws && ws_bytes >= sgb_argsort_workspace_bytes(E) + align_up(static_cast<size_t>(E > 0 ? E : 1) * 4), SGB_ERR_WORKSPACE,
+              "partition_edges: workspace too small");
+  if (E == 0) {
+    cudaMemsetAsync(edge_rowptr, 0, static_cast<size_t>(P + 2) * 4, stream);
+    return check_launch("partition_edges(empty)");
+  }
+  SGB_REQUIRE(edge_index && lab_src && lab_dst && inv_src && inv_dst && out_edge_index, SGB_ERR_ARG, "partition_edges: null argument");
+  const size_t nb = align_up(static_cast<size_t>(E) * 4);
+  uint32_t* keys = static_cast<uint32_t*>(ws);
+  uint32_t* skeys = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + nb);
+  uint32_t* order = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + 2 * nb);
+  void* sort_ws = static_cast<char*>(ws) + 3 * nb;
+#define SGB_KEYS(IT, LT)                                                                                          \
+  edge_part_keys_kernel<IT, LT><<<blocks_for(E), kT, 0, stream>>>(static_cast<const IT*>(edge_index), row_stride, \
+      col_stride, E, static_cast<const LT*>(lab_src), n_src, static_cast<const LT*>(lab_dst), n_dst, P, keys, status)
+  if (idx_bytes == 8 && lab_bytes == 8) SGB_KEYS(int64_t, int64_t);
+  else if (idx_bytes == 8) SGB_KEYS(int64_t, int32_t);
+  else if (lab_bytes == 8) SGB_KEYS(int32_t, int64_t);
+  else SGB_KEYS(int32_t, int32_t);
+#undef SGB_KEYS
+  int rc = sort_pairs(keys, nullptr, skeys, order, E, bits_for(P + 1), sort_ws, sort_pairs_workspace_bytes(E), stream, true);
+  if (rc != SGB_OK) return rc;
+  rc = rowptr_from_sorted(skeys, E, edge_rowptr, P + 1, stream);     // rowptr[P] = kept edges, rowptr[P+1] = E
+  if (rc != SGB_OK) return rc;
+  if (idx_bytes == 8)
+    edge_part_fill_kernel<int64_t><<<blocks_for(E), kT, 0, stream>>>(static_cast<const int64_t*>(edge_index), row_stride, col_stride,
+                                                                     order, edge_rowptr, P, inv_src, inv_dst,
+                                                                     static_cast<int64_t*>(out_edge_index), ld_out, kept_eid);
+  else
+    edge_part_fill_kernel<int32_t><<<blocks_for(E), kT, 0, stream>>>(static_cast<const int32_t*>(edge_index), row_stride, col_stride,
+                                                                     order, edge_rowptr, P, inv_src, inv_dst,
+                                                                     static_cast<int32_t*>(out_edge_index), ld_out, kept_eid);
+  return check_launch("partition_edges");
+}
 
 extern "C" int sgb_mask_select(const uint8_t* mask, int64_t n, int32_t* sel, int32_t* map, int32_t* count, void* ws,
                                size_t ws_bytes, void* stream_) {

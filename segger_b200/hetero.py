@@ -67,6 +67,8 @@ class HeteroBatch:
 
     def to(self, device, non_blocking: bool = False) -> "HeteroBatch":
         out = HeteroBatch()
+        if hasattr(self, "_num_graphs"):
+            out._num_graphs = self._num_graphs
         for k, s in self._nodes.items():
             for n, v in s.items():
                 out[k][n] = v.to(device, non_blocking=non_blocking) if isinstance(v, Tensor) else v

@@ -51,6 +51,7 @@ def test_forward_and_predict_step_under_inference_mode():
             {TT: bi[TT]["edge_index"], TB: bi[TB]["edge_index"]})
     for g, w in zip(got, want):
         assert torch.equal(g, w)
+    a = b = None
     assert torch.equal(emb["tx"], again["tx"]) and generic["tx"].shape == (3000, 128)
     # page-locked result memory is bounded: beyond the budget results come back as pageable copies, identical values
     import gc
@@ -65,7 +66,7 @@ def test_forward_and_predict_step_under_inference_mode():
     finally:
         L._PINNED_BUDGET = old
     assert all(not t.is_pinned() for t in paged) and all(torch.equal(a, b) for a, b in zip(paged, got))
-    del got, want, paged
+    del got, want, paged, g, w, a, b
     gc.collect()
     assert L._pinned_live < live                          # returned to the budget when the results are dropped
 
@@ -180,7 +181,7 @@ def test_config3_model_on_a_20k_tile_vs_oracle():
     """The configs[3] model (in=128, hidden=128, heads=4, 3 layers, k=20 neighbours) on a 20k-transcript tile."""
     ts, x, edges, pos, bat = synth_batch(20_000, 200, seed=3, k=20)
     ref, prod = make_models(ts.n_genes, ts.bd_x.shape[1], 128, 128, 128, 1, 4, seed=5)
-    check_forward_backward(ref, prod, x, edges, pos, bat, "r2_grad_parity_cfg3_20k", grad_scale=1e-3, noise_trials=1)
+    check_forward_backward(ref, prod, x, edges, pos, bat, "r2_grad_parity_cfg3_20k", grad_scale=1e-3, noise_trials=2)
 
 
 def test_factored_first_layer_equals_dense_form(monkeypatch):

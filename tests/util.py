@@ -101,7 +101,7 @@ class replay_random:
 # the fp64 run, which moves one output channel of that conv's lin_l / lin_r gradient -- and, diluted, every gradient
 # upstream of it -- by far more than 1e-4.  Such a gradient is not pinned by the fp32 reference itself.  The rule:
 #   * every tensor is compared with an fp64 copy of the oracle; error < 1e-4 -> fine (the overwhelming majority);
-#   * a tensor that exceeds 1e-4 must be ON THE ALLOW-LIST below and stay under min(its ceiling, 2 x the fp32 oracle's
+#   * a tensor that exceeds 1e-4 must be ON THE ALLOW-LIST below and stay under min(its ceiling, 3 x the fp32 oracle's
 #     own conditioning noise), where the noise is the larger of (fp32 oracle vs fp64 oracle) and (fp32 oracle with every
 #     weight moved by half an ulp vs fp64 oracle);
 #   * a tensor whose oracle noise is < 2.5e-5 must ALSO hold the flat 1e-4 against the fp32 oracle.
@@ -170,7 +170,7 @@ def check_forward_backward(ref, prod, x, edges, pos, bat, tag, grad_scale=1.0, n
             relaxed[n] = e64
             ceil = _ceiling(n)
             assert ceil is not None, (n, e64, "not on the RELAXED allow-list")
-            assert e64 < min(ceil, max(PARITY_TOL, 2 * noise)), (n, e64, noise, ceil)
+            assert e64 < min(ceil, max(PARITY_TOL, 3 * noise)), (n, e64, noise, ceil)
         if noise < PARITY_TOL / 4:
             assert e32 < PARITY_TOL, n
         checked += 1
