@@ -300,10 +300,12 @@ class TilePartition:
             total = e_off[-1]
             res = torch.empty(2, total, dtype=ei.dtype, device=ei.device)
             if total > 0:
-                check(lib.sgb_edges_collate(ptr(ei), ei.element_size(), ei.stride(0), ptr(_dev_i64(e_start, dev)),
-                                            ptr(_dev_i64(e_off, dev)), ptr(n_start[src]), ptr(n_off[src]), ptr(n_start[dst]),
-                                            ptr(n_off[dst]), K, total, ptr(res), total, stream_ptr(ei.device)), "edges_collate")
+                d_es, d_eo = _dev_i64(e_start, dev), _dev_i64(e_off, dev)     # named: must outlive the launch
+                check(lib.sgb_edges_collate(ptr(ei), ei.element_size(), ei.stride(0), ptr(d_es), ptr(d_eo), ptr(n_start[src]),
+                                            ptr(n_off[src]), ptr(n_start[dst]), ptr(n_off[dst]), K, total, ptr(res), total,
+                                            stream_ptr(ei.device)), "edges_collate")
                 ops._count(1)
+                out[et]["ptr"] = d_eo
             out[et]["edge_index"] = res
         return out
 

@@ -129,7 +129,9 @@ def test_tiled_prediction_with_halo_equals_whole_graph_prediction():
     with torch.no_grad():
         src, seg, sim, gene = lit.predict_step(full, 0)
     whole = {int(i): (int(s), float(v)) for i, s, v in zip(src, seg, sim)}
-    boxes = tiles.square_tiles(0.0, 0.0, ts.side + 1e-3, ts.side + 1e-3, 3, 3)
+    lo = nodes["tx"]["pos"].min(0).values - 1e-3      # cells at the rim stick out of [0, side]
+    hi = nodes["tx"]["pos"].max(0).values + 1e-3
+    boxes = tiles.square_tiles(float(lo[0]), float(lo[1]), float(hi[0]), float(hi[1]), 3, 3)
     ds = tiles.TilePredictSet(full, boxes, margin=20.0)
     seen = {}
     for i in range(len(ds)):
