@@ -365,6 +365,24 @@ SGB_API int sgb_compact_predictions(const uint8_t* mask, int64_t n, const int64_
                             const float* max_sim, const void* gene, int gene_bytes, int64_t* out_src, int64_t* out_seg,
                             float* out_sim, void* out_gene, int32_t* count, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Writer post-processing: ISTSegmentationWriter.assign_transcripts_to_cells
+ * (data/writer.py:132-253, data/utils/threshold.py:3-11).
+ * sgb_dedupe_max: one row per transcript, the prediction with the highest similarity (writer.py:199-203; exact ties ->
+ * lowest cell id).  row_bits = number of significant bits of the row indices.  order[0..count) = indices of the kept
+ * predictions, ascending in row index.
+ * sgb_gene_thresholds: per gene, over its ASSIGNED transcripts (seg >= 0): scikit-image's threshold_yen and the
+ * threshold_li iteration bounded by max_iter callbacks (li_iters = -1: not converged -> the writer back-fills with the
+ * median of the others, writer.py:242-246); counts[g] = assigned transcripts of gene g (0: thresholds are NaN).
+ * ---------------------------------------------------------------------------------------- */
+SGB_API size_t sgb_dedupe_workspace_bytes(int64_t n);
+SGB_API int sgb_dedupe_max(const int64_t* row, const int64_t* seg, const float* sim, int64_t n, int row_bits, int32_t* order,
+                   int32_t* count, void* ws, size_t ws_bytes, void* stream);
+SGB_API size_t sgb_gene_threshold_workspace_bytes(int64_t n, int n_genes);
+SGB_API int sgb_gene_thresholds(const void* gene, int gene_bytes, const int64_t* seg, const float* sim, int64_t n, int n_genes,
+                        int max_iter, double* thr_yen, double* thr_li, int32_t* li_iters, int32_t* counts, void* ws,
+                        size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

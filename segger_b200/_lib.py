@@ -107,6 +107,10 @@ _PROTOS = {
     "sgb_ranges_gather": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
     "sgb_edges_collate": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_vp]),
     "sgb_batch_vector": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp]),
+    "sgb_dedupe_workspace_bytes": (c_sz, [c_i64]),
+    "sgb_dedupe_max": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "sgb_gene_threshold_workspace_bytes": (c_sz, [c_i64, c_int]),
+    "sgb_gene_thresholds": (c_int, [c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "sgb_compact_predictions": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                         c_sz, c_vp]),
 }

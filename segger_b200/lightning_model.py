@@ -95,7 +95,7 @@ class LitISTEncoder(_Base):
         """lightning_model.py:127-134."""
         return self.model(batch.x_dict, batch.edge_index_dict, batch.pos_dict, batch.batch_dict)
 
-    def predict_step(self, batch, batch_idx: int = 0, min_similarity: Optional[float] = None):
+    def predict_step(self, batch, batch_idx: int = 0, min_similarity: Optional[float] = None, device_output: bool = False):
         """lightning_model.py:263-298: embeddings -> cosine similarity over tx-neighbors-bd candidate
         edges -> per-transcript max / arg-max -> cell id (or -1); returns CPU tensors
         (tx.index, seg_idx, max_sim, gene id) restricted to ``predict_mask``.
@@ -121,6 +121,8 @@ class LitISTEncoder(_Base):
         n_keep = head[0]
         dev = max_sim.device
         parts = (o_src[:n_keep], o_seg[:n_keep], o_sim[:n_keep], o_gene[:n_keep])
+        if device_output:        # multi-GPU inference keeps the shards on the device for the end-of-run gather
+            return parts
         sizes = [(t.numel() * t.element_size() + 15) // 16 * 16 for t in parts]
         host, lease = _result_buffer(sum(sizes))
         outs, off = [], 0

@@ -59,7 +59,9 @@ def _disc(rng, n, r0, r1):
 
 
 def synth(n_tx: int, n_cells: int, seed: int = 0, n_genes: int = 500, bd_dim: int = 128,
-          nodes_per_tile: int = 50_000) -> SynthTileSet:
+          nodes_per_tile: int = 50_000, pred_edges: bool = True) -> SynthTileSet:
+    """``pred_edges=False`` skips the host-side tx-neighbors-bd candidate list (a scipy kd-tree query): large
+    benchmarks build it with the product's point-in-polygon join instead (segger_b200.geometry)."""
     rng = np.random.default_rng(seed)
     g = int(math.ceil(math.sqrt(n_cells)))
     side = g * PITCH
@@ -79,9 +81,14 @@ def synth(n_tx: int, n_cells: int, seed: int = 0, n_genes: int = 500, bd_dim: in
     cdf = np.cumsum(prof, axis=1)
 
     def genes_for(cells):
+        # number of CDF entries below u = searchsorted(side='left'), per cell type (same values as the dense compare)
         u = rng.uniform(0, 1, cells.shape[0])
-        c = cdf[ctype[cells]]
-        return (u[:, None] > c).sum(1).clip(0, n_genes - 1).astype(np.int32)
+        t = ctype[cells]
+        out = np.empty(cells.shape[0], np.int64)
+        for k in range(cdf.shape[0]):
+            m = t == k
+            out[m] = np.searchsorted(cdf[k], u[m], side="left")
+        return out.clip(0, n_genes - 1).astype(np.int32)
 
     owner_n = np.repeat(cid, n_nuc)
     dx, dy = _disc(rng, owner_n.shape[0], 0.0, R_NUC)
@@ -123,13 +130,16 @@ def synth(n_tx: int, n_cells: int, seed: int = 0, n_genes: int = 500, bd_dim: in
     edge_tb = np.stack([nuc, cell[nuc]]).astype(np.int64)
 
     # tx-neighbors-bd: buffered-outline containment, <= PRED_MAX_K nearest cells
-    from scipy.spatial import cKDTree  # generator-side only (host preprocessing)
-    r_buf = R_CELL * (1.0 + BUFFER_RATIO)
-    _, nn = cKDTree(bd_pos.astype(np.float64)).query(
-        tx_pos.astype(np.float64), k=PRED_MAX_K, distance_upper_bound=r_buf, workers=-1)
-    valid = nn != n_cells
-    src = np.repeat(np.arange(n_tx), PRED_MAX_K).reshape(n_tx, PRED_MAX_K)[valid]
-    edge_pred = np.stack([src, nn[valid]]).astype(np.int32)
+    if pred_edges:
+        from scipy.spatial import cKDTree  # generator-side only (host preprocessing)
+        r_buf = R_CELL * (1.0 + BUFFER_RATIO)
+        _, nn = cKDTree(bd_pos.astype(np.float64)).query(
+            tx_pos.astype(np.float64), k=PRED_MAX_K, distance_upper_bound=r_buf, workers=-1)
+        valid = nn != n_cells
+        src = np.repeat(np.arange(n_tx), PRED_MAX_K).reshape(n_tx, PRED_MAX_K)[valid]
+        edge_pred = np.stack([src, nn[valid]]).astype(np.int32)
+    else:
+        edge_pred = np.zeros((2, 0), np.int32)
 
     return SynthTileSet(
         tx_pos=tx_pos, tx_gene=gene, tx_tile=tile, tx_cell=cell, tx_compartment=comp,
