@@ -315,7 +315,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--infer-tx", type=int, default=20_000_000, help="transcripts of the configs[2] inference leg (0: skip)")
-    ap.add_argument("--max-edges-per-batch", type=int, default=1_000_000, help="predict batches (reference default 1M)")
+    ap.add_argument("--max-edges-per-batch", type=int, default=8_000_000,
+                    help="edges per predict batch of the inference leg (the reference's default is 1M: also reported)")
     args = ap.parse_args()
     capture_stdout()
     if args.impl == "reference":
@@ -866,7 +867,7 @@ def inference_cfg3_leg(lit, n_tx_total, max_edges, device, world, rank, timed, h
     iy = np.clip(((ts.tx_pos[:, 1] - lo[1]) / ((hi[1] - lo[1]) / nt)).astype(np.int64), 0, nt - 1)
     tile_tx = np.bincount(iy * nt + ix, minlength=nt * nt)
     mine = assign_tiles(tile_tx.tolist(), world)[rank]
-    ds = TilePredictSet(b, boxes, margin=20.0)
+    ds = TilePredictSet(b, boxes, margin=20.0, grid=(nt, nt))
     lit.eval()
     stats = {}
 
@@ -905,6 +906,15 @@ def inference_cfg3_leg(lit, n_tx_total, max_edges, device, world, rank, timed, h
 
     run()
     ms = timed(run, 1)
+    ref_batching = None
+    if max_edges != 1_000_000:          # the reference's own batch size (max_edges_per_batch = 1M, data_module.py:158)
+        big, max_edges = max_edges, 1_000_000
+        run()
+        ms_ref = timed(run, 1)
+        ref_batching = {"max_edges_per_batch": 1_000_000, "ms": ms_ref, "value": n_tx_total / (ms_ref * 1e-3),
+                        "batches_this_rank": stats.get("batches")}
+        max_edges = big
+        run()
     # kernel-only byte model of SURVEY 8d: 4.48 GB per 1M transcripts (MP forward + score), 10.9 GB end to end
     return {"metric": "segmentation_transcripts_per_sec", "value": n_tx_total / (ms * 1e-3), "unit": "transcripts/s",
             "ms": ms, "n_tx": n_tx_total, "n_cells": n_cells, "n_gpus": world, "tiles": nt * nt, "tiles_this_rank": len(mine),
@@ -912,7 +922,7 @@ def inference_cfg3_leg(lit, n_tx_total, max_edges, device, world, rank, timed, h
             "rows_after_dedupe": stats.get("rows"), "rows_before_dedupe": stats.get("predicted_before_dedupe"),
             "assigned_frac": stats.get("assigned"), "complete": stats.get("rows") == n_tx_total,
             "frac_of_byte_model": (10.9e9 * n_tx_total / 1e6) / (ms * 1e-3) / 1e9 / (hbm_peak * world),
-            "host_synth_s": t_synth,
+            "host_synth_s": t_synth, "with_reference_batch_size": ref_batching,
             "what": "tile cut (+20 um halo) + batch assembly + predict_step per batch + device all-gather of fixed-width result "
                     "tensors + device de-duplication, all timed; graph construction (kNN, point-in-polygon) is outside"}
 

@@ -323,6 +323,10 @@ SGB_API int sgb_mask_select(const uint8_t* mask, int64_t n, int32_t* sel, int32_
 SGB_API int sgb_box_select(const void* pos, int pos_f64, int64_t n, const double* outer, const double* inner /*or NULL*/,
                    int32_t* sel, int32_t* map, uint8_t* inner_mask /*[count]*/, int32_t* count, void* ws,
                    size_t ws_bytes, void* stream);
+/* map[sel[k]] = k (fill_mode 0) or = fill (fill_mode 1) for k < *count (count == NULL: k < m): maintains the
+ * global -> tile-local node numbering of a tile subset in a persistent array (set before the edge pass, cleared after). */
+SGB_API int sgb_scatter_rank(int32_t* map, const int32_t* sel, const int32_t* count, int64_t m, int fill_mode, int32_t fill,
+                     void* stream);
 /* dst[k,:] = src[sel[k],:] for k < *count (count == NULL: k < m), rows of row_bytes bytes of any dtype: the node /
  * edge attribute slicing of HeteroData.subgraph and PartitionDataset._index_select. */
 SGB_API int sgb_gather_rows_bytes(const void* src, int64_t row_bytes, const int32_t* sel, const int32_t* count, int64_t m,

@@ -96,6 +96,7 @@ _PROTOS = {
     "sgb_mask_select": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "sgb_box_select": (c_int, [c_vp, c_int, c_i64, C.POINTER(C.c_double), C.POINTER(C.c_double), c_vp, c_vp, c_vp, c_vp,
                                c_vp, c_sz, c_vp]),
+    "sgb_scatter_rank": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i32, c_vp]),
     "sgb_gather_rows_bytes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "sgb_edge_subset": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp,
                                 c_sz, c_vp]),

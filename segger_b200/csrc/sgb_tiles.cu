@@ -221,6 +221,14 @@ __global__ void edge_part_fill_kernel(const IdxT* __restrict__ ei, int64_t row_s
   if (kept_eid) kept_eid[k] = static_cast<int32_t>(e);
 }
 
+// map[sel[k]] = k (fill < 0) or map[sel[k]] = fill for k < *count: the global -> tile-local node map of a tile subset
+__global__ void scatter_rank_kernel(int32_t* __restrict__ map, const int32_t* __restrict__ sel, const int32_t* __restrict__ count,
+                                    int64_t m, int fill_mode, int32_t fill) {
+  const int64_t lim = count ? static_cast<int64_t>(*count) : m;
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k < lim) map[sel[k]] = fill_mode ? fill : static_cast<int32_t>(k);
+}
+
 struct SelWs {
   int32_t *flags, *scan;
   void* scan_ws;
@@ -381,6 +389,15 @@ extern "C" int sgb_box_select(const void* pos, int pos_f64, int64_t n, const dou
                                                                  inner_mask);
   }
   return check_launch("box_select");
+}
+
+extern "C" int sgb_scatter_rank(int32_t* map, const int32_t* sel, const int32_t* count, int64_t m, int fill_mode, int32_t fill,
+                                void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(m >= 0 && (m == 0 || (map && sel)), SGB_ERR_ARG, "scatter_rank: bad argument");
+  if (m == 0) return SGB_OK;
+  scatter_rank_kernel<<<blocks_for(m), kT, 0, stream>>>(map, sel, count, m, fill_mode, fill);
+  return check_launch("scatter_rank");
 }
 
 extern "C" int sgb_gather_rows_bytes(const void* src, int64_t row_bytes, const int32_t* sel, const int32_t* count,

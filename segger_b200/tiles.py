@@ -316,15 +316,71 @@ class TilePartition:
 class TilePredictSet:
     """``TilePredictDataset`` for a ``HeteroBatch`` on the GPU.  ``tiles``: [P, 4] (xmin, ymin, xmax, ymax) boxes;
     ``self[i]`` = the subgraph of the nodes inside box i grown by ``margin`` (half-open, tile_dataset.py:233-238) with
-    ``predict_mask`` = inside the box itself (closed, :239-244), edges renumbered and in their original order."""
+    ``predict_mask`` = inside the box itself (closed, :239-244), edges renumbered and in their original order.
 
-    def __init__(self, data: HeteroBatch, tiles, margin: float = 0.0):
+    The reference scans every node and every edge of the dataset for every tile.  When the boxes form a regular
+    ``grid = (nx, ny)`` (``square_tiles``) and the margin is smaller than a tile, an index built once (nodes sorted by
+    grid cell, edges by the cell of their source -- two stable radix sorts per type) restricts a tile's scan to the
+    3 x 3 neighbourhood of cells; the result is identical (same nodes, same order, same edges)."""
+
+    def __init__(self, data: HeteroBatch, tiles, margin: float = 0.0, grid: Optional[Tuple[int, int]] = None):
         self.data = data
         self.tiles = [tuple(float(v) for v in t) for t in (tiles.tolist() if hasattr(tiles, "tolist") else tiles)]
         self.margin = float(margin)
         missing = [nt for nt in data.node_types if "pos" not in data[nt]]
         if missing:
             raise ValueError(f"Missing 'pos' attribute for node type: {', '.join(missing)}")
+        self._index = None
+        if grid is not None and len(self.tiles) == grid[0] * grid[1] and len(self.tiles) > 1:
+            self._build_index(grid)
+
+    # -- coarse index ------------------------------------------------------------------------------------------------
+    def _build_index(self, grid) -> None:
+        nx, ny = grid
+        x0, y0 = self.tiles[0][0], self.tiles[0][1]
+        x1, y1 = self.tiles[-1][2], self.tiles[-1][3]
+        w, h = (x1 - x0) / nx, (y1 - y0) / ny
+        if not (self.margin < w and self.margin < h):
+            return
+        P = nx * ny
+        labels, node_perm, node_ptr, maps = {}, {}, {}, {}
+        ptrs = []
+        for nt in self.data.node_types:
+            pos = self.data[nt]["pos"]
+            ix = torch.clamp(((pos[:, 0].double() - x0) / w).floor().long(), 0, nx - 1)
+            iy = torch.clamp(((pos[:, 1].double() - y0) / h).floor().long(), 0, ny - 1)
+            lab = (iy * nx + ix).to(torch.int32)
+            perm, indptr, _ = stable_argsort(lab, P)
+            labels[nt], node_perm[nt] = lab, perm
+            ptrs.append(indptr)
+            maps[nt] = torch.full((pos.size(0),), -1, dtype=torch.int32, device=pos.device)
+        edge_perm = {}
+        for et in self.data.edge_types:
+            ei = self.data[et]["edge_index"]
+            lab = labels[et[0]].index_select(0, ei[0].long())
+            perm, indptr, _ = stable_argsort(lab, P)
+            edge_perm[et] = perm
+            ptrs.append(indptr)
+        flat = torch.cat([p.to(torch.int64) for p in ptrs]).tolist()
+        o = 0
+        for nt in self.data.node_types:
+            node_ptr[nt] = flat[o:o + P + 1]; o += P + 1
+        edge_ptr = {}
+        for et in self.data.edge_types:
+            edge_ptr[et] = flat[o:o + P + 1]; o += P + 1
+        self._index = dict(nx=nx, ny=ny, node_perm=node_perm, node_ptr=node_ptr, edge_perm=edge_perm, edge_ptr=edge_ptr, maps=maps)
+
+    def _neighbourhood(self, t: int) -> List[int]:
+        nx, ny = self._index["nx"], self._index["ny"]
+        i, j = t % nx, t // nx
+        return [jj * nx + ii for jj in range(max(0, j - 1), min(ny, j + 2)) for ii in range(max(0, i - 1), min(nx, i + 2))]
+
+    def _candidates(self, perm: Tensor, ptr_: List[int], cells: List[int]) -> Tensor:
+        """ids of the given cells, ascending (the index stores them per cell; cells are disjoint)."""
+        parts = [perm[ptr_[c]:ptr_[c + 1]] for c in cells if ptr_[c + 1] > ptr_[c]]
+        if not parts:
+            return perm[:0]
+        return torch.sort(torch.cat(parts)).values       # index plumbing over the candidates only
 
     def __len__(self) -> int:
         return len(self.tiles)
@@ -332,13 +388,88 @@ class TilePredictSet:
     def __getitem__(self, idx: int) -> HeteroBatch:
         if idx < 0 or idx >= len(self):
             raise IndexError(f"Requested {idx}, but tiling only contains {len(self)} tiles.")
+        if self._index is not None:
+            return self._subset_indexed(idx)
         return self.subset(self.tiles[idx])
 
-    def subset(self, bounds: Sequence[float]) -> HeteroBatch:
+    def _boxes(self, bounds):
         x0, y0, x1, y1 = bounds
         m = self.margin
-        outer = (C.c_double * 4)(x0 - m, y0 - m, x1 + m, y1 + m)
-        inner = (C.c_double * 4)(x0, y0, x1, y1)
+        return (C.c_double * 4)(x0 - m, y0 - m, x1 + m, y1 + m), (C.c_double * 4)(x0, y0, x1, y1)
+
+    def _subset_indexed(self, t: int) -> HeteroBatch:
+        outer, inner = self._boxes(self.tiles[t])
+        lib = _lib.load()
+        data, ix = self.data, self._index
+        cells = self._neighbourhood(t)
+        sel, pmask, counts, cand_n = {}, {}, [], {}
+        for nt in data.node_types:
+            pos = data[nt]["pos"]
+            pos = (pos if pos.dtype in (torch.float32, torch.float64) else pos.float()).contiguous()
+            cand = self._candidates(ix["node_perm"][nt], ix["node_ptr"][nt], cells)
+            n, dev = cand.numel(), pos.device
+            pos_c = gather_rows(pos, cand)
+            s_loc = _i32(n, dev)
+            pm = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+            cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            ws = ops._ws(lib.sgb_select_workspace_bytes(n), dev)
+            check(lib.sgb_box_select(ptr(pos_c), int(pos.dtype == torch.float64), n, outer, inner, ptr(s_loc), None, ptr(pm),
+                                     ptr(cnt), ptr(ws), ws.numel(), stream_ptr(dev)), "box_select")
+            s_glob = gather_rows(cand, s_loc, count=cnt)             # ascending node ids of the tile (+ halo)
+            check(lib.sgb_scatter_rank(ptr(ix["maps"][nt]), ptr(s_glob), ptr(cnt), n, 0, 0, stream_ptr(dev)), "scatter_rank")
+            ops._count(9)
+            sel[nt], pmask[nt], cand_n[nt] = s_glob, pm, n
+            counts.append(cnt)
+        edges = {}
+        for et in data.edge_types:
+            src, _, dst = et
+            ei = data[et]["edge_index"]
+            ecand = self._candidates(ix["edge_perm"][et], ix["edge_ptr"][et], cells)
+            E, dev = ecand.numel(), ei.device
+            ei_c = torch.stack([gather_rows(ei[0], ecand), gather_rows(ei[1], ecand)])
+            res = torch.empty(2, E, dtype=ei.dtype, device=dev)
+            kept_loc = _i32(E, dev)
+            cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            ws = ops._ws(lib.sgb_select_workspace_bytes(E), dev)
+            check(lib.sgb_edge_subset(ptr(ei_c), ei_c.element_size(), ei_c.stride(0), ei_c.stride(1), E, ptr(ix["maps"][src]),
+                                      ix["maps"][src].numel(), ptr(ix["maps"][dst]), ix["maps"][dst].numel(), ptr(res), E,
+                                      ptr(kept_loc), ptr(cnt), ptr(ws), ws.numel(), stream_ptr(dev)), "edge_subset")
+            ops._count(7)
+            edges[et] = (res, kept_loc, ecand)
+            counts.append(cnt)
+        for nt in data.node_types:                                   # leave the persistent maps clean for the next tile
+            check(lib.sgb_scatter_rank(ptr(ix["maps"][nt]), ptr(sel[nt]), ptr(counts[data.node_types.index(nt)]), cand_n[nt], 1, -1,
+                                       stream_ptr(sel[nt].device)), "scatter_rank")
+        n_sel = torch.cat(counts).tolist()                           # the one read-back: sizes of the tile's stores
+        out = HeteroBatch()
+        out._num_graphs = 1
+        for i, nt in enumerate(data.node_types):
+            k = n_sel[i]
+            n_all = data[nt]["pos"].size(0)
+            for name, attr in data[nt].items():
+                if isinstance(attr, Tensor) and attr.dim() >= 1 and attr.size(0) == n_all:
+                    out[nt][name] = gather_rows(attr, sel[nt], m=k)
+                else:
+                    out[nt][name] = attr
+            out[nt]["predict_mask"] = pmask[nt][:k].view(torch.bool)
+            out[nt]["batch"] = set_num_graphs(torch.zeros(k, dtype=torch.int64, device=sel[nt].device), 1)
+        for j, et in enumerate(data.edge_types):
+            k = n_sel[len(data.node_types) + j]
+            res, kept_loc, ecand = edges[et]
+            out[et]["edge_index"] = res[:, :k]
+            E_all = data[et]["edge_index"].size(1)
+            extra = [n_ for n_, a_ in data[et].items() if n_ != "edge_index" and isinstance(a_, Tensor) and a_.dim() >= 1 and a_.size(0) == E_all]
+            if extra:
+                kept = gather_rows(ecand, kept_loc, m=k)
+                for name in extra:
+                    out[et][name] = gather_rows(data[et][name], kept, m=k)
+            for name, attr in data[et].items():
+                if name != "edge_index" and name not in extra:
+                    out[et][name] = attr
+        return out
+
+    def subset(self, bounds: Sequence[float]) -> HeteroBatch:
+        outer, inner = self._boxes(bounds)
         lib = _lib.load()
         data = self.data
         sel, amap, pmask, counts = {}, {}, {}, []

@@ -101,6 +101,19 @@ def test_tile_predict_subset_matches_oracle_incl_boundaries_and_dtypes():
             assert got.dtype == edges[et].dtype and torch.equal(got.cpu().long(), e_ref[et]), (i, et)
     with pytest.raises(IndexError):
         ds[9]
+    # the grid-indexed path (scan restricted to the 3 x 3 neighbourhood of cells) returns the identical subgraph
+    dsi = tiles.TilePredictSet(b.cuda(), boxes, margin=20.0, grid=(3, 3))
+    assert dsi._index is not None
+    for i in range(9):
+        a, c = ds.subset(boxes[i]), dsi[i]
+        for nt in ("tx", "bd"):
+            assert set(a[nt]) == set(c[nt])
+            for k in a[nt]:
+                assert torch.equal(a[nt][k], c[nt][k]), (i, nt, k)
+        for et in (TT, TB, PRED):
+            assert torch.equal(a[et]["edge_index"], c[et]["edge_index"]), (i, et)
+    assert all(int((m != -1).sum()) == 0 for m in dsi._index["maps"].values())      # persistent maps left clean
+    assert tiles.TilePredictSet(b.cuda(), boxes, margin=1e6, grid=(3, 3))._index is None   # halo wider than a tile: full scan
     # float64 positions compare in float64
     b64 = HeteroBatch()
     for nt in ("tx", "bd"):

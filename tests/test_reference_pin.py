@@ -292,7 +292,9 @@ def test_live_reference_module_signatures_match_drop_ins():
              (ref.triplet_loss.FastTripletSelector.__init__, triplet_loss.FastTripletSelector.__init__)]
     for r, p in pairs:
         rs, ps = inspect.signature(r), inspect.signature(p)
-        assert list(rs.parameters) == list(ps.parameters), (r.__qualname__, rs, ps)
+        # same parameters in the same order; the drop-in may append optional ones of its own
+        assert list(ps.parameters)[:len(rs.parameters)] == list(rs.parameters), (r.__qualname__, rs, ps)
+        assert all(p_.default is not inspect.Parameter.empty for p_ in list(ps.parameters.values())[len(rs.parameters):])
         for name, par in rs.parameters.items():
             if par.default is not inspect.Parameter.empty:      # (the drop-in may add a default where the reference has none)
                 assert par.default == ps.parameters[name].default, (r.__qualname__, name)
