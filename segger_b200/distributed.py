@@ -74,7 +74,8 @@ class FlatGradAllReduce:
             self._bucket_of[id(p)] = len(self.buckets) - 1
         self._seen = [0] * len(self.buckets)
         self._work = [None] * len(self.buckets)
-        self.overlap = bool(overlap) and dev.type == "cuda"
+        import os
+        self.overlap = bool(overlap) and dev.type == "cuda" and os.environ.get("SEGGER_B200_ALLREDUCE_OVERLAP", "1") != "0"
         self._stream = torch.cuda.Stream(dev) if self.overlap else None
         if self.overlap:
             for p in self.params:
