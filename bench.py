@@ -391,11 +391,13 @@ def main():
         return float(ms.item())
 
     # ---- device-resident measurement -----------------------------------------------------------
-    for _ in range(W):
-        train_step(dev_in)
+    # the clock sampler (an nvidia-smi child process) is started BEFORE the warm-up: spawning it stalls the launching
+    # thread for tens of milliseconds, which must not land inside the timed steps; it keeps sampling through them
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(W):
+        train_step(dev_in)
     l0 = ops.LAUNCHES
     ms_total = timed(lambda: train_step(dev_in), K)
     launches = (ops.LAUNCHES - l0)
