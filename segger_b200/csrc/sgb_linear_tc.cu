@@ -623,6 +623,340 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
   }
 }
 
+// ================================================================================================
+// Forward / dgrad kernel, third generation: the activation operand travels through TENSOR MEMORY.
+//
+// gemm_tf32x3_kernel keeps hi and lo of BOTH operands in shared memory, so every K=8 MMA reads 8 KB of it and the
+// producers write 32 KB per slab on top of the 16 KB cp.async landing: shared-memory bandwidth, not the tensor
+// pipe, sets the pace (profiles/r1c_gemm_knockouts.txt).  Here
+//   * a producer thread owns one ROW of the 128-row tile: it reads its 32 raw fp32 of the slab from the (swizzled)
+//     cp.async landing zone, splits them in registers and stores hi | lo with tcgen05.st straight into 64 TMEM
+//     columns of its lane -- the A operand of `tcgen05.mma ... [d], [a_tmem], b_desc` (TS form).  Shared memory no
+//     longer holds a split copy of A, and the tensor core reads only B from it (4 KB per MMA instead of 8);
+//   * the freed 32 KB per stage buy a fourth pipeline stage (4 x 32 KB of packed weights + 4 x 16 KB raw A);
+//   * B_RES: when the whole packed weight panel of an n-tile (hi + lo, all k-stages) fits in 128 KB (K <= 128 at
+//     BN = 128) it is loaded ONCE per CTA -- the grid is a multiple of the n-tile count, so a persistent CTA keeps
+//     its n-tile -- and the per-tile re-streaming of the weights through L2 (2/3 of the kernel's L2->SM traffic)
+//     disappears.
+// TMEM: [0, 2*BN) two chunk accumulators, [256, 512) four A slots of 64 columns (hi 32 | lo 32).
+// ================================================================================================
+constexpr int kTsAcc = 2;
+constexpr int kTsRaw = 4;          // raw-A landing ring (16 KB slots), filled kTsRaw-1 slabs ahead
+constexpr int kTsASlots = 4;       // TMEM A slots
+constexpr uint32_t kTsACol0 = 256;
+
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+
+template <int BN, int S, bool B_RES>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t kBTile = BN * 128;            // bytes of one hi (or lo) B tile of a k-stage
+  constexpr uint32_t kBStage = 2 * kBTile;
+  constexpr uint32_t kRawTile = BM * 128;          // 16 KB: raw fp32 A slab
+  constexpr int CW = BN / 2;
+  constexpr int PW = kPW;
+  constexpr int kStgLd = PW + 4;
+  static_assert(kTsAcc * BN <= static_cast<int>(kTsACol0), "accumulators overlap the A slots");
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_b = smem;                                              // S stages (ring) or S resident k-stages
+  uint8_t* smem_rawa = smem + static_cast<size_t>(S) * kBStage;        // kTsRaw landing slots
+  uint8_t* smem_stg = smem_rawa + static_cast<size_t>(kTsRaw) * kRawTile;
+  __shared__ uint64_t bar_full[kTsASlots], bar_empty[kTsASlots], bar_tfull[kTsAcc], bar_tempty[kTsAcc], bar_bres;
+  __shared__ uint32_t tmem_base_holder;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the A slots and (streamed) B stages advance together: ring depth = kTsASlots; B_RES keeps S k-stages resident
+  constexpr int R = kTsASlots;
+  static_assert(B_RES || S == R, "streamed weights share the ring of the A slots");
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < R; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), kProducerThreads + (B_RES ? 0 : 1));
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int a = 0; a < kTsAcc; ++a) {
+      mbar_init(smem_u32(&bar_tfull[a]), 1);
+      mbar_init(smem_u32(&bar_tempty[a]), kEpiWarps * 32);
+    }
+    mbar_init(smem_u32(&bar_bres), 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_holder)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  const int64_t num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  const int64_t tiles = num_m * num_n;
+  const int64_t num_ks = (p.K + BK - 1) / BK;
+
+  if (warp < kProducerWarps) {
+    // ===================================== producers =====================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+    const int t = threadIdx.x;                        // = row of the tile this thread owns in the split
+    // flattened slab sequence of this CTA: (tile, ks)
+    struct Cur { int64_t tile, ks; bool live; };
+    auto init = [&](Cur& c) { c.tile = blockIdx.x; c.ks = 0; c.live = c.tile < tiles; };
+    auto adv = [&](Cur& c) {
+      if (++c.ks == num_ks) { c.ks = 0; c.tile += gridDim.x; c.live = c.tile < tiles; }
+    };
+    auto issue_raw = [&](const Cur& c, int rslot) {
+      const int64_t mb = c.tile / num_n;
+      stage_raw<BM, false>(p.A, p.lda, mb * BM, p.M, c.ks * BK, p.K, smem_u32(smem_rawa + static_cast<size_t>(rslot) * kRawTile), t);
+    };
+    Cur pi, ci;
+    init(pi); init(ci);
+    int prslot = 0, crslot = 0, aslot = 0;
+    uint32_t aphase = 0;
+#pragma unroll
+    for (int i = 0; i < kTsRaw - 1; ++i) {
+      if (pi.live) { issue_raw(pi, prslot); adv(pi); }
+      cp_async_commit();
+      prslot = (prslot + 1 == kTsRaw) ? 0 : prslot + 1;
+    }
+    const uint32_t lane_field = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    while (ci.live) {
+      cp_async_wait<kTsRaw - 2>();                    // this thread's chunks of the slab have landed ...
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");   // ... and everybody else's; all are also done
+                                                                          // reading the slot refilled below
+      if (pi.live) { issue_raw(pi, prslot); adv(pi); }
+      cp_async_commit();
+      prslot = (prslot + 1 == kTsRaw) ? 0 : prslot + 1;
+      // this thread's row of the slab: 8 x 16 B at the swizzled chunk positions
+      const uint8_t* rt = smem_rawa + static_cast<size_t>(crslot) * kRawTile;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(rt + chunk_offset<BM, false>(t, c));
+        const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float h = rn_tf32(x[e]);
+          hi[c * 4 + e] = __float_as_uint(h);
+          lo[c * 4 + e] = __float_as_uint(rn_tf32(x[e] - h));
+        }
+      }
+      crslot = (crslot + 1 == kTsRaw) ? 0 : crslot + 1;
+      mbar_wait(smem_u32(&bar_empty[aslot]), aphase ^ 1u);             // the MMAs that read this A slot have retired
+      tc_fence_after();
+      const uint32_t a_addr = tmem_base + lane_field + kTsACol0 + static_cast<uint32_t>(aslot) * 64u;
+      tc_st32(a_addr, hi);
+      tc_st32(a_addr + 32u, lo);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_full[aslot]));
+      if (++aslot == R) { aslot = 0; aphase ^= 1u; }
+      adv(ci);
+    }
+    cp_async_wait<0>();
+  } else if (warp >= kMmaWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
+    if (warp == kBLoadWarp && lane == 0) {
+      // ===================================== packed-weight loader =====================================
+      if constexpr (B_RES) {
+        const int64_t nb = blockIdx.x % num_n;        // grid is a multiple of num_n: every tile of this CTA has this nb
+        if (blockIdx.x < tiles) {
+          mbar_arrive_expect_tx(smem_u32(&bar_bres), static_cast<uint32_t>(num_ks) * kBStage);
+          for (int64_t ks = 0; ks < num_ks; ++ks)
+            bulk_g2s(smem_u32(smem_b + static_cast<size_t>(ks) * kBStage), p.Bp + static_cast<size_t>(nb * num_ks + ks) * (2 * BN * 32),
+                     kBStage, smem_u32(&bar_bres));
+        }
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+          const int64_t nb = tile % num_n;
+          for (int64_t ks = 0; ks < num_ks; ++ks) {
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+            mbar_arrive_expect_tx(smem_u32(&bar_full[stage]), kBStage);
+            bulk_g2s(smem_u32(smem_b + static_cast<size_t>(stage) * kBStage), p.Bp + static_cast<size_t>(nb * num_ks + ks) * (2 * BN * 32),
+                     kBStage, smem_u32(&bar_full[stage]));
+            if (++stage == R) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    // ===================================== MMA issuer =====================================
+    if (warp == kMmaWarp && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t cc = 0;
+      if constexpr (B_RES) {
+        if (blockIdx.x < tiles) mbar_wait(smem_u32(&bar_bres), 0);
+      }
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int64_t ks = 0; ks < num_ks; ++ks, ++cc) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          const uint32_t b_hi = smem_u32(smem_b + static_cast<size_t>(B_RES ? ks : stage) * kBStage), b_lo = b_hi + kBTile;
+          const uint32_t a_hi = tmem_base + kTsACol0 + static_cast<uint32_t>(stage) * 64u, a_lo = a_hi + 32u;
+          const uint32_t buf = cc % kTsAcc;
+          mbar_wait(smem_u32(&bar_tempty[buf]), ((cc / kTsAcc) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          uint32_t accum = 0;
+          // small terms first: lo*hi, hi*lo, then hi*hi (terms >= 4 adds lo*lo in front)
+          for (int term = ((p.dbg & 4) ? 3 : (p.terms >= 4 ? 0 : 1)); term < 4; ++term) {
+            const uint32_t ab = (term == 3 || term == 2) ? a_hi : a_lo;
+            const uint32_t bb = (term == 3 || term == 1) ? b_hi : b_lo;
+            for (int j = 0; j < BK / 8; ++j) {
+              tc_mma_tf32_ts(d_tmem, ab + static_cast<uint32_t>(j) * 8u, make_sdesc(bb + j * 32u, 16u, 1024u, 2u), idesc, accum);
+              accum = 1u;
+            }
+          }
+          tc_commit(smem_u32(&bar_tfull[buf]));
+          tc_commit(smem_u32(&bar_empty[stage]));
+          if (++stage == R) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue =====================================
+    const int q = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
+    float* stg = reinterpret_cast<float*>(smem_stg) + (warp - kEpiWarp0) * (32 * kStgLd);
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * CW);
+    uint32_t cc = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int64_t nb = tile % num_n, mb = tile / num_n;
+      const int64_t n0 = nb * BN + half * CW;
+      float acc[CW];
+#pragma unroll
+      for (int i = 0; i < CW; ++i) acc[i] = 0.f;
+      for (int64_t c = 0; c < num_ks; ++c, ++cc) {
+        const uint32_t buf = cc % kTsAcc;
+        mbar_wait(smem_u32(&bar_tfull[buf]), (cc / kTsAcc) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < CW; c0 += 32) {
+          if (p.dbg & 1) break;
+          uint32_t r0[32];
+          tc_ld32(lane_base + buf * BN + c0, r0);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bar_tempty[buf]));
+      }
+      float* C = p.C;
+      constexpr int LR = PW / 4;
+      const int sub = lane / LR, c4 = (lane % LR) * 4;
+      const bool vec_c = (p.ldc % 4 == 0) && aligned16(C) && (n0 % 4 == 0);
+      const bool vec_a = p.C_act && (p.ldca % 4 == 0) && aligned16(p.C_act) && (n0 % 4 == 0);
+      const bool vec_p = p.act_pre && (p.ld_pre % 4 == 0) && aligned16(p.act_pre) && (n0 % 4 == 0);
+      const bool vec_g = p.gtab && (p.ld_gtab % 4 == 0) && aligned16(p.gtab) && (n0 % 4 == 0);
+#pragma unroll
+      for (int c0 = 0; c0 < CW; c0 += PW) {
+        if (p.dbg & 8) break;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < PW; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * kStgLd + j) = make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
+        __syncwarp();
+        const int64_t n = n0 + c0 + c4;
+        if (n < p.N) {
+          const bool whole = n + 4 <= p.N;
+          float b4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.bias) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (n + e < p.N) b4[e] = __ldg(p.bias + n + e);
+          }
+#pragma unroll 1
+          for (int it = 0; it < LR; ++it) {
+            const int r = it * (32 / LR) + sub;
+            const int64_t grow = mb * BM + q * 32 + r;
+            if (grow >= p.M) continue;
+            const float4 t4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + c4);
+            float v[4] = {t4.x + b4[0], t4.y + b4[1], t4.z + b4[2], t4.w + b4[3]};
+            float* dst = C + grow * p.ldc + n;
+            if (p.accumulate) {
+              if (whole && vec_c) {
+                const float4 o = *reinterpret_cast<const float4*>(dst);
+                v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (n + e < p.N) v[e] += dst[e];
+              }
+            }
+            if (p.gtab) {
+              const int64_t id = p.gid_bytes == 8 ? static_cast<const int64_t*>(p.gids)[grow]
+                                                  : static_cast<int64_t>(static_cast<const int32_t*>(p.gids)[grow]);
+              const float* tp = p.gtab + id * p.ld_gtab + n;
+              if (whole && vec_g) {
+                const float4 o = ldg4(tp);
+                v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (n + e < p.N) v[e] += __ldg(tp + e);
+              }
+            }
+            if (p.act_pre) {
+              const float* pp = p.act_pre + grow * p.ld_pre + n;
+              float u[4] = {0.f, 0.f, 0.f, 0.f};
+              if (whole && vec_p) {
+                const float4 o = ldg4(pp);
+                u[0] = o.x; u[1] = o.y; u[2] = o.z; u[3] = o.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (n + e < p.N) u[e] = __ldg(pp + e);
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] *= act_grad(u[e], p.act);
+            }
+            if (whole && vec_c) {
+              st4(dst, make_float4(v[0], v[1], v[2], v[3]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (n + e < p.N) dst[e] = v[e];
+            }
+            if (p.C_act) {
+              float* da = p.C_act + grow * p.ldca + n;
+              if (whole && vec_a) {
+                st4(da, make_float4(act_apply(v[0], p.act), act_apply(v[1], p.act), act_apply(v[2], p.act), act_apply(v[3], p.act)));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (n + e < p.N) da[e] = act_apply(v[e], p.act);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 __global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t MN, int64_t N,
                                         float* __restrict__ out, int64_t ldo, int accumulate) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -689,6 +1023,39 @@ size_t packed_b_bytes(int64_t N, int64_t K) {
   return align_up(static_cast<size_t>(ceil_div(N, bn)) * ceil_div(K, BK) * (2 * bn * 128));
 }
 
+template <int BN, int S, bool B_RES>
+int launch_ts(TcParams p, cudaStream_t stream) {
+  p.stages = S;
+  p.dbg = env_int("SEGGER_B200_TC_DBG", 0, 255, 0);
+  constexpr size_t smem = static_cast<size_t>(S) * (2 * BN * 128) + static_cast<size_t>(kTsRaw) * (BM * 128) + stg_bytes(kPW) + 1024;
+  static_assert(smem + 512 <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_ts_kernel<BN, S, B_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return set_error(SGB_ERR_CUDA, "tc gemm (ts): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int64_t num_n = ceil_div(p.N, BN);
+  const int64_t tiles = ceil_div(p.M, BM) * num_n;
+  int64_t grid = tiles < sm_count() ? tiles : sm_count();
+  if (B_RES) {                         // a persistent CTA keeps its n-tile: grid multiple of num_n
+    grid = grid / num_n * num_n;
+    if (grid < num_n) grid = num_n < tiles ? num_n : tiles;
+  }
+  gemm_tf32x3_ts_kernel<BN, S, B_RES><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
+  return check_launch("gemm_tf32x3_ts");
+}
+
+// SEGGER_B200_GEMM_TS=0 keeps the second-generation kernel (A/B of the two designs)
+static bool ts_enabled() {
+  static int flag = -1;
+  if (flag < 0) {
+    const char* e = getenv("SEGGER_B200_GEMM_TS");
+    flag = (e && e[0] == '0') ? 0 : 1;
+  }
+  return flag == 1;
+}
+
 int run_packed(TcParams p, const float* w, int64_t ldw, int src_mn, void* ws, cudaStream_t stream) {
   const int bn = pick_bn(p.N);
   const int num_n = static_cast<int>(ceil_div(p.N, bn)), num_ks = static_cast<int>(ceil_div(p.K, BK));
@@ -699,6 +1066,22 @@ int run_packed(TcParams p, const float* w, int64_t ldw, int src_mn, void* ws, cu
   int rc = check_launch("pack_b");
   if (rc != SGB_OK) return rc;
   p.Bp = out;
+  if (ts_enabled() && p.splits == 1) {
+    // resident weights when every k-stage of an n-tile's packed panel fits in 128 KB beside the raw-A ring
+    if (bn == 128) {
+      if (num_ks <= 4 && num_n <= sm_count()) {
+        if (num_ks <= 2) return launch_ts<128, 2, true>(p, stream);
+        return launch_ts<128, 4, true>(p, stream);
+      }
+      return launch_ts<128, 4, false>(p, stream);
+    }
+    if (num_ks <= 8 && num_n <= sm_count()) {
+      if (num_ks <= 2) return launch_ts<64, 2, true>(p, stream);
+      if (num_ks <= 4) return launch_ts<64, 4, true>(p, stream);
+      return launch_ts<64, 8, true>(p, stream);
+    }
+    return launch_ts<64, 4, false>(p, stream);
+  }
   return bn == 64 ? launch_tc<64, false, false, true>(p, stream) : launch_tc<128, false, false, true>(p, stream);
 }
 
