@@ -641,6 +641,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
 // TMEM: [0, 2*BN) two chunk accumulators, [256, 512) four A slots of 64 columns (hi 32 | lo 32).
 // ================================================================================================
 constexpr int kTsAcc = 2;
+// register budget of the TS kernel (512 threads, 64K registers): 128 x 120 + 256 x 176 + 128 x 40 = 65536
+constexpr int kTsRegsProducer = 120, kTsRegsEpilogue = 176, kTsRegsControl = 40;
 constexpr int kTsRaw = 4;          // raw-A landing ring (16 KB slots), filled kTsRaw-1 slabs ahead
 constexpr int kTsASlots = 4;       // TMEM A slots
 constexpr uint32_t kTsACol0 = 256;
@@ -671,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
   constexpr uint32_t kBTile = BN * 128;            // bytes of one hi (or lo) B tile of a k-stage
   constexpr uint32_t kBStage = 2 * kBTile;
   constexpr uint32_t kRawTile = BM * 128;          // 16 KB: raw fp32 A slab
-  constexpr int CW = BN / 2;
+  constexpr int CW = BN;                            // an epilogue thread owns one row x all BN columns of its group's tile
   constexpr int PW = kPW;
   constexpr int kStgLd = PW + 4;
   static_assert(kTsAcc * BN <= static_cast<int>(kTsACol0), "accumulators overlap the A slots");
@@ -695,7 +697,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
     }
     for (int a = 0; a < kTsAcc; ++a) {
       mbar_init(smem_u32(&bar_tfull[a]), 1);
-      mbar_init(smem_u32(&bar_tempty[a]), kEpiWarps * 32);
+      mbar_init(smem_u32(&bar_tempty[a]), (kEpiWarps / 2) * 32);     // the epilogue GROUP that owns the tile
     }
     mbar_init(smem_u32(&bar_bres), 1);
     fence_barrier_init();
@@ -715,7 +717,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
 
   if (warp < kProducerWarps) {
     // ===================================== producers =====================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTsRegsProducer));
     const int t = threadIdx.x;                        // = row of the tile this thread owns in the split
     // flattened slab sequence of this CTA: (tile, ks)
     struct Cur { int64_t tile, ks; bool live; };
@@ -748,6 +750,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       // this thread's row of the slab: 8 x 16 B at the swizzled chunk positions
       const uint8_t* rt = smem_rawa + static_cast<size_t>(crslot) * kRawTile;
       uint32_t hi[32], lo[32];
+      if (p.dbg & 2) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) { hi[e] = 0u; lo[e] = 0u; }
+      } else
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const float4 v = *reinterpret_cast<const float4*>(rt + chunk_offset<BM, false>(t, c));
@@ -763,9 +769,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       mbar_wait(smem_u32(&bar_empty[aslot]), aphase ^ 1u);             // the MMAs that read this A slot have retired
       tc_fence_after();
       const uint32_t a_addr = tmem_base + lane_field + kTsACol0 + static_cast<uint32_t>(aslot) * 64u;
-      tc_st32(a_addr, hi);
-      tc_st32(a_addr + 32u, lo);
-      tc_wait_st();
+      if (!(p.dbg & 16)) {
+        tc_st32(a_addr, hi);
+        tc_st32(a_addr + 32u, lo);
+        tc_wait_st();
+      }
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_full[aslot]));
       if (++aslot == R) { aslot = 0; aphase ^= 1u; }
@@ -773,7 +781,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
     }
     cp_async_wait<0>();
   } else if (warp >= kMmaWarp) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTsRegsControl));
     if (warp == kBLoadWarp && lane == 0) {
       // ===================================== packed-weight loader =====================================
       if constexpr (B_RES) {
@@ -836,14 +844,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
     }
   } else {
     // ===================================== epilogue =====================================
+    // Two groups of four warps alternate TILES: while one group transposes and writes its finished tile out, the other
+    // one drains the chunk accumulators of the next tile, so the tensor core never waits for a write-out (with both
+    // halves of one tile on all eight warps the write-out cost 40 % of the K = 128 GEMMs: knock-out 8).
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTsRegsEpilogue));
     const int q = warp & 3;
-    const int half = (warp - kEpiWarp0) >> 2;
+    const int grp = (warp - kEpiWarp0) >> 2;
     float* stg = reinterpret_cast<float*>(smem_stg) + (warp - kEpiWarp0) * (32 * kStgLd);
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * CW);
-    uint32_t cc = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int64_t ti = grp; blockIdx.x + ti * gridDim.x < tiles; ti += 2) {
+      const int64_t tile = blockIdx.x + ti * gridDim.x;
       const int64_t nb = tile % num_n, mb = tile / num_n;
-      const int64_t n0 = nb * BN + half * CW;
+      const int64_t n0 = nb * BN;
+      uint32_t cc = static_cast<uint32_t>(ti * num_ks);
       float acc[CW];
 #pragma unroll
       for (int i = 0; i < CW; ++i) acc[i] = 0.f;
