@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
   uint8_t* smem_b = smem;                                              // S stages (ring) or S resident k-stages
   uint8_t* smem_rawa = smem + static_cast<size_t>(S) * kBStage;        // kTsRaw landing slots
   uint8_t* smem_stg = smem_rawa + static_cast<size_t>(kTsRaw) * kRawTile;
-  __shared__ uint64_t bar_full[kTsASlots], bar_empty[kTsASlots], bar_tfull[kTsAcc], bar_tempty[kTsAcc], bar_bres;
+  __shared__ uint64_t bar_full[kTsASlots], bar_empty[kTsASlots], bar_tfull[kTsAcc], bar_tempty[kTsAcc], bar_bres, bar_turn[2];
   __shared__ uint32_t tmem_base_holder;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -700,6 +700,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       mbar_init(smem_u32(&bar_tempty[a]), (kEpiWarps / 2) * 32);     // the epilogue GROUP that owns the tile
     }
     mbar_init(smem_u32(&bar_bres), 1);
+    mbar_init(smem_u32(&bar_turn[0]), (kEpiWarps / 2) * 32);
+    mbar_init(smem_u32(&bar_turn[1]), (kEpiWarps / 2) * 32);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
@@ -857,6 +859,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       const int64_t nb = tile % num_n, mb = tile / num_n;
       const int64_t n0 = nb * BN;
       uint32_t cc = static_cast<uint32_t>(ti * num_ks);
+      // The chunk barriers carry one parity bit: a group may only start waiting for its tile's chunks once the other
+      // group has drained the previous tile, otherwise the wait would match a completion two phases early.  The
+      // hand-over is a barrier per group ("your turn"), completed by the 128 threads of the other group.
+      if (ti > 0) mbar_wait(smem_u32(&bar_turn[grp]), static_cast<uint32_t>(((ti >> 1) - (grp == 0 ? 1 : 0)) & 1));
       float acc[CW];
 #pragma unroll
       for (int i = 0; i < CW; ++i) acc[i] = 0.f;
@@ -876,6 +882,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
         tc_fence_before();
         mbar_arrive(smem_u32(&bar_tempty[buf]));
       }
+      mbar_arrive(smem_u32(&bar_turn[grp ^ 1]));      // the other group may now wait for the next tile's chunks
       float* C = p.C;
       constexpr int LR = PW / 4;
       const int sub = lane / LR, c4 = (lane % LR) * 4;
