@@ -536,13 +536,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
       const bool vec_c = (p.ldc % 4 == 0) && aligned16(C) && (n0 % 4 == 0);
       const bool vec_a = p.C_act && (p.ldca % 4 == 0) && aligned16(p.C_act) && (n0 % 4 == 0);
       const bool vec_p = p.act_pre && (p.ld_pre % 4 == 0) && aligned16(p.act_pre) && (n0 % 4 == 0);
-#pragma unroll
-      for (int c0 = 0; c0 < CW; c0 += PW) {
+      // One ROLLED loop over the write-out passes: the body below (bias / accumulate / table gather / activation, each
+      // behind a run-time flag) is emitted once instead of CW/PW times -- unrolled it was over half of the kernel's SASS
+      // and the instruction cache, not the LSU, bounded the write-out.  Only the register -> staging copy is selected
+      // per pass (compile-time register indices under `pass == k`).
+#pragma unroll 1
+      for (int pass = 0; pass < CW / PW; ++pass) {
+        const int c0 = pass * PW;
         if (p.dbg & 8) break;
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < PW; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * kStgLd + j) = make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
+        for (int k = 0; k < CW / PW; ++k) {
+          if (pass == k) {
+#pragma unroll
+            for (int j = 0; j < PW; j += 4)
+              *reinterpret_cast<float4*>(stg + lane * kStgLd + j) =
+                  make_float4(acc[k * PW + j], acc[k * PW + j + 1], acc[k * PW + j + 2], acc[k * PW + j + 3]);
+          }
+        }
         __syncwarp();
         const int64_t n = n0 + c0 + c4;
         if (n < p.N) {
@@ -667,13 +678,15 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
 }
 
-template <int BN, int S, bool B_RES>
+template <int BN, int S, bool B_RES, bool PP>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t kBTile = BN * 128;            // bytes of one hi (or lo) B tile of a k-stage
   constexpr uint32_t kBStage = 2 * kBTile;
   constexpr uint32_t kRawTile = BM * 128;          // 16 KB: raw fp32 A slab
-  constexpr int CW = BN;                            // an epilogue thread owns one row x all BN columns of its group's tile
+  // PP: two epilogue groups alternate tiles (a thread owns one row x all BN columns); else all eight warps share a
+  // tile (one row x BN/2 columns per thread)
+  constexpr int CW = PP ? BN : BN / 2;
   constexpr int PW = kPW;
   constexpr int kStgLd = PW + 4;
   static_assert(kTsAcc * BN <= static_cast<int>(kTsACol0), "accumulators overlap the A slots");
@@ -697,7 +710,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
     }
     for (int a = 0; a < kTsAcc; ++a) {
       mbar_init(smem_u32(&bar_tfull[a]), 1);
-      mbar_init(smem_u32(&bar_tempty[a]), (kEpiWarps / 2) * 32);     // the epilogue GROUP that owns the tile
+      mbar_init(smem_u32(&bar_tempty[a]), (PP ? kEpiWarps / 2 : kEpiWarps) * 32);   // the epilogue warps that own the tile
     }
     mbar_init(smem_u32(&bar_bres), 1);
     mbar_init(smem_u32(&bar_turn[0]), (kEpiWarps / 2) * 32);
@@ -851,18 +864,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
     // halves of one tile on all eight warps the write-out cost 40 % of the K = 128 GEMMs: knock-out 8).
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTsRegsEpilogue));
     const int q = warp & 3;
-    const int grp = (warp - kEpiWarp0) >> 2;
+    const int grp = (warp - kEpiWarp0) >> 2;          // PP: tile parity this group serves; else: column half
     float* stg = reinterpret_cast<float*>(smem_stg) + (warp - kEpiWarp0) * (32 * kStgLd);
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int64_t ti = grp; blockIdx.x + ti * gridDim.x < tiles; ti += 2) {
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (PP ? 0u : static_cast<uint32_t>(grp * CW));
+    for (int64_t ti = PP ? grp : 0; blockIdx.x + ti * gridDim.x < tiles; ti += PP ? 2 : 1) {
       const int64_t tile = blockIdx.x + ti * gridDim.x;
       const int64_t nb = tile % num_n, mb = tile / num_n;
-      const int64_t n0 = nb * BN;
+      const int64_t n0 = nb * BN + (PP ? 0 : grp * CW);
       uint32_t cc = static_cast<uint32_t>(ti * num_ks);
       // The chunk barriers carry one parity bit: a group may only start waiting for its tile's chunks once the other
       // group has drained the previous tile, otherwise the wait would match a completion two phases early.  The
       // hand-over is a barrier per group ("your turn"), completed by the 128 threads of the other group.
-      if (ti > 0) mbar_wait(smem_u32(&bar_turn[grp]), static_cast<uint32_t>(((ti >> 1) - (grp == 0 ? 1 : 0)) & 1));
+      if (PP && ti > 0) mbar_wait(smem_u32(&bar_turn[grp]), static_cast<uint32_t>(((ti >> 1) - (grp == 0 ? 1 : 0)) & 1));
       float acc[CW];
 #pragma unroll
       for (int i = 0; i < CW; ++i) acc[i] = 0.f;
@@ -882,7 +895,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
         tc_fence_before();
         mbar_arrive(smem_u32(&bar_tempty[buf]));
       }
-      mbar_arrive(smem_u32(&bar_turn[grp ^ 1]));      // the other group may now wait for the next tile's chunks
+      if (PP) mbar_arrive(smem_u32(&bar_turn[grp ^ 1]));      // the other group may now wait for the next tile's chunks
       float* C = p.C;
       constexpr int LR = PW / 4;
       const int sub = lane / LR, c4 = (lane % LR) * 4;
@@ -890,13 +903,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       const bool vec_a = p.C_act && (p.ldca % 4 == 0) && aligned16(p.C_act) && (n0 % 4 == 0);
       const bool vec_p = p.act_pre && (p.ld_pre % 4 == 0) && aligned16(p.act_pre) && (n0 % 4 == 0);
       const bool vec_g = p.gtab && (p.ld_gtab % 4 == 0) && aligned16(p.gtab) && (n0 % 4 == 0);
-#pragma unroll
-      for (int c0 = 0; c0 < CW; c0 += PW) {
+      // One ROLLED loop over the write-out passes: the body below (bias / accumulate / table gather / activation, each
+      // behind a run-time flag) is emitted once instead of CW/PW times -- unrolled it was over half of the kernel's SASS
+      // and the instruction cache, not the LSU, bounded the write-out.  Only the register -> staging copy is selected
+      // per pass (compile-time register indices under `pass == k`).
+#pragma unroll 1
+      for (int pass = 0; pass < CW / PW; ++pass) {
+        const int c0 = pass * PW;
         if (p.dbg & 8) break;
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < PW; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * kStgLd + j) = make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
+        for (int k = 0; k < CW / PW; ++k) {
+          if (pass == k) {
+#pragma unroll
+            for (int j = 0; j < PW; j += 4)
+              *reinterpret_cast<float4*>(stg + lane * kStgLd + j) =
+                  make_float4(acc[k * PW + j], acc[k * PW + j + 1], acc[k * PW + j + 2], acc[k * PW + j + 3]);
+          }
+        }
         __syncwarp();
         const int64_t n = n0 + c0 + c4;
         if (n < p.N) {
@@ -1043,15 +1067,15 @@ size_t packed_b_bytes(int64_t N, int64_t K) {
   return align_up(static_cast<size_t>(ceil_div(N, bn)) * ceil_div(K, BK) * (2 * bn * 128));
 }
 
-template <int BN, int S, bool B_RES>
-int launch_ts(TcParams p, cudaStream_t stream) {
+template <int BN, int S, bool B_RES, bool PP>
+int launch_ts_pp(TcParams p, cudaStream_t stream) {
   p.stages = S;
   p.dbg = env_int("SEGGER_B200_TC_DBG", 0, 255, 0);
   constexpr size_t smem = static_cast<size_t>(S) * (2 * BN * 128) + static_cast<size_t>(kTsRaw) * (BM * 128) + stg_bytes(kPW) + 1024;
   static_assert(smem + 512 <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_ts_kernel<BN, S, B_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_ts_kernel<BN, S, B_RES, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return set_error(SGB_ERR_CUDA, "tc gemm (ts): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -1062,8 +1086,20 @@ int launch_ts(TcParams p, cudaStream_t stream) {
     grid = grid / num_n * num_n;
     if (grid < num_n) grid = num_n < tiles ? num_n : tiles;
   }
-  gemm_tf32x3_ts_kernel<BN, S, B_RES><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
+  gemm_tf32x3_ts_kernel<BN, S, B_RES, PP><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
   return check_launch("gemm_tf32x3_ts");
+}
+
+// Epilogue mode, chosen per shape from scripts/bench_gemm.py on B200 (profiles/r2_gemm_epilogue_modes.md): alternating
+// tile groups hide the write-out behind the next tile's MMAs once the reduction is deep enough for four warps to finish
+// a tile inside it (BN = 64: >= 4 k-stages; BN = 128: >= 10); on shallower tiles all eight warps share one tile.
+// SEGGER_B200_GEMM_PP=0|1 forces a mode.
+template <int BN, int S, bool B_RES>
+int launch_ts(TcParams p, cudaStream_t stream) {
+  static int force = env_int("SEGGER_B200_GEMM_PP", 0, 1, -1);
+  const int64_t num_ks = ceil_div(p.K, BK);
+  const bool pp = force >= 0 ? force == 1 : (BN == 64 ? num_ks >= 4 : num_ks >= 10);
+  return pp ? launch_ts_pp<BN, S, B_RES, true>(p, stream) : launch_ts_pp<BN, S, B_RES, false>(p, stream);
 }
 
 // SEGGER_B200_GEMM_TS=0 keeps the second-generation kernel (A/B of the two designs)
