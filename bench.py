@@ -124,6 +124,18 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc = None
 
+    def wait_first_sample(self, timeout: float = 15.0):
+        """Block until nvidia-smi has printed its first line: its start-up (NVML initialisation, ~1 s on a fresh box)
+        holds driver locks that stall kernel launches, which must not overlap the timed steps."""
+        t0 = time.time()
+        while self.proc is not None and time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                pass
+            time.sleep(0.05)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
@@ -314,6 +326,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_cuda"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-step", action="store_true",
+                    help="profiling aid: the headline step legs only (the launch list under ncu), no secondary legs")
     ap.add_argument("--infer-tx", type=int, default=20_000_000, help="transcripts of the configs[2] inference leg (0: skip)")
     ap.add_argument("--max-edges-per-batch", type=int, default=8_000_000,
                     help="edges per predict batch of the inference leg (the reference's default is 1M: also reported)")
@@ -391,11 +405,13 @@ def main():
         return float(ms.item())
 
     # ---- device-resident measurement -----------------------------------------------------------
-    # the clock sampler (an nvidia-smi child process) is started BEFORE the warm-up: spawning it stalls the launching
-    # thread for tens of milliseconds, which must not land inside the timed steps; it keeps sampling through them
+    # the clock sampler (an nvidia-smi child process) is started BEFORE the warm-up and has printed its first sample
+    # before the warm-up begins: its start-up stalls kernel launches for up to a second on a fresh box, which must not
+    # land inside the timed steps; it keeps sampling (every 100 ms) through them
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
     for _ in range(W):
         train_step(dev_in)
     l0 = ops.LAUNCHES
@@ -448,6 +464,13 @@ def main():
             traceback.print_exc()
             return {"error": f"{type(e).__name__}: {e}"}
 
+    if args.only_step:
+        if rank == 0:
+            emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                  "ms_per_step": ms_step, "e2e_ms_per_step": ms_e2e, "gpu_launches": launches, "only_step": True})
+        if world > 1:
+            dist.destroy_process_group()
+        return
     loss_step = guarded(losses_step_time, lit, dev_in, n_tx, n_cells, device, flat, opt, timed, K, ms_step)
     hbm_peak, bf16_peak, peak_src = peaks()
     roof = guarded(kernel_rooflines, dev_in, n_tx, n_cells, heads, hid, n_layers, device, hbm_peak, bf16_peak, peak_src,
@@ -455,6 +478,7 @@ def main():
     strong = guarded(strong_scaling_leg, args.workload, lit, flat, opt, device, world, rank, timed, K, W, t_tx.size(1))
     seg = guarded(segmentation_throughput, lit, host, ts, device, world, rank, timed, hbm_peak, peak_src, k,
                   not args.no_cpu_baseline)
+    small = guarded(small_tile_graph_leg, device, timed, K) if world == 1 else None
     infer = None
     if args.infer_tx > 0 and args.workload == "cfg2":
         infer = guarded(inference_cfg3_leg, lit, args.infer_tx, args.max_edges_per_batch, device, world, rank, timed, hbm_peak)
@@ -500,12 +524,68 @@ def main():
         "strong_scaling": strong,
         "segmentation": seg,
         "inference_cfg3": infer,
+        "small_tile_cfg1": small,
         "training_step_with_losses": loss_step,
         "cpu_baseline": cpu,
     }
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def small_tile_graph_leg(device, timed, K):
+    """BASELINE configs[0] (one 50k-transcript / 500-cell tile, the reference's own tile size): the training step eager
+    (launch-bound: ~300 launches of a few microseconds) and replayed from a CUDA graph (segger_b200.graphs).  The
+    tile's CSRs are built once -- tiles keep their edges across epochs -- in BOTH variants, so the two differ only in
+    how the launches reach the GPU."""
+    from segger_b200 import graphs, ops
+    from segger_b200.lightning_model import LitISTEncoder
+    n_tx, n_cells, k, in_c, hid, out_c, n_mid, heads = WORKLOADS["cfg1"]
+    ts, host = build_workload("cfg1", seed=0, device=device)
+    torch.manual_seed(0)
+    lit = LitISTEncoder(ts.n_genes, in_channels=in_c, hidden_channels=hid, out_channels=out_c, n_mid_layers=n_mid,
+                        n_heads=heads).to(device)
+    lit.train()
+    model = lit.model
+    d = to_device(host, device, TRAIN_KEYS)
+    inputs = model_inputs(d)
+    with torch.no_grad():
+        model(*inputs)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    t_tx = torch.randn(n_tx, out_c, generator=g).to(device)
+    t_bd = torch.randn(n_cells, out_c, generator=g).to(device)
+    edge_layers = (n_mid + 2) * (host["e_tt"].size(1) + host["e_tb"].size(1))
+
+    def forward_loss():
+        out = model(*inputs)
+        return (out["tx"] * t_tx).sum() / n_tx + (out["bd"] * t_bd).sum() / n_cells
+
+    def eager():
+        opt.zero_grad(set_to_none=True)
+        forward_loss().backward()
+        opt.step()
+
+    for _ in range(3):
+        eager()
+    l0 = ops.LAUNCHES
+    reps = max(20, K)
+    ms_eager = timed(eager, reps) / reps
+    launches_eager = (ops.LAUNCHES - l0) / reps
+    step = graphs.graphed_train_step(forward_loss, opt, warmup=3)
+    for _ in range(3):
+        step.replay()
+    ms_graph = timed(step.replay, reps) / reps
+    loss = float(step.out.item())
+    return {"workload": WORKLOADS_DESC["cfg1"], "edge_layers_per_step": edge_layers,
+            "eager": {"ms_per_step": ms_eager, "value": edge_layers / (ms_eager * 1e-3), "gpu_launches_per_step": launches_eager},
+            "cuda_graph": {"ms_per_step": ms_graph, "value": edge_layers / (ms_graph * 1e-3),
+                           "gpu_launches_in_graph": step.launches, "loss_finite": bool(np.isfinite(loss))},
+            "unit": UNIT, "steps": reps,
+            "what": "forward + synthetic linear loss + backward + fused capturable Adam on one resident tile; CSRs of the "
+                    "tile built once (static across epochs) in both variants; dropout seeds from a device word in the "
+                    "graph (fresh mask every replay)"}
 
 
 def losses_step_time(lit, d, n_tx, n_cells, device, flat, opt, timed, K, ms_synth):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 200
+#define SGB_VERSION 201
 
 #if defined(__GNUC__)
 #define SGB_API __attribute__((visibility("default")))
@@ -73,12 +73,15 @@ SGB_API int sgb_csr_build(const void* edge_index, int idx_bytes, int64_t row_str
  * out = pre-activation (o + bias); out_act (optional) = GELU(out) (fuses ist_encoder.py:325).
  * out may be NULL when out_act is given (inference: only the activated output is written).
  * stat_max/stat_den [n_dst,H] are saved for the backward.  seed/p_drop/training drive the
- * counter-based dropout keyed on (seed, original edge id, head).
+ * counter-based dropout keyed on (seed, original edge id, head).  seed_dev (or NULL) points to one device-resident
+ * 64-bit word that is ADDED to seed when the kernel runs: a captured CUDA graph freezes by-value arguments, so a
+ * replayed training step advances that word to draw a fresh mask (forward and backward read the same word).
  * ---------------------------------------------------------------------------------------- */
 SGB_API int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, int64_t ld_r, const float* att,
                   const float* bias /*or NULL*/, const int32_t* dst_rowptr, const int32_t* dst_col,
                   const int32_t* dst_eid, int64_t n_dst, int64_t E, int H, int C, float negative_slope,
-                  float p_drop, uint64_t seed, int training, float* out /*or NULL*/, int64_t ld_out,
+                  float p_drop, uint64_t seed, const uint64_t* seed_dev /*or NULL*/, int training,
+                  float* out /*or NULL*/, int64_t ld_out,
                   float* out_act /*or NULL*/, int64_t ld_act, float* stat_max, float* stat_den,
                   void* stream);
 
@@ -106,8 +109,8 @@ SGB_API int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, int6
                   const int32_t* dst_rowptr, const int32_t* dst_col, const int32_t* dst_eid,
                   const int32_t* src_rowptr, const int32_t* src_dst, const int32_t* src_pos,
                   int64_t n_src, int64_t n_dst, int64_t E, int H, int C, float negative_slope,
-                  float p_drop, uint64_t seed, int training, const float* stat_max,
-                  const float* stat_den, float* grad_x_l, int64_t ld_gl, float* grad_x_r,
+                  float p_drop, uint64_t seed, const uint64_t* seed_dev /*or NULL*/, int training,
+                  const float* stat_max, const float* stat_den, float* grad_x_l, int64_t ld_gl, float* grad_x_r,
                   int64_t ld_gr, float* grad_att, float* grad_bias /*or NULL*/, void* ws,
                   size_t ws_bytes, void* stream);
 

@@ -70,6 +70,7 @@ template <int VEC> struct Chunk { static constexpr int value = VEC == 1 ? 8 : (V
 // ================================================================================================
 template <int VEC, int CV>
 __global__ void __launch_bounds__(256) gatv2_fwd_vec_kernel(const GatParams p) {
+  const uint64_t seed_eff = p.training ? gat_seed(p) : 0;
   using HM = HeadMap<VEC, CV>;
   constexpr int S = HM::kSlots;
   constexpr int CH = Chunk<VEC>::value;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(256) gatv2_fwd_vec_kernel(const GatParams p) {
           s[q] += pe;
           w[q] = pe;
           if (p.training)
-            w[q] = rng_keep(p.seed, e, p.H, HM::head(q, lane), p.drop_thr) ? pe * p.keep_scale : 0.f;
+            w[q] = rng_keep(seed_eff, e, p.H, HM::head(q, lane), p.drop_thr) ? pe * p.keep_scale : 0.f;
         }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) fma4(acc[v], w[HM::slot_of(v)], x[c][v]);
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) gatv2_fwd_vec_kernel(const GatParams p) {
 // ================================================================================================
 template <int VEC, int CV>
 __global__ void __launch_bounds__(256) gatv2_bwd_dst_vec_kernel(const GatParams p) {
+  const uint64_t seed_eff = p.training ? gat_seed(p) : 0;
   using HM = HeadMap<VEC, CV>;
   constexpr int S = HM::kSlots;
   constexpr int CH = Chunk<VEC>::value;
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(256) gatv2_bwd_dst_vec_kernel(const GatParams 
             const int h = HM::head(q, lane);
             const float alpha = __expf(lg[q] - m[q]) * inv[q];
             float ks = 1.0f;
-            if (p.training) ks = rng_keep(p.seed, e, p.H, h, p.drop_thr) ? p.keep_scale : 0.f;
+            if (p.training) ks = rng_keep(seed_eff, e, p.H, h, p.drop_thr) ? p.keep_scale : 0.f;
             delta[q] = alpha * (dd[q] * ks - cdot[q]);
             if (HM::writer(lane)) {
               const int64_t idx = static_cast<int64_t>(base + c) * p.H + h;
@@ -401,6 +403,7 @@ __device__ __forceinline__ float warp_sum(float x) {
 
 template <int TC>
 __global__ void __launch_bounds__(256) gatv2_fwd_gen_kernel(const GatParams p) {
+  const uint64_t seed_eff = p.training ? gat_seed(p) : 0;
   const int lane = threadIdx.x & 31;
   const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (item >= p.n_dst * p.H) return;
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(256) gatv2_fwd_gen_kernel(const GatParams p) {
     const float pe = __expf(lg - mn);
     s = s * sc + pe;
     float w = pe;
-    if (p.training) w = rng_keep(p.seed, __ldg(p.eid + k), p.H, h, p.drop_thr) ? pe * p.keep_scale : 0.f;
+    if (p.training) w = rng_keep(seed_eff, __ldg(p.eid + k), p.H, h, p.drop_thr) ? pe * p.keep_scale : 0.f;
 #pragma unroll
     for (int t = 0; t < TC; ++t) acc[t] = acc[t] * sc + w * x[t];
     m = mn;
@@ -459,6 +462,7 @@ __global__ void __launch_bounds__(256) gatv2_fwd_gen_kernel(const GatParams p) {
 // warps_total must be a multiple of H so that every warp keeps one head for its whole life.
 template <int TC>
 __global__ void __launch_bounds__(256) gatv2_bwd_dst_gen_kernel(const GatParams p) {
+  const uint64_t seed_eff = p.training ? gat_seed(p) : 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t wg = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * 8;
@@ -511,7 +515,7 @@ __global__ void __launch_bounds__(256) gatv2_bwd_dst_gen_kernel(const GatParams 
       const float lg = warp_sum(pl), dd = warp_sum(pd);
       const float alpha = __expf(lg - m) * inv;
       float ks = 1.0f;
-      if (p.training) ks = rng_keep(p.seed, __ldg(p.eid + k), p.H, h, p.drop_thr) ? p.keep_scale : 0.f;
+      if (p.training) ks = rng_keep(seed_eff, __ldg(p.eid + k), p.H, h, p.drop_thr) ? p.keep_scale : 0.f;
       const float delta = alpha * (dd * ks - cdot);
       if (lane == 0) {
         p.e_delta[static_cast<int64_t>(k) * p.H + h] = delta;
@@ -685,7 +689,7 @@ static int validate_common(const char* fn, const float* x_l, const float* x_r, c
 extern "C" int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, int64_t ld_r, const float* att,
                              const float* bias, const int32_t* dst_rowptr, const int32_t* dst_col,
                              const int32_t* dst_eid, int64_t n_dst, int64_t E, int H, int C, float negative_slope,
-                             float p_drop, uint64_t seed, int training, float* out, int64_t ld_out, float* out_act,
+                             float p_drop, uint64_t seed, const uint64_t* seed_dev, int training, float* out, int64_t ld_out, float* out_act,
                              int64_t ld_act, float* stat_max, float* stat_den, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = validate_common("gatv2_fwd", x_l, x_r, att, n_dst, E, H, C);
@@ -703,7 +707,7 @@ extern "C" int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, i
   p.x_l = x_l; p.x_r = x_r; p.att = att; p.bias = bias; p.ld_l = ld_l; p.ld_r = ld_r;
   p.rowptr = dst_rowptr; p.col = dst_col; p.eid = dst_eid; p.n_dst = n_dst; p.H = H; p.C = C;
   p.slope = negative_slope; p.training = train ? 1 : 0; p.drop_thr = drop_threshold(p_drop);
-  p.keep_scale = 1.0f / (1.0f - p_drop); p.seed = seed;
+  p.keep_scale = 1.0f / (1.0f - p_drop); p.seed = seed; p.seed_dev = seed_dev;
   p.out = out; p.out_act = out_act; p.ld_out = ld_out; p.ld_act = ld_act; p.stat_max = stat_max; p.stat_den = stat_den;
   if (aligned && !legacy_path() && quad_fwd_launch(p, stream)) return check_launch("gatv2_fwd(quad)");
   if (sh.path == Path::kVec) {
@@ -776,7 +780,7 @@ extern "C" int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, i
                              int gelu_fused, float* g_buf, const int32_t* dst_rowptr, const int32_t* dst_col,
                              const int32_t* dst_eid, const int32_t* src_rowptr, const int32_t* src_dst,
                              const int32_t* src_pos, int64_t n_src, int64_t n_dst, int64_t E, int H, int C,
-                             float negative_slope, float p_drop, uint64_t seed, int training, const float* stat_max,
+                             float negative_slope, float p_drop, uint64_t seed, const uint64_t* seed_dev, int training, const float* stat_max,
                              const float* stat_den, float* grad_x_l, int64_t ld_gl, float* grad_x_r, int64_t ld_gr,
                              float* grad_att, float* grad_bias, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -807,7 +811,7 @@ extern "C" int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, i
   p.x_l = x_l; p.x_r = x_r; p.att = att; p.bias = bias; p.ld_l = ld_l; p.ld_r = ld_r;
   p.rowptr = dst_rowptr; p.col = dst_col; p.eid = dst_eid; p.n_dst = n_dst; p.n_src = n_src; p.H = H; p.C = C;
   p.slope = negative_slope; p.training = train ? 1 : 0; p.drop_thr = drop_threshold(p_drop);
-  p.keep_scale = 1.0f / (1.0f - p_drop); p.seed = seed;
+  p.keep_scale = 1.0f / (1.0f - p_drop); p.seed = seed; p.seed_dev = seed_dev;
   p.out = const_cast<float*>(out); p.ld_out = ld_out;
   p.stat_max = const_cast<float*>(stat_max); p.stat_den = const_cast<float*>(stat_den);
   p.grad_out = grad_out; p.ld_g = ld_g; p.gelu_fused = gelu_fused; p.g_buf = g_buf;

@@ -31,6 +31,7 @@ struct GatParams {
   uint32_t drop_thr;
   float keep_scale;
   uint64_t seed;
+  const uint64_t* seed_dev;   // optional device word added to `seed` (CUDA-graph replays draw new masks); see gat_seed()
   // forward outputs / backward saved inputs
   float *out, *out_act;
   int64_t ld_out, ld_act;
@@ -46,6 +47,13 @@ struct GatParams {
   float* partial;            // per-CTA (vector path) / per-warp (generic path) partial sums
   const int32_t *t_rowptr, *t_dst, *t_pos;
 };
+
+// Effective dropout seed of a launch: the by-value seed plus, when given, a device-resident word.  A captured CUDA graph
+// freezes by-value arguments, so a replayed training step advances the device word instead (segger_b200/graphs.py).
+__device__ __forceinline__ uint64_t gat_seed(const GatParams& p) {
+  return p.seed_dev ? p.seed + __ldg(reinterpret_cast<const unsigned long long*>(p.seed_dev)) : p.seed;
+}
+
 
 
 // Per-edge scalar record written by the dst pass for the src pass, in dst-CSR order:

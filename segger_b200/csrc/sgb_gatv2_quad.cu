@@ -146,6 +146,7 @@ __device__ __forceinline__ void sts4(uint32_t saddr, const float4 v) {
 // ================================================================================================
 template <int V, int LPR, int H, int D>
 __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
+  const uint64_t seed_eff = p.training ? gat_seed(p) : 0;
   constexpr int G = 32 / LPR, VPH = V / H;
   static_assert(V % H == 0, "a lane must hold whole heads");
   extern __shared__ float4 q_smem[];
@@ -263,13 +264,13 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
           }
         }
         uint32_t eh = 0;
-        if (training) eh = rng_edge(p.seed, static_cast<uint32_t>(e));
+        if (training) eh = rng_edge(seed_eff, static_cast<uint32_t>(e));
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           const float pe = act ? __expf(lg[h] - m[h]) : 0.f;
           ss[h] += pe;
           float w = pe;
-          if (training) w = rng_head(eh, p.seed, h) >= p.drop_thr ? pe * p.keep_scale : 0.f;
+          if (training) w = rng_head(eh, seed_eff, h) >= p.drop_thr ? pe * p.keep_scale : 0.f;
 #pragma unroll
           for (int u = 0; u < VPH; ++u) fma4(acc[h * VPH + u], w, x[h * VPH + u]);
         }
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
 // two-thirds-empty wave).
 template <int V, int LPR, int H, int D, int MINB>
 __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
+  const uint64_t seed_eff = p.training ? gat_seed(p) : 0;
   constexpr int G = 32 / LPR, VPH = V / H, F4 = V * LPR;
   constexpr int SH = rec_scalars(H), RSB = rec_bytes(H, LPR);
   extern __shared__ float4 q_smem[];
@@ -446,13 +448,13 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
         if (training && k + 1 < c_deg) eid_next = __ldg(p.eid + c_beg + k + 1);
         const int jcol = (direct_src && act) ? __ldg(p.col + c_beg + k) : 0;
         uint32_t eh = 0;
-        if (training) eh = rng_edge(p.seed, static_cast<uint32_t>(e));
+        if (training) eh = rng_edge(seed_eff, static_cast<uint32_t>(e));
         float delta[H], alk[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           const float alpha = act ? __expf(lg[h] - m[h]) * inv[h] : 0.f;
           float ks = 1.0f;
-          if (training) ks = rng_head(eh, p.seed, h) >= p.drop_thr ? p.keep_scale : 0.f;
+          if (training) ks = rng_head(eh, seed_eff, h) >= p.drop_thr ? p.keep_scale : 0.f;
           delta[h] = alpha * (dd[h] * ks - cdot[h]);
           alk[h] = alpha * ks;
         }

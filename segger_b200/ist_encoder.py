@@ -36,6 +36,12 @@ def set_num_graphs(batch: Tensor, num_graphs: int) -> Tensor:
     return batch
 
 
+def _detached(x_dict):
+    """The layer inputs kept for `attention_weights`, without their autograd history: holding the graph would keep
+    last step's AccumulateGrad nodes (and their stream) alive into the next step, which breaks CUDA-graph capture."""
+    return {k: (v.detach() if isinstance(v, Tensor) else v) for k, v in x_dict.items()}
+
+
 def _known_num_graphs(batch: Optional[Tensor]) -> Optional[int]:
     if batch is None or batch.numel() == 0:
         return 1
@@ -127,6 +133,7 @@ class SkipGAT(Module):
         )
         self._attn_weights: Dict[Tuple[str, str, str], Tensor] = {}
         self._last = None
+        self._last_factor = None
 
     # -- fused path ----------------------------------------------------------------------------
     def _fusable(self, x_dict, edge_index_dict) -> bool:
@@ -159,7 +166,8 @@ class SkipGAT(Module):
         training = self.training and tt.dropout > 0.0
         seed_tt = ops.new_seed() if training else 0
         seed_tb = ops.new_seed() if training else 0
-        self._last = (x_dict, edge_index_dict)
+        self._last = (_detached(x_dict), edge_index_dict)
+        self._last_factor = None if tx_table is None else (tx_ids, tx_table.detach())
         h_tx, h_bd = ops.SkipGATLayerFn.apply(
             x_tx, x_bd,
             tt.lin_l.weight, tt.lin_l.bias, tt.lin_r.weight, tt.lin_r.bias, tt.att, tt.bias,
@@ -171,7 +179,8 @@ class SkipGAT(Module):
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict: Dict[str, Tensor]) -> Dict[str, Tensor]:
         if self._fusable(x_dict, edge_index_dict):
             return self.forward_fused(x_dict, edge_index_dict)
-        self._last = (x_dict, edge_index_dict)
+        self._last = (_detached(x_dict), edge_index_dict)
+        self._last_factor = None
         # Reference builds {edge: False for edge in self.conv.convs} -- string keys that HeteroConv
         # never matches, i.e. a no-op kwarg (Appendix B.2); we simply do not pass it.
         return self.conv(x_dict, edge_index_dict)
@@ -186,7 +195,11 @@ class SkipGAT(Module):
             self.eval()
             try:
                 conv = self.conv.convs[TT]
-                _, (_, alpha) = conv(x_dict["tx"].detach(), edge_index_dict[TT], return_attention_weights=True)
+                x_tx = x_dict["tx"].detach()
+                if getattr(self, "_last_factor", None) is not None:      # factored first layer: rebuild cat(table[ids], x)
+                    ids, table = self._last_factor
+                    x_tx = torch.cat([table[ids.long()], x_tx], dim=-1)
+                _, (_, alpha) = conv(x_tx, edge_index_dict[TT], return_attention_weights=True)
             finally:
                 self.train(was)
         self._attn_weights[TT] = alpha

@@ -227,9 +227,48 @@ class _CsrCache:
 CSR_CACHE = _CsrCache()
 
 
-def new_seed() -> int:
-    """63-bit seed drawn from torch's default (CPU) generator: torch.manual_seed governs dropout."""
+_SEED_WORD: Optional[Tensor] = None      # device int64 [1] added to every dropout seed (see device_seed)
+_SEED_SITE = 0
+
+
+class device_seed:
+    """``with device_seed(word):`` -- dropout seeds come from a DEVICE word instead of the CPU generator.
+
+    Inside the block ``new_seed()`` returns ``(call-site number, word)``: the kernels add the word's current value to the
+    call-site number when they run, so a CUDA graph captured inside the block draws a fresh mask on every replay once the
+    word is advanced on the device (segger_b200/graphs.py does ``word += odd constant`` as the first node of the graph).
+    Forward and backward of one step read the same value.  The call-site numbers restart at every ``with``."""
+
+    def __init__(self, word: Tensor):
+        if word.dtype != torch.int64 or word.numel() != 1 or not word.is_cuda:
+            raise ValueError("device_seed: expected a CUDA int64 tensor with one element")
+        self.word = word
+
+    def __enter__(self):
+        global _SEED_WORD, _SEED_SITE
+        self._prev = (_SEED_WORD, _SEED_SITE)
+        _SEED_WORD, _SEED_SITE = self.word, 0
+        return self
+
+    def __exit__(self, *exc):
+        global _SEED_WORD, _SEED_SITE
+        _SEED_WORD, _SEED_SITE = self._prev
+        return False
+
+
+def new_seed():
+    """63-bit seed drawn from torch's default (CPU) generator: torch.manual_seed governs dropout.  Under
+    ``device_seed`` -> (call-site number, device word) instead (no host RNG, graph-capturable)."""
+    global _SEED_SITE
+    if _SEED_WORD is not None:
+        _SEED_SITE += 1
+        return (_SEED_SITE * 0x9E3779B97F4A7C15) & (2 ** 62 - 1), _SEED_WORD
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def _split_seed(seed):
+    """seed (int | (int, device word)) -> (by-value seed, device word or None)."""
+    return seed if isinstance(seed, tuple) else (seed, None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -427,9 +466,10 @@ def gatv2_fwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], csr
     smax = torch.empty(n_dst, H, dtype=torch.float32, device=dev)
     sden = torch.empty(n_dst, H, dtype=torch.float32, device=dev)
     att, bias = _vec(att.reshape(-1)), _vec(bias)
+    seed_val, seed_dev = _split_seed(seed)
     check(_lib.load().sgb_gatv2_fwd(ptr(x_l), _ld(x_l), ptr(x_r), _ld(x_r), ptr(att), ptr(bias), ptr(csr.rowptr),
-                                    ptr(csr.col), ptr(csr.eid), n_dst, csr.E, H, C, slope, p_drop, seed,
-                                    int(training), ptr(out), _ld(out) if out is not None else 0, ptr(out_act),
+                                    ptr(csr.col), ptr(csr.eid), n_dst, csr.E, H, C, slope, p_drop, seed_val,
+                                    ptr(seed_dev), int(training), ptr(out), _ld(out) if out is not None else 0, ptr(out_act),
                                     _ld(out_act) if out_act is not None else 0, ptr(smax), ptr(sden),
                                     stream_ptr(dev)), "gatv2_fwd")
     _count(1)
@@ -464,10 +504,11 @@ def gatv2_bwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], out
               and os.environ.get("SEGGER_B200_GAT") != "legacy" and os.environ.get("SEGGER_B200_GAT_DIRECT", "1") != "0"
               and all(t.data_ptr() % 16 == 0 and _ld(t) % 4 == 0 for t in (x_l, x_r, out_pre, grad_out, grad_x_l, grad_x_r)))
     t_rowptr, t_dst, t_pos = (None, None, None) if direct else (csr.t_rowptr, csr.t_dst, csr.t_pos)
+    seed_val, seed_dev = _split_seed(seed)
     check(lib.sgb_gatv2_bwd(ptr(x_l), _ld(x_l), ptr(x_r), _ld(x_r), ptr(att), ptr(bias), ptr(out_pre), _ld(out_pre),
                             ptr(grad_out), _ld(grad_out), int(gelu_fused), ptr(g_buf), ptr(csr.rowptr), ptr(csr.col),
                             ptr(csr.eid), ptr(t_rowptr), ptr(t_dst), ptr(t_pos), n_src, n_dst, csr.E,
-                            H, C, slope, p_drop, seed, int(training), ptr(smax), ptr(sden), ptr(grad_x_l),
+                            H, C, slope, p_drop, seed_val, ptr(seed_dev), int(training), ptr(smax), ptr(sden), ptr(grad_x_l),
                             _ld(grad_x_l), ptr(grad_x_r), _ld(grad_x_r), ptr(g_att), ptr(g_bias), ptr(ws),
                             ws.numel(), stream_ptr(dev)), "gatv2_bwd")
     _count(3)
@@ -488,6 +529,9 @@ def gatv2_alpha(x_l, x_r, att, csr: EdgeCSR, H, C, slope, smax, sden) -> Tensor:
 def dropout_keep_mask(seed: int, E: int, H: int, p: float, device) -> Tensor:
     """[E,H] bool keep mask identical to the one the fused kernels regenerate (test hook)."""
     mask = torch.empty(E, H, dtype=torch.uint8, device=device)
+    seed, word = _split_seed(seed)
+    if word is not None:          # test hook only: reading the word synchronises
+        seed = (seed + int(word.item())) & (2 ** 64 - 1)
     check(_lib.load().sgb_dropout_mask(seed, E, H, p, ptr(mask), stream_ptr(device)), "dropout_mask")
     _count(1)
     return mask.bool()

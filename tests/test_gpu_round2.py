@@ -121,6 +121,58 @@ def test_forward_is_sync_free_on_a_seen_batch():
     assert torch.equal(out, want)
 
 
+def test_graphed_train_step_replays_equal_eager_steps_bit_for_bit():
+    """segger_b200.graphs: a captured training step (forward + loss + backward + capturable Adam, dropout seeds from the
+    device word) replayed twice leaves the parameters exactly where the same five eager steps leave them -- so the
+    replays draw the dropout masks an eager run with the same seed word draws, and a new mask every replay."""
+    import copy
+    from segger_b200 import graphs
+    ts, x, edges, pos, bat = synth_batch(6000, 60, seed=31)
+    _, prod = make_models(ts.n_genes, ts.bd_x.shape[1], 32, 64, 64, 0, 2, seed=2)
+    prod.train()
+    twin = copy.deepcopy(prod)
+    args = (to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
+    gen = torch.Generator().manual_seed(3)
+    t_tx = torch.randn(6000, 64, generator=gen).cuda()
+
+    def make(model):
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True, fused=True)
+        def fl():
+            out = model(*args)
+            return (out["tx"] * t_tx).sum() / 6000 + out["bd"].square().sum() / 60
+        return opt, fl
+
+    opt_a, fl_a = make(prod)
+    prod(*args)                                         # resolve lazy layers and batch tags before the capture
+    twin(*args)
+    torch.manual_seed(5)
+    step = graphs.graphed_train_step(fl_a, opt_a, warmup=3)
+    wrap = lambda v: (v + (1 << 63)) % (1 << 64) - (1 << 63)          # int64 wrap-around, as the device add does
+    word0 = wrap(int(step.seed_word.item()) - 3 * graphs._GOLDEN)    # 3 warm-up passes advanced it (a capture runs nothing)
+    losses = [float(step.replay().item()), float(step.replay().item())]
+    assert step.launches > 50
+    assert losses[0] != losses[1]                                     # new dropout mask / new weights every replay
+    # 3 warm-up + 2 replays = 5 steps, the word advanced once per step
+    assert ((int(step.seed_word.item()) - word0) - 5 * graphs._GOLDEN) % (1 << 64) == 0
+
+    opt_b, fl_b = make(twin)
+    word = torch.tensor([word0], dtype=torch.int64).cuda()
+    eager = []
+    for i in range(5):
+        word.add_(graphs._GOLDEN)
+        with ops.device_seed(word):
+            opt_b.zero_grad(set_to_none=True)
+            loss = fl_b()
+            loss.backward()
+            opt_b.step()
+            eager.append(float(loss.item()))
+    assert eager[3:] == losses
+    for (n, a), (_, b) in zip(prod.named_parameters(), twin.named_parameters()):
+        if isinstance(a, torch.nn.parameter.UninitializedParameter):
+            continue                                    # the dead bd-contains-tx conv is never materialised (B.1)
+        assert torch.equal(a, b), n
+
+
 def test_encoder_train_mode_parity_with_the_kernels_own_dropout_masks():
     """Train mode end to end: the masks the fused kernels regenerate (sgb_dropout_mask of the seeds drawn from torch's
     generator) are injected into the oracle layer by layer -> outputs and gradients within 1e-4."""
@@ -202,9 +254,11 @@ def test_factored_first_layer_equals_dense_form(monkeypatch):
         sum((out[k] * g[k]).sum() for k in g).backward()
         res[flag] = ({k: v.detach().clone() for k, v in out.items()},
                      {n: p.grad.clone() for n, p in prod.named_parameters() if p.grad is not None})
+        res[flag] += (prod.conv_layers[0].attention_weights[TT].clone(),)     # first layer: factored input rebuilt
     for k in ("tx", "bd"):
         assert rel_err(res["1"][0][k], res["0"][0][k]) < 1e-5, k
     assert res["0"][1].keys() == res["1"][1].keys()
+    assert float((res["1"][2] - res["0"][2]).abs().max()) < 1e-5
     # both forms are fp32 roundings of the same (partly ill-conditioned) gradients: measured against the fp64 oracle the
     # factored form must be as close as the dense one
     import copy
