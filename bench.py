@@ -921,7 +921,7 @@ def inference_cfg3_leg(lit, n_tx_total, max_edges, device, world, rank, timed, h
     from segger_b200.hetero import HeteroBatch
     from segger_b200.neighbors import kdtree_neighbors
     from segger_b200.synth import synth
-    from segger_b200.tiles import TilePredictSet, square_tiles
+    from segger_b200.tiles import TilePredictSet, slice_slots, square_tiles
     from segger_b200.writer import dedupe_predictions
     n_cells = n_tx_total // 100
     t0 = time.perf_counter()
@@ -953,29 +953,34 @@ def inference_cfg3_leg(lit, n_tx_total, max_edges, device, world, rank, timed, h
     lit.eval()
     stats = {}
 
+    # tiles are cut in GROUPS (TilePredictSet.cut: all tiles of a group in a handful of launches, collated on the device);
+    # a group is sized to fill one batch of `max_edges` edges from the mean edges per tile incl. halo, then split by the
+    # exact per-tile counts the cut returns, so no batch exceeds max_edges (a batch never spans two groups)
+    E_all = sum(int(b[et]["edge_index"].size(1)) for et in (TT, TB, PRED))
+    w_tile = float(hi[0] - lo[0]) / nt
+    est_edges = E_all / (nt * nt) * ((w_tile + 40.0) / w_tile) ** 2
+
     def run():
         ops.CSR_CACHE.clear()
-        shards, pending, pend_edges, n_batches = [], [], 0, 0
-
-        def flush():
-            nonlocal pending, pend_edges, n_batches
-            if not pending:
-                return
-            batch = concat_tiles(pending)
-            with torch.no_grad():
-                shards.append(lit.predict_step(batch, 0, device_output=True))
-            ops.CSR_CACHE.clear()
-            pending, pend_edges = [], 0
-            n_batches += 1
-
-        for t in mine:
-            tile = ds[t]
-            e = sum(int(tile[et]["edge_index"].size(1)) for et in (TT, TB, PRED))
-            if pending and pend_edges + e > max_edges:
-                flush()
-            pending.append(tile)
-            pend_edges += e
-        flush()
+        shards, n_batches = [], 0
+        G = max(1, min(64, int(max_edges // est_edges)))
+        for g0 in range(0, len(mine), G):
+            ids = mine[g0:g0 + G]
+            group, info = ds.cut(ids)
+            per_slot = [sum(info["edges"][et][s_] for et in (TT, TB, PRED)) for s_ in range(len(ids))]
+            a, acc = 0, 0
+            cuts = []
+            for s_, e in enumerate(per_slot):
+                if s_ > a and acc + e > max_edges:
+                    cuts.append((a, s_)); a, acc = s_, 0
+                acc += e
+            cuts.append((a, len(ids)))
+            for (a, b_) in cuts:
+                batch = slice_slots(group, info, a, b_)
+                with torch.no_grad():
+                    shards.append(lit.predict_step(batch, 0, device_output=True))
+                ops.CSR_CACHE.clear()
+                n_batches += 1
         if shards:
             cols = [torch.cat([s[i] for s in shards]) for i in range(4)]
         else:
@@ -1005,38 +1010,8 @@ def inference_cfg3_leg(lit, n_tx_total, max_edges, device, world, rank, timed, h
             "assigned_frac": stats.get("assigned"), "complete": stats.get("rows") == n_tx_total,
             "frac_of_byte_model": (10.9e9 * n_tx_total / 1e6) / (ms * 1e-3) / 1e9 / (hbm_peak * world),
             "host_synth_s": t_synth, "with_reference_batch_size": ref_batching,
-            "what": "tile cut (+20 um halo) + batch assembly + predict_step per batch + device all-gather of fixed-width result "
+            "what": "grouped tile cut (+20 um halo; TilePredictSet.cut, collated on the device) + predict_step per batch + device all-gather of fixed-width result "
                     "tensors + device de-duplication, all timed; graph construction (kNN, point-in-polygon) is outside"}
-
-
-def concat_tiles(tiles):
-    """PyG collate of prediction tiles: concatenate node stores, shift edge indices by the node offsets, batch vectors."""
-    from segger_b200.hetero import HeteroBatch
-    from segger_b200.ist_encoder import set_num_graphs
-    if len(tiles) == 1:
-        return tiles[0]
-    out = HeteroBatch()
-    out._num_graphs = len(tiles)
-    offs = {}
-    for nt in tiles[0].node_types:
-        sizes = [t[nt]["pos"].size(0) for t in tiles]
-        offs[nt] = np.concatenate([[0], np.cumsum(sizes)]).tolist()
-        for name in tiles[0][nt]:
-            if name == "batch":
-                continue
-            out[nt][name] = torch.cat([t[nt][name] for t in tiles])
-        dev = tiles[0][nt]["pos"].device
-        bvec = torch.repeat_interleave(torch.arange(len(tiles), device=dev), torch.tensor(sizes, device=dev))
-        out[nt]["batch"] = set_num_graphs(bvec, len(tiles))
-    for et in tiles[0].edge_types:
-        src, _, dst = et
-        parts = []
-        for i, t in enumerate(tiles):
-            ei = t[et]["edge_index"]
-            shift = torch.tensor([[offs[src][i]], [offs[dst][i]]], dtype=ei.dtype, device=ei.device)
-            parts.append(ei + shift)
-        out[et]["edge_index"] = torch.cat(parts, 1)
-    return out
 
 
 if __name__ == "__main__":

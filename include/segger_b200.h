@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 201
+#define SGB_VERSION 202
 
 #if defined(__GNUC__)
 #define SGB_API __attribute__((visibility("default")))
@@ -364,6 +364,23 @@ SGB_API int sgb_edges_collate(const void* edge_index, int idx_bytes, int64_t ld_
                       const int64_t* e_out_off, const int64_t* src_starts, const int64_t* src_out_off,
                       const int64_t* dst_starts, const int64_t* dst_out_off, int K, int64_t total_edges, void* out,
                       int64_t ld_out, void* stream);
+/* Batched prediction-tile cut: TilePredictDataset._subset (data/tile_dataset.py:218-246) for T tiles ("slots") at once,
+ * producing the collated batch of data_module.py:333-344 directly.  Candidates are contiguous ranges of an id array
+ * sorted by grid cell (rng_start[R], rng_off[R+1] = exclusive prefix sum of the range lengths, rng_slot[R]; C = total
+ * candidates); boxes [T][8] = (outer x0,y0,x1,y1 half-open; inner x0,y0,x1,y1 closed) per slot.
+ * nodes: mask[c] = candidate inside its slot's outer box; keys[c] = slot << 40 | id << 1 | inside-inner (written where
+ *        mask is set); slot_counts[T] = kept per slot.  Sorting the kept keys gives the collated node order.
+ * edges: (edge ids sorted by the cell of their source) kept iff both endpoints are among the slot's nodes -- binary search
+ *        in the slot's segment [ptr[slot], ptr[slot+1]) of the SORTED node keys of the source / destination node type;
+ *        pu/pv = positions found (= collated node numbers), ekeys[c] = slot << 40 | edge id. */
+SGB_API int sgb_tilecut_nodes(const int32_t* perm, const void* pos, int pos_f64, const int64_t* rng_start, const int64_t* rng_off,
+                      const int32_t* rng_slot, int R, int64_t C, const double* boxes, int T, int64_t* keys, uint8_t* mask,
+                      int32_t* slot_counts, void* stream);
+SGB_API int sgb_tilecut_edges(const int32_t* eperm, const void* edge_index, int idx_bytes, int64_t row_stride, int64_t col_stride,
+                      const int64_t* rng_start, const int64_t* rng_off, const int32_t* rng_slot, int R, int64_t C,
+                      const void* src_pos, int pos_f64, const double* boxes, int T, const int64_t* src_keys,
+                      const int64_t* src_ptr, const int64_t* dst_keys, const int64_t* dst_ptr, int64_t* ekeys, int32_t* pu,
+                      int32_t* pv, uint8_t* mask, int32_t* slot_counts, void* stream);
 /* batch[r] = k for out_off[k] <= r < out_off[k+1] (the PyG Batch.batch vector). */
 SGB_API int sgb_batch_vector(const int64_t* out_off, int K, int64_t total_rows, int64_t* batch, void* stream);
 /* `src_idx[mask], seg_idx[mask], max_sim[mask], gen_idx[mask]` of LitISTEncoder.predict_step

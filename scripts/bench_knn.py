@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--max-n", type=int, default=50_000_000)
     ap.add_argument("--check-n", type=int, default=1_000_000)
     a = ap.parse_args()
-    hbm, _ = bench.peaks()
+    hbm = bench.peaks()[0]
     rng = np.random.default_rng(0)
     rows = []
     for kind in ("uniform", "clustered"):

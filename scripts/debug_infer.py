@@ -9,6 +9,7 @@ from segger_b200.hetero import HeteroBatch
 from segger_b200.lightning_model import LitISTEncoder
 from segger_b200.neighbors import kdtree_neighbors
 from segger_b200.synth import synth
+from segger_b200 import tiles
 from segger_b200.tiles import TilePredictSet, square_tiles
 TT, TB, PRED = bench.TT, bench.TB, bench.PRED
 dev = torch.device("cuda")
@@ -41,8 +42,8 @@ print("cut one tile (indexed): %.2f ms" % timeit(lambda: ds[nt + 1], 20))
 ds0 = TilePredictSet(b, boxes, margin=20.0)
 print("cut one tile (full scan): %.2f ms" % timeit(lambda: ds0[nt + 1], 5))
 tl = [ds[i] for i in range(16)]
-print("concat 16 tiles: %.2f ms" % timeit(lambda: bench.concat_tiles(tl), 5))
-bb = bench.concat_tiles(tl)
+print("concat 16 tiles: %.2f ms" % timeit(lambda: tiles.collate_tiles(tl), 5))
+bb = tiles.collate_tiles(tl)
 n16 = int(bb["tx"]["x"].size(0))
 def pred():
     ops.CSR_CACHE.clear()

@@ -103,6 +103,9 @@ _PROTOS = {
     "sgb_argsort_workspace_bytes": (c_sz, [c_i64]),
     "sgb_argsort_stable": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "sgb_invert_permutation": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "sgb_tilecut_nodes": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "sgb_tilecut_edges": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_vp, c_int,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sgb_partition_edges": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp,
                                     c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "sgb_ranges_gather": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),

@@ -127,6 +127,57 @@ def test_tile_predict_subset_matches_oracle_incl_boundaries_and_dtypes():
     assert torch.equal(t["tx"]["index"].cpu(), n_ref["tx"]["index"]) and torch.equal(t["tx"]["predict_mask"].cpu(), n_ref["tx"]["predict_mask"])
 
 
+def test_batched_tile_cut_equals_collated_per_tile_subsets():
+    """TilePredictSet.cut (all tiles of a group in two flag kernels per store) == collate of the per-tile subsets,
+    element for element: node order, attributes, predict_mask, batch vectors, renumbered edges in original order.
+    slice_slots / collate_tiles re-cut a group into batches."""
+    for pos_dtype, e_dtype in ((torch.float32, torch.int64), (torch.float64, torch.int32)):
+        ts, nodes, edges, b = _graph(n_tx=40000, n_cells=400, seed=9)
+        for nt in ("tx", "bd"):
+            b[nt]["pos"] = nodes[nt]["pos"].to(pos_dtype)
+        for et in (TT, TB, PRED):
+            b[et]["edge_index"] = edges[et].to(e_dtype)
+        b[TT]["weight"] = torch.arange(edges[TT].size(1), dtype=torch.float32)       # an edge attribute rides along
+        lo = nodes["tx"]["pos"].min(0).values - 1e-3
+        hi = nodes["tx"]["pos"].max(0).values + 1e-3
+        boxes = tiles.square_tiles(float(lo[0]), float(lo[1]), float(hi[0]), float(hi[1]), 4, 4)
+        ds = tiles.TilePredictSet(b.cuda(), boxes, margin=15.0, grid=(4, 4))
+        assert ds._index is not None
+        ids = [5, 0, 15, 6, 10]
+        want = tiles.collate_tiles([ds[t] for t in ids])
+        got, info = ds.cut(ids)
+        assert got.num_graphs == want.num_graphs == 5
+        for nt in ("tx", "bd"):
+            assert set(got[nt]) == set(want[nt])
+            for k in want[nt]:
+                assert got[nt][k].dtype == want[nt][k].dtype and torch.equal(got[nt][k], want[nt][k]), (nt, k)
+            assert info["nodes"][nt] == [int(ds[t][nt]["pos"].size(0)) for t in ids]
+        for et in (TT, TB, PRED):
+            assert got[et]["edge_index"].dtype == e_dtype
+            assert torch.equal(got[et]["edge_index"], want[et]["edge_index"]), et
+            assert info["edges"][et] == [int(ds[t][et]["edge_index"].size(1)) for t in ids]
+        assert torch.equal(got[TT]["weight"], want[TT]["weight"])
+        # slots [1, 4) of the group == the collate of those three tiles; two slices collated back == the group
+        mid = tiles.slice_slots(got, info, 1, 4)
+        want_mid = tiles.collate_tiles([ds[t] for t in ids[1:4]])
+        back = tiles.collate_tiles([tiles.slice_slots(got, info, 0, 2), tiles.slice_slots(got, info, 2, 5)])
+        for a, c in ((mid, want_mid), (back, got)):
+            assert a.num_graphs == c.num_graphs
+            for nt in ("tx", "bd"):
+                for k in c[nt]:
+                    assert torch.equal(a[nt][k], c[nt][k]), (nt, k)
+            for et in (TT, TB, PRED):
+                assert torch.equal(a[et]["edge_index"], c[et]["edge_index"]), et
+    # a group runs through predict_step like any collated batch
+    torch.manual_seed(0)
+    lit = LitISTEncoder(ts.n_genes, in_channels=32, n_mid_layers=0).cuda().eval()
+    with torch.no_grad():
+        r_got = lit.predict_step(got, 0)
+        r_want = lit.predict_step(want, 0)
+    for x, y in zip(r_got, r_want):
+        assert torch.equal(x, y)
+
+
 def test_tiled_prediction_with_halo_equals_whole_graph_prediction():
     """Tiles + 20 um halo are independent units (receptive field = n_layers x 5 um): predicting tile by tile and keeping
     the inner-tile rows gives exactly the assignments of one pass over the whole graph."""

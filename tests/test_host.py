@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/segger_b200.h but not exported"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS), set(names) ^ set(_lib.EXPORTED_SYMBOLS)
-    assert lib.sgb_version() == 201
+    assert lib.sgb_version() == 202
 
 
 def test_ctypes_prototypes_match_header_arity():
