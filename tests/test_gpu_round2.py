@@ -68,7 +68,12 @@ def test_forward_and_predict_step_under_inference_mode():
     assert all(not t.is_pinned() for t in paged) and all(torch.equal(a, b) for a, b in zip(paged, got))
     del got, want, paged, g, w, a, b
     gc.collect()
-    assert L._pinned_live < live                          # returned to the budget when the results are dropped
+    with torch.inference_mode():
+        extra = lit.predict_step(bi, 0)
+    held = L._pinned_live
+    del extra
+    gc.collect()
+    assert L._pinned_live < held                          # returned to the budget when the results are dropped
 
 
 def test_malformed_edge_index_raises_index_error():
