@@ -678,6 +678,43 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
 }
 
+// Specialised write-out of one staged pass (32 rows x PW columns of a warp) for the common epilogues: the general body
+// below carries every option behind run-time flags (bias, accumulate, table gather, activation and its derivative, scalar
+// tails) and is ~1.4k SASS instructions of which ~40 execute; ncu's source view put 44 % of an epilogue warp's life in
+// that loop at ~7 cycles per instruction (branches, address arithmetic, one exposed shared-memory load per row group).
+// MODE 0: C = acc + bias.  1: + table[gid[row]].  2: + C_act = act(C).  3: C += acc + bias.  All need whole, 16-byte
+// aligned float4 columns; the four row groups of the pass are unrolled so their loads overlap.
+template <int MODE, int PW, int BMt>
+__device__ __forceinline__ void ts_write_rows(const TcParams& p, const float* __restrict__ stg, int lane, int64_t row0, int64_t n,
+                                              const float (&b4)[4]) {
+  constexpr int LR = PW / 4;
+  constexpr int kStgLd = PW + 4;
+  const int sub = lane / LR, c4 = (lane % LR) * 4;
+  float4 t[LR];
+#pragma unroll
+  for (int it = 0; it < LR; ++it) t[it] = *reinterpret_cast<const float4*>(stg + (it * (32 / LR) + sub) * kStgLd + c4);
+#pragma unroll
+  for (int it = 0; it < LR; ++it) {
+    const int64_t grow = row0 + it * (32 / LR) + sub;
+    if (grow >= p.M) continue;
+    float4 v = make_float4(t[it].x + b4[0], t[it].y + b4[1], t[it].z + b4[2], t[it].w + b4[3]);
+    float* dst = p.C + grow * p.ldc + n;
+    if (MODE == 3) {
+      const float4 o = *reinterpret_cast<const float4*>(dst);
+      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    }
+    if (MODE == 1) {
+      const int64_t id = p.gid_bytes == 8 ? static_cast<const int64_t*>(p.gids)[grow]
+                                          : static_cast<int64_t>(static_cast<const int32_t*>(p.gids)[grow]);
+      const float4 o = ldg4(p.gtab + id * p.ld_gtab + n);
+      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    }
+    st4(dst, v);
+    if (MODE == 2)
+      st4(p.C_act + grow * p.ldca + n, make_float4(act_apply(v.x, p.act), act_apply(v.y, p.act), act_apply(v.z, p.act), act_apply(v.w, p.act)));
+  }
+}
+
 template <int BN, int S, bool B_RES, bool PP>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -903,6 +940,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       const bool vec_a = p.C_act && (p.ldca % 4 == 0) && aligned16(p.C_act) && (n0 % 4 == 0);
       const bool vec_p = p.act_pre && (p.ld_pre % 4 == 0) && aligned16(p.act_pre) && (n0 % 4 == 0);
       const bool vec_g = p.gtab && (p.ld_gtab % 4 == 0) && aligned16(p.gtab) && (n0 % 4 == 0);
+      // epilogue class of this launch (uniform): 0 plain, 1 + table gather, 2 + activated copy, 3 accumulate, 4 general
+      const int wmode = (!vec_c || p.act_pre) ? 4
+                        : p.gtab ? ((vec_g && !p.accumulate && !p.C_act) ? 1 : 4)
+                        : p.C_act ? ((vec_a && !p.accumulate) ? 2 : 4)
+                        : p.accumulate ? 3 : 0;
       // One ROLLED loop over the write-out passes: the body below (bias / accumulate / table gather / activation, each
       // behind a run-time flag) is emitted once instead of CW/PW times -- unrolled it was over half of the kernel's SASS
       // and the instruction cache, not the LSU, bounded the write-out.  Only the register -> staging copy is selected
@@ -929,6 +971,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
           if (p.bias) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) if (n + e < p.N) b4[e] = __ldg(p.bias + n + e);
+          }
+          if (whole && wmode != 4) {
+            const int64_t row0 = mb * BM + q * 32;
+            if (wmode == 0) ts_write_rows<0, PW, BM>(p, stg, lane, row0, n, b4);
+            else if (wmode == 1) ts_write_rows<1, PW, BM>(p, stg, lane, row0, n, b4);
+            else if (wmode == 2) ts_write_rows<2, PW, BM>(p, stg, lane, row0, n, b4);
+            else ts_write_rows<3, PW, BM>(p, stg, lane, row0, n, b4);
+            continue;
           }
 #pragma unroll 1
           for (int it = 0; it < LR; ++it) {
@@ -1090,15 +1140,14 @@ int launch_ts_pp(TcParams p, cudaStream_t stream) {
   return check_launch("gemm_tf32x3_ts");
 }
 
-// Epilogue mode, chosen per shape from scripts/bench_gemm.py on B200 (profiles/r2_gemm_epilogue_modes.md): alternating
-// tile groups hide the write-out behind the next tile's MMAs once the reduction is deep enough for four warps to finish
-// a tile inside it (BN = 64: >= 4 k-stages; BN = 128: >= 10); on shallower tiles all eight warps share one tile.
-// SEGGER_B200_GEMM_PP=0|1 forces a mode.
+// Epilogue mode, chosen from scripts/bench_gemm.py on B200 (profiles/r2_gemm_epilogue_modes.md): alternating tile groups
+// hide a tile's write-out behind the next tile's MMAs whenever a tile has at least three k-stages of MMA work to hide
+// it behind; on shallower tiles all eight warps share one tile.  SEGGER_B200_GEMM_PP=0|1 forces a mode.
 template <int BN, int S, bool B_RES>
 int launch_ts(TcParams p, cudaStream_t stream) {
   static int force = env_int("SEGGER_B200_GEMM_PP", 0, 1, -1);
   const int64_t num_ks = ceil_div(p.K, BK);
-  const bool pp = force >= 0 ? force == 1 : (BN == 64 ? num_ks >= 4 : num_ks >= 10);
+  const bool pp = force >= 0 ? force == 1 : num_ks >= 3;
   return pp ? launch_ts_pp<BN, S, B_RES, true>(p, stream) : launch_ts_pp<BN, S, B_RES, false>(p, stream);
 }
 

@@ -173,8 +173,8 @@ def test_graphed_train_step_replays_equal_eager_steps_bit_for_bit():
             eager.append(float(loss.item()))
     assert eager[3:] == losses
     for (n, a), (_, b) in zip(prod.named_parameters(), twin.named_parameters()):
-        if isinstance(a, torch.nn.parameter.UninitializedParameter):
-            continue                                    # the dead bd-contains-tx conv is never materialised (B.1)
+        if isinstance(a, torch.nn.parameter.UninitializedParameter) or "contains" in n:
+            continue                                    # the dead bd-contains-tx conv: never materialised / never touched (B.1)
         assert torch.equal(a, b), n
 
 
