@@ -771,15 +771,39 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
     // ===================================== producers =====================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTsRegsProducer));
     const int t = threadIdx.x;                        // = row of the tile this thread owns in the split
-    // flattened slab sequence of this CTA: (tile, ks)
-    struct Cur { int64_t tile, ks; bool live; };
-    auto init = [&](Cur& c) { c.tile = blockIdx.x; c.ks = 0; c.live = c.tile < tiles; };
+    // flattened slab sequence of this CTA: (tile, ks).  Everything that depends on the tile only -- the 64-bit tile ->
+    // row-block division, this thread's first source row, which of its 8 rows exist -- is computed when the cursor
+    // enters a tile, so a slab costs 8 LDGSTS with immediate shared-memory offsets (ncu: the generic stage_raw was 256
+    // of the producers' ~720 instructions per slab, the division another ~100, and the producers were 70 % busy).
+    struct Cur { int64_t tile, ks; bool live; const float* rowbase; uint32_t rows_ok; };
+    const int chunk = t & 7, r0 = t >> 3;                       // 16-byte chunk / first row this thread copies
+    const uint32_t soff0 = chunk_offset<BM, false>(r0, chunk);  // row r0 + 16 i lands 2048 i bytes further on
+    auto enter = [&](Cur& c) {
+      c.live = c.tile < tiles;
+      if (!c.live) return;
+      const int64_t mb = static_cast<int64_t>(static_cast<uint32_t>(c.tile) / static_cast<uint32_t>(num_n));   // tiles < 2^31
+      const int64_t row = mb * BM + r0;
+      c.rowbase = p.A + row * p.lda + chunk * 4;
+      uint32_t m = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m |= (row + 16 * i < p.M) ? (1u << i) : 0u;
+      c.rows_ok = m;
+    };
+    auto init = [&](Cur& c) { c.tile = blockIdx.x; c.ks = 0; enter(c); };
     auto adv = [&](Cur& c) {
-      if (++c.ks == num_ks) { c.ks = 0; c.tile += gridDim.x; c.live = c.tile < tiles; }
+      if (++c.ks == num_ks) { c.ks = 0; c.tile += gridDim.x; enter(c); }
     };
     auto issue_raw = [&](const Cur& c, int rslot) {
-      const int64_t mb = c.tile / num_n;
-      stage_raw<BM, false>(p.A, p.lda, mb * BM, p.M, c.ks * BK, p.K, smem_u32(smem_rawa + static_cast<size_t>(rslot) * kRawTile), t);
+      const int64_t k = c.ks * BK + chunk * 4;
+      const bool kok = k < p.K;                                   // K % 4 == 0 guaranteed by the dispatcher
+      const float* g = c.rowbase + c.ks * BK;
+      const uint32_t dst = smem_u32(smem_rawa + static_cast<size_t>(rslot) * kRawTile) + soff0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = kok && ((c.rows_ok >> i) & 1u);
+        cp_async16_zfill(dst + 2048u * i, ok ? static_cast<const void*>(g + static_cast<int64_t>(16 * i) * p.lda) : static_cast<const void*>(p.A),
+                         ok ? 16u : 0u);
+      }
     };
     Cur pi, ci;
     init(pi); init(ci);
