@@ -684,34 +684,32 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
 // that loop at ~7 cycles per instruction (branches, address arithmetic, one exposed shared-memory load per row group).
 // MODE 0: C = acc + bias.  1: + table[gid[row]].  2: + C_act = act(C).  3: C += acc + bias.  All need whole, 16-byte
 // aligned float4 columns; the four row groups of the pass are unrolled so their loads overlap.
-template <int MODE, int PW, int BMt>
-__device__ __forceinline__ void ts_write_rows(const TcParams& p, const float* __restrict__ stg, int lane, int64_t row0, int64_t n,
-                                              const float (&b4)[4]) {
+template <int MODE, int PW>
+__device__ __forceinline__ void ts_write_rows(const float* __restrict__ stg_lane /* stg + sub * ld + c4 */, float* __restrict__ dst,
+                                              int64_t row_step /* floats between row groups */, int rows_left /* - sub */,
+                                              const float4 b, float* __restrict__ dst_act, int64_t act_step, int act,
+                                              const float* const (&trow)[PW / 4]) {
   constexpr int LR = PW / 4;
   constexpr int kStgLd = PW + 4;
-  const int sub = lane / LR, c4 = (lane % LR) * 4;
   float4 t[LR];
 #pragma unroll
-  for (int it = 0; it < LR; ++it) t[it] = *reinterpret_cast<const float4*>(stg + (it * (32 / LR) + sub) * kStgLd + c4);
+  for (int it = 0; it < LR; ++it) t[it] = *reinterpret_cast<const float4*>(stg_lane + it * (32 / LR) * kStgLd);
 #pragma unroll
   for (int it = 0; it < LR; ++it) {
-    const int64_t grow = row0 + it * (32 / LR) + sub;
-    if (grow >= p.M) continue;
-    float4 v = make_float4(t[it].x + b4[0], t[it].y + b4[1], t[it].z + b4[2], t[it].w + b4[3]);
-    float* dst = p.C + grow * p.ldc + n;
+    if (it * (32 / LR) >= rows_left) break;
+    float4 v = make_float4(t[it].x + b.x, t[it].y + b.y, t[it].z + b.z, t[it].w + b.w);
+    float* d = dst + it * row_step;
     if (MODE == 3) {
-      const float4 o = *reinterpret_cast<const float4*>(dst);
+      const float4 o = *reinterpret_cast<const float4*>(d);
       v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
     }
     if (MODE == 1) {
-      const int64_t id = p.gid_bytes == 8 ? static_cast<const int64_t*>(p.gids)[grow]
-                                          : static_cast<int64_t>(static_cast<const int32_t*>(p.gids)[grow]);
-      const float4 o = ldg4(p.gtab + id * p.ld_gtab + n);
+      const float4 o = ldg4(trow[it]);
       v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
     }
-    st4(dst, v);
+    st4(d, v);
     if (MODE == 2)
-      st4(p.C_act + grow * p.ldca + n, make_float4(act_apply(v.x, p.act), act_apply(v.y, p.act), act_apply(v.z, p.act), act_apply(v.w, p.act)));
+      st4(dst_act + it * act_step, make_float4(act_apply(v.x, act), act_apply(v.y, act), act_apply(v.z, act), act_apply(v.w, act)));
   }
 }
 
@@ -969,6 +967,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
                         : p.gtab ? ((vec_g && !p.accumulate && !p.C_act) ? 1 : 4)
                         : p.C_act ? ((vec_a && !p.accumulate) ? 2 : 4)
                         : p.accumulate ? 3 : 0;
+      // per-tile addressing of the specialised paths: this lane's first destination row (row group 0) and column chunk
+      const int64_t fast_row = mb * BM + q * 32 + sub;
+      const int fast_rows = static_cast<int>(min(static_cast<int64_t>(32), p.M - (mb * BM + q * 32))) - sub;   // row group `it` exists iff it * 8 < fast_rows
+      float* fast_dst = C + fast_row * p.ldc + n0 + c4;
+      const int64_t fast_step = static_cast<int64_t>(32 / LR) * p.ldc;
+      float* fast_dst_act = p.C_act ? p.C_act + fast_row * p.ldca + n0 + c4 : nullptr;
+      const int64_t fast_act_step = static_cast<int64_t>(32 / LR) * p.ldca;
+      const float* fast_trow[LR];
+#pragma unroll
+      for (int it = 0; it < LR; ++it) {
+        fast_trow[it] = nullptr;
+        if (wmode == 1 && it * (32 / LR) < fast_rows) {
+          const int64_t grow = fast_row + it * (32 / LR);
+          const int64_t id = p.gid_bytes == 8 ? static_cast<const int64_t*>(p.gids)[grow]
+                                              : static_cast<int64_t>(static_cast<const int32_t*>(p.gids)[grow]);
+          fast_trow[it] = p.gtab + id * p.ld_gtab + n0 + c4;
+        }
+      }
       // One ROLLED loop over the write-out passes: the body below (bias / accumulate / table gather / activation, each
       // behind a run-time flag) is emitted once instead of CW/PW times -- unrolled it was over half of the kernel's SASS
       // and the instruction cache, not the LSU, bounded the write-out.  Only the register -> staging copy is selected
@@ -997,11 +1013,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
             for (int e = 0; e < 4; ++e) if (n + e < p.N) b4[e] = __ldg(p.bias + n + e);
           }
           if (whole && wmode != 4) {
-            const int64_t row0 = mb * BM + q * 32;
-            if (wmode == 0) ts_write_rows<0, PW, BM>(p, stg, lane, row0, n, b4);
-            else if (wmode == 1) ts_write_rows<1, PW, BM>(p, stg, lane, row0, n, b4);
-            else if (wmode == 2) ts_write_rows<2, PW, BM>(p, stg, lane, row0, n, b4);
-            else ts_write_rows<3, PW, BM>(p, stg, lane, row0, n, b4);
+            const float4 bv = make_float4(b4[0], b4[1], b4[2], b4[3]);
+            const float* sl = stg + sub * kStgLd + c4;
+            float* d = fast_dst + c0;
+            if (wmode == 0) ts_write_rows<0, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, fast_trow);
+            else if (wmode == 1) {
+              const float* tr[LR];
+#pragma unroll
+              for (int it = 0; it < LR; ++it) tr[it] = fast_trow[it] + c0;
+              ts_write_rows<1, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, tr);
+            } else if (wmode == 2) ts_write_rows<2, PW>(sl, d, fast_step, fast_rows, bv, fast_dst_act + c0, fast_act_step, p.act, fast_trow);
+            else ts_write_rows<3, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, fast_trow);
             continue;
           }
 #pragma unroll 1
