@@ -226,6 +226,26 @@ __device__ __forceinline__ void stage_raw(const float* __restrict__ src, int64_t
   }
 }
 
+// MN-major staging with everything that depends on the tile only hoisted out of the per-slab path (wgrad: both operands
+// stream through here): `base` = src + mn0 + chunk * 4, `mn_ok` bit b = this thread's columns of 32-wide block b exist,
+// `raw0` = slot address + this thread's first chunk offset.  Row r0 + 16 i of the slab is reduction row r0 + 16 (i & 1) of
+// block i >> 1, whose shared-memory offset differs from the first by a compile-time constant.
+template <int EXT>
+__device__ __forceinline__ void stage_raw_mn_fast(const float* __restrict__ base, int64_t ld, uint32_t mn_ok, int64_t k0,
+                                                  int64_t k_end, uint32_t raw0, int r0) {
+  constexpr int NV = EXT * 8 / kProducerThreads;
+  const int64_t k = k0 + r0;
+  const float* g0 = base + k * ld;
+  const int64_t half = 16 * ld;
+  const bool k_ok0 = k < k_end, k_ok1 = k + 16 < k_end;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const bool ok = ((i & 1) ? k_ok1 : k_ok0) && ((mn_ok >> (i >> 1)) & 1u);
+    const float* g = g0 + ((i & 1) ? half : 0) + (i >> 1) * 32;
+    cp_async16_zfill(raw0 + static_cast<uint32_t>((4 * (i & 1) * (EXT / 32) + (i >> 1)) * 512), ok ? g : base, ok ? 16u : 0u);
+  }
+}
+
 // SUM (MN-major only): also accumulate the raw values per 32-wide MN block into cs[] -- thread t sees, for every
 // block, the same 4 columns (chunk t & 7) of two reduction rows per slab, so cs[blk] is a partial column sum.
 template <int EXT, bool MN, bool SUM = false>
@@ -329,13 +349,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
 
   // tile / k-slab cursor shared by the producer, loader and (implicitly) MMA / epilogue loops: tiles are dealt
   // round-robin to the persistent CTAs, a tile's reduction range is cut into BK-deep slabs
-  struct Cur { int64_t tile, k0, ke, mb, nb; bool live; };
+  struct Cur { int64_t tile, k0, ke, mb, nb; bool live; const float *a_base, *b_base; uint32_t a_ok, b_ok; };
+  const int st_chunk = threadIdx.x & 7;              // producers: 16-byte chunk this thread stages (MN-major fast path)
   auto tile_range = [&](Cur& c) {
     const int64_t sp = c.tile / (num_n * num_m);
     c.nb = c.tile % num_n;
     c.mb = (c.tile / num_n) % num_m;
     c.k0 = sp * p.k_per_split;
     c.ke = min(p.K, c.k0 + p.k_per_split);
+    if constexpr (A_MN) {
+      const int64_t mn = c.mb * BM + st_chunk * 4;
+      c.a_base = p.A + mn;
+      c.a_ok = 0;
+#pragma unroll
+      for (int b = 0; b < BM / 32; ++b) c.a_ok |= (mn + 32 * b < p.M) ? (1u << b) : 0u;
+    }
+    if constexpr (B_MN && !B_PACKED) {
+      const int64_t mn = c.nb * BN + st_chunk * 4;
+      c.b_base = p.B + mn;
+      c.b_ok = 0;
+#pragma unroll
+      for (int b = 0; b < BN / 32; ++b) c.b_ok |= (mn + 32 * b < p.N) ? (1u << b) : 0u;
+    }
   };
   auto init = [&](Cur& c) {
     c.tile = blockIdx.x;
@@ -363,12 +398,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
     // bandwidth, which the tensor core's own operand reads nearly saturate at N = 128; profiles/r1c_gemm_knockouts.txt.)
     int istage = 0, cstage = 0;
     uint32_t iphase = 0;
+    const int st_r0 = t >> 3;
+    const uint32_t st_offa = chunk_offset<BM, true>(st_r0, st_chunk), st_offb = chunk_offset<BN, true>(st_r0, st_chunk);
     auto issue = [&](const Cur& c) {
-      const int64_t nb = c.tile % num_n, mb = (c.tile / num_n) % num_m;
       mbar_wait(smem_u32(&bar_empty[istage]), iphase ^ 1u);
       uint8_t* st = smem + static_cast<size_t>(istage) * kStageBytes;
-      stage_raw<BM, A_MN>(p.A, p.lda, mb * BM, p.M, c.k0, c.ke, smem_u32(st), t);
-      if constexpr (!B_PACKED) stage_raw<BN, B_MN>(p.B, p.ldb, nb * BN, p.N, c.k0, c.ke, smem_u32(st + 2 * kATile), t);
+      if constexpr (A_MN) stage_raw_mn_fast<BM>(c.a_base, p.lda, c.a_ok, c.k0, c.ke, smem_u32(st) + st_offa, st_r0);
+      else stage_raw<BM, false>(p.A, p.lda, c.mb * BM, p.M, c.k0, c.ke, smem_u32(st), t);
+      if constexpr (!B_PACKED) {
+        if constexpr (B_MN) stage_raw_mn_fast<BN>(c.b_base, p.ldb, c.b_ok, c.k0, c.ke, smem_u32(st + 2 * kATile) + st_offb, st_r0);
+        else stage_raw<BN, false>(p.B, p.ldb, c.nb * BN, p.N, c.k0, c.ke, smem_u32(st + 2 * kATile), t);
+      }
       if (++istage == S) { istage = 0; iphase ^= 1u; }
     };
     // fused bias gradient (wgrad): column sums of dy, accumulated while its slabs pass through the producers
