@@ -176,6 +176,11 @@ __device__ __forceinline__ float act_grad(float x, int act) {
 __device__ __forceinline__ float rn_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// The low half of a split is only ever a tensor-core operand: kind::tf32 ignores the 13 low mantissa bits of its
+// operands, so rounding to nearest needs the carry (+ 2^12 ulp) but not the mask.  (The high half keeps the mask: it is
+// also subtracted from x, which needs the exact tf32 value.)  SEGGER_B200-internal: parity tests compare bit-identical
+// error figures with and without this shortcut.
+__device__ __forceinline__ float rn_tf32_operand(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
 // Operand slab staging: EXT rows of the MN dimension x BK reduction elements starting at (mn0, k0).
 // Every producer thread owns NV 16-byte chunks of the slab: it copies them global -> shared with cp.async
@@ -241,8 +246,10 @@ __device__ __forceinline__ void stage_raw_mn_fast(const float* __restrict__ base
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const bool ok = ((i & 1) ? k_ok1 : k_ok0) && ((mn_ok >> (i >> 1)) & 1u);
-    const float* g = g0 + ((i & 1) ? half : 0) + (i >> 1) * 32;
-    cp_async16_zfill(raw0 + static_cast<uint32_t>((4 * (i & 1) * (EXT / 32) + (i >> 1)) * 512), ok ? g : base, ok ? 16u : 0u);
+    // src-size 0 reads nothing (pure zero fill): the address of an out-of-range chunk is never dereferenced, so it is
+    // not replaced by a safe one -- the two row pointers then serve all chunks with immediate offsets
+    const float* g = ((i & 1) ? g0 + half : g0) + (i >> 1) * 32;
+    cp_async16_zfill(raw0 + static_cast<uint32_t>((4 * (i & 1) * (EXT / 32) + (i >> 1)) * 512), g, ok ? 16u : 0u);
   }
 }
 
@@ -262,10 +269,10 @@ __device__ __forceinline__ void split_slab(const uint8_t* raw_tile, uint8_t* hi_
       c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
     }
     float4 h, l;
-    h.x = rn_tf32(v.x); l.x = rn_tf32(v.x - h.x);
-    h.y = rn_tf32(v.y); l.y = rn_tf32(v.y - h.y);
-    h.z = rn_tf32(v.z); l.z = rn_tf32(v.z - h.z);
-    h.w = rn_tf32(v.w); l.w = rn_tf32(v.w - h.w);
+    h.x = rn_tf32(v.x); l.x = rn_tf32_operand(v.x - h.x);
+    h.y = rn_tf32(v.y); l.y = rn_tf32_operand(v.y - h.y);
+    h.z = rn_tf32(v.z); l.z = rn_tf32_operand(v.z - h.z);
+    h.w = rn_tf32(v.w); l.w = rn_tf32_operand(v.w - h.w);
     *reinterpret_cast<float4*>(hi_tile + off) = h;
     *reinterpret_cast<float4*>(lo_tile + off) = l;
   }
@@ -876,7 +883,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
         for (int e = 0; e < 4; ++e) {
           const float h = rn_tf32(x[e]);
           hi[c * 4 + e] = __float_as_uint(h);
-          lo[c * 4 + e] = __float_as_uint(rn_tf32(x[e] - h));
+          lo[c * 4 + e] = __float_as_uint(rn_tf32_operand(x[e] - h));
         }
       }
       crslot = (crslot + 1 == kTsRaw) ? 0 : crslot + 1;
