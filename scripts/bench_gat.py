@@ -40,7 +40,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     touched_tt = int(torch.unique(d["e_tt"][0]).numel())
     touched_tb = int(torch.unique(d["e_tb"][0]).numel())
-    hbm, _ = bench.peaks()
+    hbm = bench.peaks()[0]
 
     def time_it(fn):
         fn(); torch.cuda.synchronize()
