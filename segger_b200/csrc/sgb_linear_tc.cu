@@ -43,9 +43,11 @@ constexpr int kEpiWarp0 = kProducerWarps;      // warpgroups 1-2
 constexpr int kEpiWarps = 8;       // two per TMEM lane quarter, each owning half of the tile's columns
 constexpr int kMmaWarp = kEpiWarp0 + kEpiWarps;   // warpgroup 3: MMA issuer, packed-weight loader, two idle warps
 constexpr int kBLoadWarp = kMmaWarp + 1;
+constexpr int kHelperWarp0 = kMmaWarp + 2;      // wgrad: the two otherwise idle warps of warpgroup 3 stage + split half of B
+constexpr int kHelperThreads = 64;
 constexpr int kThreads = 16 * 32;  // 512: four whole warpgroups, so setmaxnreg can move registers between the roles
 // Register budget (64K per SM, 128 per thread at launch): warpgroup 3 gives up 72 per thread, the producers take them.
-constexpr int kRegsProducer = 200, kRegsControl = 56;
+constexpr int kRegsProducer = 184, kRegsControl = 72;   // 128 x 184 + 256 x 128 + 128 x 72 = 64K
 constexpr int kMaxStages = 4;
 // epilogue transpose buffer: per warp 32 rows x (PW + 4) floats, PW = columns written out per pass
 constexpr int kPW = 16;            // 64-byte row segments per write-out pass: leaves shared memory for a third 64 KB stage
@@ -235,10 +237,10 @@ __device__ __forceinline__ void stage_raw(const float* __restrict__ src, int64_t
 // stream through here): `base` = src + mn0 + chunk * 4, `mn_ok` bit b = this thread's columns of 32-wide block b exist,
 // `raw0` = slot address + this thread's first chunk offset.  Row r0 + 16 i of the slab is reduction row r0 + 16 (i & 1) of
 // block i >> 1, whose shared-memory offset differs from the first by a compile-time constant.
-template <int EXT>
+template <int EXT, int NVL = EXT * 8 / kProducerThreads>
 __device__ __forceinline__ void stage_raw_mn_fast(const float* __restrict__ base, int64_t ld, uint32_t mn_ok, int64_t k0,
                                                   int64_t k_end, uint32_t raw0, int r0) {
-  constexpr int NV = EXT * 8 / kProducerThreads;
+  constexpr int NV = NVL;
   const int64_t k = k0 + r0;
   const float* g0 = base + k * ld;
   const int64_t half = 16 * ld;
@@ -253,11 +255,53 @@ __device__ __forceinline__ void stage_raw_mn_fast(const float* __restrict__ base
   }
 }
 
+// wgrad helpers (64 threads, ht = 0..63): the upper half of B's 32-wide MN blocks (blk >= EXT / 64), all 32 reduction
+// rows: thread ht owns chunk ht & 7 of rows (ht >> 3) + 8 j, j < 4, of each of those blocks.  `base` / `mn_ok` as above.
+template <int EXT>
+__device__ __forceinline__ uint32_t helper_off0(int ht) {
+  return chunk_offset<EXT, true>((EXT / 64) * 32 + (ht >> 3), ht & 7);
+}
+template <int EXT>
+__device__ __forceinline__ void stage_raw_mn_helper(const float* __restrict__ base, int64_t ld, uint32_t mn_ok, int64_t k0,
+                                                    int64_t k_end, uint32_t raw0, int ht) {
+  const int64_t k = k0 + (ht >> 3);
+  const float* g0 = base + k * ld + (EXT / 64) * 32;
+  const int64_t step = 8 * ld;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool kok = k + 8 * j < k_end;
+#pragma unroll
+    for (int b = 0; b < EXT / 64; ++b) {
+      const bool ok = kok && ((mn_ok >> (EXT / 64 + b)) & 1u);
+      cp_async16_zfill(raw0 + static_cast<uint32_t>((2 * j * (EXT / 32) + b) * 512), g0 + j * step + b * 32, ok ? 16u : 0u);
+    }
+  }
+}
+template <int EXT>
+__device__ __forceinline__ void split_slab_helper(uint8_t* hi_tile, uint8_t* lo_tile, int ht) {
+  const uint32_t off0 = helper_off0<EXT>(ht);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int b = 0; b < EXT / 64; ++b) {
+      const uint32_t off = off0 + static_cast<uint32_t>((2 * j * (EXT / 32) + b) * 512);
+      const float4 v = *reinterpret_cast<const float4*>(hi_tile + off);
+      float4 h, l;
+      h.x = rn_tf32(v.x); l.x = rn_tf32_operand(v.x - h.x);
+      h.y = rn_tf32(v.y); l.y = rn_tf32_operand(v.y - h.y);
+      h.z = rn_tf32(v.z); l.z = rn_tf32_operand(v.z - h.z);
+      h.w = rn_tf32(v.w); l.w = rn_tf32_operand(v.w - h.w);
+      *reinterpret_cast<float4*>(hi_tile + off) = h;
+      *reinterpret_cast<float4*>(lo_tile + off) = l;
+    }
+  }
+}
+
 // SUM (MN-major only): also accumulate the raw values per 32-wide MN block into cs[] -- thread t sees, for every
 // block, the same 4 columns (chunk t & 7) of two reduction rows per slab, so cs[blk] is a partial column sum.
-template <int EXT, bool MN, bool SUM = false>
+template <int EXT, bool MN, bool SUM = false, int NVL = EXT * 8 / kProducerThreads>
 __device__ __forceinline__ void split_slab(const uint8_t* raw_tile, uint8_t* hi_tile, uint8_t* lo_tile, int t, float4* cs = nullptr) {
-  constexpr int NV = EXT * 8 / kProducerThreads;
+  constexpr int NV = NVL;
   const int chunk = t & 7;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -329,10 +373,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int stages = S;
+  // wgrad (both operands streamed, MN-major): the producers were the busiest role (ncu source view: 82 % of their
+  // cycles issuing); the two idle warps of warpgroup 3 take the upper half of B's columns off them
+  constexpr bool kHelp = A_MN && B_MN && !B_PACKED;
+  constexpr int kNvB = BN * 8 / kProducerThreads / (kHelp ? 2 : 1);     // B row slots per main producer thread
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), kProducerThreads + (B_PACKED ? 1 : 0));
+      mbar_init(smem_u32(&bar_full[s]), kProducerThreads + (B_PACKED ? 1 : 0) + (kHelp ? kHelperThreads : 0));
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     for (int a = 0; a < kAccBufs; ++a) {
@@ -413,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
       if constexpr (A_MN) stage_raw_mn_fast<BM>(c.a_base, p.lda, c.a_ok, c.k0, c.ke, smem_u32(st) + st_offa, st_r0);
       else stage_raw<BM, false>(p.A, p.lda, c.mb * BM, p.M, c.k0, c.ke, smem_u32(st), t);
       if constexpr (!B_PACKED) {
-        if constexpr (B_MN) stage_raw_mn_fast<BN>(c.b_base, p.ldb, c.b_ok, c.k0, c.ke, smem_u32(st + 2 * kATile) + st_offb, st_r0);
+        if constexpr (B_MN) stage_raw_mn_fast<BN, kNvB>(c.b_base, p.ldb, c.b_ok, c.k0, c.ke, smem_u32(st + 2 * kATile) + st_offb, st_r0);
         else stage_raw<BN, false>(p.B, p.ldb, c.nb * BN, p.N, c.k0, c.ke, smem_u32(st + 2 * kATile), t);
       }
       if (++istage == S) { istage = 0; iphase ^= 1u; }
@@ -463,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
       cp_async_wait<S - 2>();                       // this thread's chunks of slab `ci` have landed
       uint8_t* st = smem + static_cast<size_t>(cstage) * kStageBytes;
       if (!(p.dbg & 2)) split_slab<BM, A_MN, kColsum>(st, st, st + kATile, t, cs);
-      if constexpr (!B_PACKED) if (!(p.dbg & 2)) split_slab<BN, B_MN>(st + 2 * kATile, st + 2 * kATile, st + 2 * kATile + kBTile, t);
+      if constexpr (!B_PACKED) if (!(p.dbg & 2)) split_slab<BN, B_MN, false, kNvB>(st + 2 * kATile, st + 2 * kATile, st + 2 * kATile + kBTile, t);
       fence_proxy_async();
       mbar_arrive(smem_u32(&bar_full[cstage]));
       if (++cstage == S) cstage = 0;
@@ -492,6 +540,43 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
         bulk_g2s(smem_u32(st + 2 * kATile), p.Bp + static_cast<size_t>(blk) * (2 * BN * 32), 2 * kBTile, smem_u32(&bar_full[stage]));
         if (++stage == S) { stage = 0; phase ^= 1u; }
         advance(b);
+      }
+    }
+    if constexpr (kHelp) {
+      if (warp >= kHelperWarp0) {
+        // ===================================== wgrad helpers =====================================
+        // same protocol as the producers (stage S-1 slabs ahead into the slot, later split the very same chunks in
+        // place, arrive on the slot's full barrier), on the upper half of B's column blocks
+        const int ht = threadIdx.x - kHelperWarp0 * 32;
+        const uint32_t hoff = helper_off0<BN>(ht);
+        int istage = 0, cstage = 0;
+        uint32_t iphase = 0;
+        auto issue = [&](const Cur& c) {
+          mbar_wait(smem_u32(&bar_empty[istage]), iphase ^ 1u);
+          uint8_t* st = smem + static_cast<size_t>(istage) * kStageBytes;
+          stage_raw_mn_helper<BN>(c.b_base, p.ldb, c.b_ok, c.k0, c.ke, smem_u32(st + 2 * kATile) + hoff, ht);
+          if (++istage == S) { istage = 0; iphase ^= 1u; }
+        };
+        Cur pi, ci;
+        init(pi);
+        init(ci);
+#pragma unroll
+        for (int i = 0; i < S - 1; ++i) {
+          if (pi.live) { issue(pi); advance(pi); }
+          cp_async_commit();
+        }
+        while (ci.live) {
+          cp_async_wait<S - 2>();
+          uint8_t* st = smem + static_cast<size_t>(cstage) * kStageBytes;
+          if (!(p.dbg & 2)) split_slab_helper<BN>(st + 2 * kATile, st + 2 * kATile + kBTile, ht);
+          fence_proxy_async();
+          mbar_arrive(smem_u32(&bar_full[cstage]));
+          if (++cstage == S) cstage = 0;
+          advance(ci);
+          if (pi.live) { issue(pi); advance(pi); }
+          cp_async_commit();
+        }
+        cp_async_wait<0>();
       }
     }
     // ===================================== MMA issuer =====================================
