@@ -224,29 +224,31 @@ segment_sum_stage1_vec_kernel(const float* __restrict__ dy, int64_t ldy, const u
   flush(n);
 }
 
-// Stage 2: warp per table row; segments spanning several chunks are summed in chunk order.
+// Stage 2: one warp per (table row, 32-column group); segments spanning several chunks are summed in chunk order (the
+// order per column is what it was with one warp per row, so results are bit-identical -- but a hot gene's few hundred
+// chunks are now walked by D / 32 warps side by side instead of one warp looping over the column groups).
 __global__ void __launch_bounds__(256)
-embedding_bwd_stage2_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int D, const float* __restrict__ part,
-                            float* __restrict__ grad_table) {
+embedding_bwd_stage2_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int D, int col_groups,
+                            const float* __restrict__ part, float* __restrict__ grad_table) {
   const int lane = threadIdx.x & 31;
-  const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (g >= n_rows) return;
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t g = w / col_groups;
+  const int c = static_cast<int>(w % col_groups) * 32 + lane;
+  if (g >= n_rows || c >= D) return;
   const int64_t s = rowptr[g], e = rowptr[g + 1];
   float* dst = grad_table + g * D;
   if (s == e) {
-    for (int c = lane; c < D; c += 32) dst[c] = 0.f;
+    dst[c] = 0.f;
     return;
   }
   const int64_t c_first = s / kEmbChunk, c_last = (e - 1) / kEmbChunk;
   if (c_first == c_last) return;  // written by stage 1
-  for (int c = lane; c < D; c += 32) {
-    float acc = 0.f;
-    for (int64_t ch = c_first; ch <= c_last; ++ch) {
-      const int slot = (ch == c_first && s != ch * kEmbChunk) ? 1 : 0;
-      acc += part[(ch * 2 + slot) * D + c];
-    }
-    dst[c] = acc;
+  float acc = 0.f;
+  for (int64_t ch = c_first; ch <= c_last; ++ch) {
+    const int slot = (ch == c_first && s != ch * kEmbChunk) ? 1 : 0;
+    acc += part[(ch * 2 + slot) * D + c];
   }
+  dst[c] = acc;
 }
 
 // ---- positional features ----
@@ -618,7 +620,9 @@ extern "C" int sgb_embedding_bwd(const float* dy, int64_t ldy, const void* ids, 
     embedding_bwd_stage1_kernel<<<s1_blocks, 256, 0, stream>>>(
         dy, ldy, e.sid, e.perm, e.rowptr, N, D, table, table ? act : SGB_ACT_NONE, grad_table, e.part);
   }
-  embedding_bwd_stage2_kernel<<<static_cast<unsigned>(ceil_div(n_rows, 8)), 256, 0, stream>>>(e.rowptr, n_rows, D, e.part, grad_table);
+  const int col_groups = (D + 31) / 32;
+  embedding_bwd_stage2_kernel<<<static_cast<unsigned>(ceil_div(n_rows * col_groups, 8)), 256, 0, stream>>>(e.rowptr, n_rows, D, col_groups,
+                                                                                                  e.part, grad_table);
   return check_launch("embedding_bwd");
 }
 
