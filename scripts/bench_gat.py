@@ -56,7 +56,9 @@ def main():
     res = {}
     outs = {}
     for path in a.paths.split(","):
-        os.environ["SEGGER_B200_GAT"] = path
+        # "quad_nosort": the quad kernels with the warp's rows in chunk order (A/B of the degree-ordered quads)
+        os.environ["SEGGER_B200_GAT"] = "quad" if path.startswith("quad") else path
+        os.environ["SEGGER_B200_GAT_SORT"] = "0" if path == "quad_nosort" else "1"
         for name, (xl, xr, csr, gg, ns, nd, touched) in {
             "tt": (y[:, :F], y[:, F:2 * F], csr_tt, gt, n_tx, n_tx, touched_tt),
             "tb": (y[:, 2 * F:], y_bd, csr_tb, gb, n_tx, n_cells, touched_tb),

@@ -51,6 +51,44 @@ __device__ __forceinline__ float4 lrelu_max4(const float4 z, float slope) {
   return make_float4(fmaxf(z.x, slope * z.x), fmaxf(z.y, slope * z.y), fmaxf(z.z, slope * z.z), fmaxf(z.w, slope * z.w));
 }
 
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE round-to-nearest operations per issue slot).  These
+// kernels are bound by instruction issue, not by the fp32 pipes, so every per-element add / multiply / fma of the
+// per-edge step works on the (x, y) and (z, w) halves of a float4.
+__device__ __forceinline__ float2 lo2(const float4 a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ float2 hi2(const float4 a) { return make_float2(a.z, a.w); }
+__device__ __forceinline__ float4 cat2(const float2 a, const float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+__device__ __forceinline__ float4 add4p(const float4 a, const float4 b) {
+  return cat2(__fadd2_rn(lo2(a), lo2(b)), __fadd2_rn(hi2(a), hi2(b)));
+}
+__device__ __forceinline__ float4 mul4p(const float4 a, const float4 b) {
+  return cat2(__fmul2_rn(lo2(a), lo2(b)), __fmul2_rn(hi2(a), hi2(b)));
+}
+// acc += w * x
+__device__ __forceinline__ void fma4p(float4& acc, const float w, const float4 x) {
+  const float2 w2 = make_float2(w, w);
+  acc = cat2(__ffma2_rn(w2, lo2(x), lo2(acc)), __ffma2_rn(w2, hi2(x), hi2(acc)));
+}
+// acc += a (.) b
+__device__ __forceinline__ void fma4v(float4& acc, const float4 a, const float4 b) {
+  acc = cat2(__ffma2_rn(lo2(a), lo2(b), lo2(acc)), __ffma2_rn(hi2(a), hi2(b), hi2(acc)));
+}
+__device__ __forceinline__ void scale4p(float4& a, const float s) {
+  const float2 s2 = make_float2(s, s);
+  a = cat2(__fmul2_rn(lo2(a), s2), __fmul2_rn(hi2(a), s2));
+}
+// two-lane running dot product: p += a (.) b over both halves; the caller adds p.x + p.y at the end
+__device__ __forceinline__ void dot4p(float2& p, const float4 a, const float4 b) {
+  p = __ffma2_rn(lo2(a), lo2(b), p);
+  p = __ffma2_rn(hi2(a), hi2(b), p);
+}
+// lrelu(x + r) for 0 <= slope <= 1 as max(z, slope*z), packed add / multiply
+__device__ __forceinline__ float4 lrelu_sum4p(const float4 x, const float4 r, const float slope) {
+  const float2 s2 = make_float2(slope, slope);
+  const float2 z0 = __fadd2_rn(lo2(x), lo2(r)), z1 = __fadd2_rn(hi2(x), hi2(r));
+  const float2 m0 = __fmul2_rn(z0, s2), m1 = __fmul2_rn(z1, s2);
+  return make_float4(fmaxf(z0.x, m0.x), fmaxf(z0.y, m0.y), fmaxf(z1.x, m1.x), fmaxf(z1.y, m1.y));
+}
+
 template <int LPR>
 __device__ __forceinline__ float group_sum(float x) {
 #pragma unroll
@@ -58,13 +96,50 @@ __device__ __forceinline__ float group_sum(float x) {
   return x;
 }
 
-// rows of this lane group in quad q: CSR range [beg, beg+deg), mx = max degree over the warp's groups
+// The rows of a warp's chunk live in lanes: lane l holds (first CSR position, degree, row offset inside the chunk) of
+// the row it will hand to lane group l % G of quad l / G.  A quad advances its G rows in lock step for max-degree
+// steps, so rows of unequal degree waste issue slots (kNN in-degrees: 1.32 x E/G steps in chunk order).  The chunk's
+// rows are therefore dealt out in order of decreasing degree (1.06 x): results per row are unchanged (a row's edges
+// keep their CSR order), only the grouping of rows into quads -- and with it the summation order of the
+// grad_att / grad_bias partial sums -- differs.
+constexpr int kNoRow = 0x7fffffff;   // row offset of an empty lane: wrow0 + kNoRow >= n for every n < 2^31
+
 template <int LPR>
-__device__ __forceinline__ void quad_info(int rp_b, int rp_e, int q, int g, int& beg, int& deg, int& mx) {
+__device__ __forceinline__ void chunk_rows(const int32_t* __restrict__ rowptr, int64_t wrow0, int nrows, int64_t n, int lane,
+                                           bool sort, int& rp_b, int& rp_d, int& rp_o) {
+  constexpr int G = 32 / LPR;
+  const int b = __ldg(rowptr + min(wrow0 + lane, n));
+  const int e = __ldg(rowptr + min(wrow0 + lane + 1, n));
+  const bool valid = lane < nrows;
+  rp_b = b;
+  rp_d = valid ? e - b : 0;
+  rp_o = valid ? lane : kNoRow;
+  // (rows of equal degree -- the out-degrees of a kNN graph -- have nothing to gain: skip)
+  const bool ragged = __reduce_max_sync(kFull, valid ? rp_d : 0) != __reduce_min_sync(kFull, valid ? rp_d : 0x7fffffff);
+  if (G > 1 && sort && nrows > G && ragged) {
+    // distinct keys: decreasing (clamped) degree, then lane; empty lanes last.  Any permutation is correct.
+    const uint32_t dk = static_cast<uint32_t>(min(rp_d, 0x3ffffff));
+    const uint32_t key = valid ? ((0x3ffffffu - dk) << 5 | static_cast<uint32_t>(lane)) : (0xffffffe0u | static_cast<uint32_t>(lane));
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) rank += __shfl_sync(kFull, key, j) < key ? 1 : 0;
+    int inv = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) inv = __shfl_sync(kFull, rank, j) == lane ? j : inv;
+    rp_b = __shfl_sync(kFull, rp_b, inv);
+    rp_d = __shfl_sync(kFull, rp_d, inv);
+    rp_o = __shfl_sync(kFull, rp_o, inv);
+  }
+}
+
+// rows of this lane group in quad q: CSR range [beg, beg+deg), row offset off, mx = max degree over the warp's groups
+template <int LPR>
+__device__ __forceinline__ void quad_info(int rp_b, int rp_d, int rp_o, int q, int g, int& beg, int& deg, int& off, int& mx) {
   constexpr int G = 32 / LPR;
   const int idx = q * G + g;
   beg = __shfl_sync(kFull, rp_b, idx);
-  deg = __shfl_sync(kFull, rp_e, idx) - beg;
+  deg = __shfl_sync(kFull, rp_d, idx);
+  off = __shfl_sync(kFull, rp_o, idx);
   mx = (G == 1) ? deg : __reduce_max_sync(kFull, deg);
 }
 
@@ -79,18 +154,18 @@ struct Pipe {
   uint32_t ring;        // shared-space byte address of this lane's column of the ring
   int pslot = 0, cslot = 0;
   // producer cursor
-  int pq = 0, pk = 0, p_beg = 0, p_deg = 0, p_n = 0;
+  int pq = 0, pk = 0, p_beg = 0, p_deg = 0, p_off = 0, p_n = 0;
   int nq = 0;
-  int rp_b = 0, rp_e = 0;
+  int rp_b = 0, rp_d = 0, rp_o = 0;
   int g = 0;
 
-  __device__ __forceinline__ void start(int nq_, int rp_b_, int rp_e_, int g_) {
-    nq = nq_; rp_b = rp_b_; rp_e = rp_e_; g = g_;
+  __device__ __forceinline__ void start(int nq_, int rp_b_, int rp_d_, int rp_o_, int g_) {
+    nq = nq_; rp_b = rp_b_; rp_d = rp_d_; rp_o = rp_o_; g = g_;
     pq = 0; pk = 0;
     pslot = 0; cslot = 0;   // a previous chunk leaves only empty groups behind: restart the ring in phase
     if (nq > 0) {
       int mx;
-      quad_info<LPR>(rp_b, rp_e, 0, g, p_beg, p_deg, mx);
+      quad_info<LPR>(rp_b, rp_d, rp_o, 0, g, p_beg, p_deg, p_off, mx);
       p_n = mx + NH;
     }
   }
@@ -101,7 +176,7 @@ struct Pipe {
       ++pq;
       if (pq < nq) {
         int mx;
-        quad_info<LPR>(rp_b, rp_e, pq, g, p_beg, p_deg, mx);
+        quad_info<LPR>(rp_b, rp_d, rp_o, pq, g, p_beg, p_deg, p_off, mx);
         p_n = mx + NH;
       }
     }
@@ -145,7 +220,7 @@ __device__ __forceinline__ void sts4(uint32_t saddr, const float4 v) {
 // Forward
 // ================================================================================================
 template <int V, int LPR, int H, int D>
-__global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
+__global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks, const int sort) {
   const uint64_t seed_eff = p.training ? gat_seed(p) : 0;
   constexpr int G = 32 / LPR, VPH = V / H;
   static_assert(V % H == 0, "a lane must hold whole heads");
@@ -169,9 +244,9 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
     const int64_t wrow0 = chunk * rpw;
     const int nrows = static_cast<int>(min(static_cast<int64_t>(rpw), p.n_dst - wrow0));
     const int nq = (nrows + G - 1) / G;
-    const int rp_b = __ldg(p.rowptr + min(wrow0 + lane, p.n_dst));
-    const int rp_e = __ldg(p.rowptr + min(wrow0 + lane + 1, p.n_dst));
-    pipe.start(nq, rp_b, rp_e, g);
+    int rp_b, rp_d, rp_o;
+    chunk_rows<LPR>(p.rowptr, wrow0, nrows, p.n_dst, lane, sort != 0, rp_b, rp_d, rp_o);
+    pipe.start(nq, rp_b, rp_d, rp_o, g);
 
     const float* nsrc = nullptr;
     bool nact = false;
@@ -179,7 +254,7 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
       nact = false;
       if (pipe.pq < pipe.nq) {
         if (pipe.pk == 0) {
-          const int64_t row = wrow0 + pipe.pq * G + g;
+          const int64_t row = wrow0 + pipe.p_off;
           nact = row < p.n_dst;
           nsrc = p.x_r + row * p.ld_r;
         } else {
@@ -204,9 +279,9 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
     for (int i = 0; i < D - 1; ++i) { issue(); gen(); }
 
     for (int q = 0; q < nq; ++q) {
-      int c_beg, c_deg, c_mx;
-      quad_info<LPR>(rp_b, rp_e, q, g, c_beg, c_deg, c_mx);
-      const int64_t row = wrow0 + q * G + g;
+      int c_beg, c_deg, c_off, c_mx;
+      quad_info<LPR>(rp_b, rp_d, rp_o, q, g, c_beg, c_deg, c_off, c_mx);
+      const int64_t row = wrow0 + c_off;
       const bool rvalid = row < p.n_dst;
 
       issue(); gen(); cp_wait<D - 1>();
@@ -232,13 +307,13 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
         float lg[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          float p1 = 0.f;
+          float2 p1 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int u = 0; u < VPH; ++u) {
             const int t = h * VPH + u;
-            p1 += dot4(a[t], lrelu_max4(add4(x[t], r[t]), slope));
+            dot4p(p1, a[t], lrelu_sum4p(x[t], r[t], slope));
           }
-          lg[h] = group_sum<LPR>(p1);
+          lg[h] = group_sum<LPR>(p1.x + p1.y);
         }
         const int e = eid_next;
         if (training && k + 1 < c_deg) eid_next = __ldg(p.eid + c_beg + k + 1);
@@ -258,7 +333,7 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
               const float sc = __expf(m[h] - mn);
               ss[h] *= sc;
 #pragma unroll
-              for (int u = 0; u < VPH; ++u) scale4(acc[h * VPH + u], sc);
+              for (int u = 0; u < VPH; ++u) scale4p(acc[h * VPH + u], sc);
               m[h] = mn;
             }
           }
@@ -272,7 +347,7 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
           float w = pe;
           if (training) w = rng_head(eh, seed_eff, h) >= p.drop_thr ? pe * p.keep_scale : 0.f;
 #pragma unroll
-          for (int u = 0; u < VPH; ++u) fma4(acc[h * VPH + u], w, x[h * VPH + u]);
+          for (int u = 0; u < VPH; ++u) fma4p(acc[h * VPH + u], w, x[h * VPH + u]);
         }
       }
 
@@ -310,7 +385,7 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
 // that every CTA is resident from the start: a grid of 4 x #SMs with only 3 CTAs fitting runs a second,
 // two-thirds-empty wave).
 template <int V, int LPR, int H, int D, int MINB>
-__global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
+__global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks, const int sort) {
   const uint64_t seed_eff = p.training ? gat_seed(p) : 0;
   constexpr int G = 32 / LPR, VPH = V / H, F4 = V * LPR;
   constexpr int SH = rec_scalars(H), RSB = rec_bytes(H, LPR);
@@ -341,9 +416,9 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
     const int64_t wrow0 = chunk * rpw;
     const int nrows = static_cast<int>(min(static_cast<int64_t>(rpw), p.n_dst - wrow0));
     const int nq = (nrows + G - 1) / G;
-    const int rp_b = __ldg(p.rowptr + min(wrow0 + lane, p.n_dst));
-    const int rp_e = __ldg(p.rowptr + min(wrow0 + lane + 1, p.n_dst));
-    pipe.start(nq, rp_b, rp_e, g);
+    int rp_b, rp_d, rp_o;
+    chunk_rows<LPR>(p.rowptr, wrow0, nrows, p.n_dst, lane, sort != 0, rp_b, rp_d, rp_o);
+    pipe.start(nq, rp_b, rp_d, rp_o, g);
 
     const float* nsrc = nullptr;
     bool nact = false;
@@ -351,7 +426,7 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
       nact = false;
       if (pipe.pq < pipe.nq) {
         if (pipe.pk < 3) {
-          const int64_t row = wrow0 + pipe.pq * G + g;
+          const int64_t row = wrow0 + pipe.p_off;
           nact = row < p.n_dst;
           nsrc = pipe.pk == 0 ? p.x_r + row * p.ld_r : (pipe.pk == 1 ? p.grad_out + row * p.ld_g : p.out + row * p.ld_out);
         } else {
@@ -376,9 +451,9 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
     for (int i = 0; i < D - 1; ++i) { issue(); gen(); }
 
     for (int q = 0; q < nq; ++q) {
-      int c_beg, c_deg, c_mx;
-      quad_info<LPR>(rp_b, rp_e, q, g, c_beg, c_deg, c_mx);
-      const int64_t row = wrow0 + q * G + g;
+      int c_beg, c_deg, c_off, c_mx;
+      quad_info<LPR>(rp_b, rp_d, rp_o, q, g, c_beg, c_deg, c_off, c_mx);
+      const int64_t row = wrow0 + c_off;
       const bool rvalid = row < p.n_dst;
       float m[H], inv[H];
 #pragma unroll
@@ -431,17 +506,17 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
         float lg[H], dd[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          float p1 = 0.f, pd = 0.f;
+          float2 p1 = make_float2(0.f, 0.f), pd = make_float2(0.f, 0.f);
 #pragma unroll
           for (int u = 0; u < VPH; ++u) {
             const int t = h * VPH + u;
             const float4 x = lds4(pipe.read_addr(t));
-            pd += dot4(g4[t], x);
-            z[t] = lrelu_max4(add4(x, r[t]), slope);
-            p1 += dot4(a[t], z[t]);
+            dot4p(pd, g4[t], x);
+            z[t] = lrelu_sum4p(x, r[t], slope);
+            dot4p(p1, a[t], z[t]);
           }
-          lg[h] = group_sum<LPR>(p1);
-          dd[h] = group_sum<LPR>(pd);
+          lg[h] = group_sum<LPR>(p1.x + p1.y);
+          dd[h] = group_sum<LPR>(pd.x + pd.y);
         }
         pipe.consumed();
         const int e = eid_next;
@@ -477,8 +552,7 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
           const float4 zz = z[t];
           if (!direct_src) {           // (warp-uniform) the common form: accumulate dL/dz_e into grad_x_r with FMAs
             const bool px = zz.x > 0.f, py = zz.y > 0.f, pz = zz.z > 0.f, pw = zz.w > 0.f;
-            gr[t].x = fmaf(px ? d : ds, a[t].x, gr[t].x); gr[t].y = fmaf(py ? d : ds, a[t].y, gr[t].y);
-            gr[t].z = fmaf(pz ? d : ds, a[t].z, gr[t].z); gr[t].w = fmaf(pw ? d : ds, a[t].w, gr[t].w);
+            fma4v(gr[t], make_float4(px ? d : ds, py ? d : ds, pz ? d : ds, pw ? d : ds), a[t]);
             zbits |= (px ? 1u : 0u) << (4 * t) | (py ? 2u : 0u) << (4 * t) | (pz ? 4u : 0u) << (4 * t) | (pw ? 8u : 0u) << (4 * t);
           } else {                     // one source per edge: grad_x_l[j] = dL/dz_e + alpha'_e g_i is written here too
             const float4 dz = make_float4((zz.x > 0.f ? d : ds) * a[t].x, (zz.y > 0.f ? d : ds) * a[t].y,
@@ -490,7 +564,7 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
                   make_float4(fmaf(ak, g4[t].x, dz.x), fmaf(ak, g4[t].y, dz.y), fmaf(ak, g4[t].z, dz.z), fmaf(ak, g4[t].w, dz.w)));
             }
           }
-          fma4(gatt[t], d, zz);
+          fma4p(gatt[t], d, zz);
         }
         if (act && !direct_src) *reinterpret_cast<uint16_t*>(rec_ptr + SH * 4 + 2 * s) = static_cast<uint16_t>(zbits);
       }
@@ -556,7 +630,7 @@ __global__ void quad_colsum_kernel(const float* __restrict__ partial, int nb, in
 // Backward, src-CSR (transposed) pass: grad_x_l
 // ================================================================================================
 template <int V, int LPR, int H, int D>
-__global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks) {
+__global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks, const int sort) {
   // grad_x_l[j] = sum over out-edges e = (j -> i) of  delta_e * att (.) lrelu'(z_e)  +  alpha'_e * g_i
   // Per edge the ring carries the V float4 of g_i this lane consumes and the edge's record (scalars + lrelu' bits):
   // neither x_r[i] nor the row's own x_l is read.
@@ -587,9 +661,9 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const Gat
     const int64_t wrow0 = chunk * rpw;
     const int nrows = static_cast<int>(min(static_cast<int64_t>(rpw), p.n_src - wrow0));
     const int nq = (nrows + G - 1) / G;
-    const int rp_b = __ldg(p.t_rowptr + min(wrow0 + lane, p.n_src));
-    const int rp_e = __ldg(p.t_rowptr + min(wrow0 + lane + 1, p.n_src));
-    pipe.start(nq, rp_b, rp_e, g);
+    int rp_b, rp_d, rp_o;
+    chunk_rows<LPR>(p.t_rowptr, wrow0, nrows, p.n_src, lane, sort != 0, rp_b, rp_d, rp_o);
+    pipe.start(nq, rp_b, rp_d, rp_o, g);
 
     const float* nsrc = nullptr;
     const char* nrec = nullptr;
@@ -623,9 +697,9 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const Gat
     for (int i = 0; i < D - 1; ++i) { issue(); gen(); }
 
     for (int q = 0; q < nq; ++q) {
-      int c_beg, c_deg, c_mx;
-      quad_info<LPR>(rp_b, rp_e, q, g, c_beg, c_deg, c_mx);
-      const int64_t row = wrow0 + q * G + g;
+      int c_beg, c_deg, c_off, c_mx;
+      quad_info<LPR>(rp_b, rp_d, rp_o, q, g, c_beg, c_deg, c_off, c_mx);
+      const int64_t row = wrow0 + c_off;
       const bool rvalid = row < p.n_src;
 
       issue(); gen(); cp_wait<D - 1>();        // header step: nothing to read
@@ -651,11 +725,9 @@ __global__ void __launch_bounds__(kQThreads) gatv2_bwd_src_quad_kernel(const Gat
           const float d = act ? rec[t / VPH] : 0.f;
           const float al = act ? rec[H + t / VPH] : 0.f;
           const float ds = d * slope;
-          acc[t].x = fmaf((zb >> (4 * t)) & 1u ? d : ds, a[t].x, acc[t].x);
-          acc[t].y = fmaf((zb >> (4 * t + 1)) & 1u ? d : ds, a[t].y, acc[t].y);
-          acc[t].z = fmaf((zb >> (4 * t + 2)) & 1u ? d : ds, a[t].z, acc[t].z);
-          acc[t].w = fmaf((zb >> (4 * t + 3)) & 1u ? d : ds, a[t].w, acc[t].w);
-          if (act) fma4(acc[t], al, gg);
+          fma4v(acc[t], make_float4((zb >> (4 * t)) & 1u ? d : ds, (zb >> (4 * t + 1)) & 1u ? d : ds,
+                                    (zb >> (4 * t + 2)) & 1u ? d : ds, (zb >> (4 * t + 3)) & 1u ? d : ds), a[t]);
+          if (act) fma4p(acc[t], al, gg);
         }
         pipe.consumed();
         __syncwarp();   // all lanes are done with this step's record before its slot is refilled
@@ -712,6 +784,12 @@ int pick_rpw(int64_t n_rows, int G) {
 
 constexpr int kDFwd = 4, kDDst = 4, kDSrc = 4;
 
+// SEGGER_B200_GAT_SORT=0: rows keep their chunk order inside a warp (A/B of the degree-ordered quads); read per call
+int quad_sort() {
+  const char* e = getenv("SEGGER_B200_GAT_SORT");
+  return (e && e[0] == '0') ? 0 : 1;
+}
+
 template <typename K>
 bool set_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)) == cudaSuccess;
@@ -739,7 +817,7 @@ bool quad_fwd_launch(const GatParams& p, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(kQW) * kDFwd * V * 512;                                   \
     auto kern = gatv2_fwd_quad_kernel<V, L, Hh, kDFwd>;                                               \
     if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                      \
-    kern<<<blocks, kQThreads, smem, stream>>>(p, rpw, nchunks);                                       \
+    kern<<<blocks, kQThreads, smem, stream>>>(p, rpw, nchunks, quad_sort());                                       \
     return true;                                                                                      \
   }
   SGB_QUAD_COMBOS(X)
@@ -790,11 +868,11 @@ bool quad_bwd_launch(const GatParams& p, float* grad_att, float* grad_bias, cuda
     if (quad_dst_minb() == 4) {                                                                       \
       auto kern = gatv2_bwd_dst_quad_kernel<V, L, Hh, kDDst, 4>;                                      \
       if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                    \
-      kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks);                                         \
+      kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks, quad_sort());                                         \
     } else {                                                                                          \
       auto kern = gatv2_bwd_dst_quad_kernel<V, L, Hh, kDDst, 3>;                                      \
       if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                    \
-      kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks);                                         \
+      kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks, quad_sort());                                         \
     }                                                                                                 \
   }
     SGB_QUAD_COMBOS(X)
@@ -811,7 +889,7 @@ bool quad_bwd_launch(const GatParams& p, float* grad_att, float* grad_bias, cuda
     const size_t smem = static_cast<size_t>(kQW) * kDSrc * (V + 1) * 512;                         \
     auto kern = gatv2_bwd_src_quad_kernel<V, L, Hh, kDSrc>;                                           \
     if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                      \
-    kern<<<blocks, kQThreads, smem, stream>>>(p, rpw, nchunks);                                       \
+    kern<<<blocks, kQThreads, smem, stream>>>(p, rpw, nchunks, quad_sort());                                       \
   }
     SGB_QUAD_COMBOS(X)
 #undef X

@@ -280,13 +280,14 @@ class ISTEncoder(torch.nn.Module):
 
     def _forward(self, x_dict, edge_index_dict, pos_dict, batch_dict):
         fused = (len(self.conv_layers) > 0 and self.conv_layers[0]._fusable(x_dict, edge_index_dict))
-        csr = None
+        csr, pending = None, None
         if fused:
+            # new graphs are built on a side stream while this stream runs the input stage (ops.csr_build_overlapped)
             need_t = torch.is_grad_enabled()
             N, M = x_dict["tx"].size(0), x_dict["bd"].size(0)
-            csr = {TT: ops.CSR_CACHE.get(edge_index_dict[TT], N, N, need_t),
-                   TB: ops.CSR_CACHE.get(edge_index_dict[TB], N, M, need_t)}
-        self._resolve_meta(list(csr.values()) if csr else [], batch_dict)
+            pending = ops.csr_build_overlapped([(edge_index_dict[TT], N, N), (edge_index_dict[TB], N, M)], need_t)
+            csr = {TT: pending.csrs[0], TB: pending.csrs[1]}
+        self._resolve_meta([], batch_dict)          # tile counts of the batch vectors (the input stage needs them)
         # The transcript input is cat(GELU(Embedding[gene]), GELU(pos MLP)): its first half takes only n_genes distinct
         # values, so the first layer consumes it in factored form (ids + a [n_genes, in] table) and that half of its
         # projections becomes a table lookup instead of half the GEMM (ops.SkipGATLayerFn).  SEGGER_B200_FACTOR=0 turns
@@ -305,6 +306,10 @@ class ISTEncoder(torch.nn.Module):
         tx_factor = None
         if factor:
             tx_factor = (x_dict["tx"].contiguous(), _GeluFn.apply(first_tx.weight))
+        if pending is not None:
+            pending.join()
+            pending.resolve()                       # status words of a new graph, read from the side stream's copy
+            self._resolve_meta(pending.csrs, None)  # (deferred / cached CSRs: the original path)
         # Graph convolutions with GATv2 + GELU (ist_encoder.py:323-325)
         if fused:
             for li, conv_layer in enumerate(self.conv_layers):
