@@ -73,6 +73,10 @@ SGB_API int sgb_csr_build(const void* edge_index, int idx_bytes, int64_t row_str
  * out = pre-activation (o + bias); out_act (optional) = GELU(out) (fuses ist_encoder.py:325).
  * out may be NULL when out_act is given (inference: only the activated output is written).
  * stat_max/stat_den [n_dst,H] are saved for the backward.  seed/p_drop/training drive the
+ * e_logit (optional, [E, H]): where the sub-warp kernels run (sgb_gatv2_quad_supported) the forward leaves the raw
+ * logit of every (edge, head) there, in dst-CSR order, and a backward that is handed the same buffer reads it back
+ * instead of re-evaluating att . leaky_relu(x_l[j] + x_r[i]) (4H bytes per edge against ~3 instructions per edge and
+ * feature).  Other kernel paths ignore it (sgb_gatv2_bwd then must be given NULL as well).
  * counter-based dropout keyed on (seed, original edge id, head).  seed_dev (or NULL) points to one device-resident
  * 64-bit word that is ADDED to seed when the kernel runs: a captured CUDA graph freezes by-value arguments, so a
  * replayed training step advances that word to draw a fresh mask (forward and backward read the same word).
@@ -83,6 +87,7 @@ SGB_API int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, int6
                   float p_drop, uint64_t seed, const uint64_t* seed_dev /*or NULL*/, int training,
                   float* out /*or NULL*/, int64_t ld_out,
                   float* out_act /*or NULL*/, int64_t ld_act, float* stat_max, float* stat_den,
+                  float* e_logit /*or NULL: [E, H] raw logits e_ij in dst-CSR order, for sgb_gatv2_bwd*/,
                   void* stream);
 
 /* 1 iff (H, C) is covered by the sub-warp-per-row kernels (needed for the one-source-per-edge form of sgb_gatv2_bwd:
@@ -110,7 +115,9 @@ SGB_API int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, int6
                   const int32_t* src_rowptr, const int32_t* src_dst, const int32_t* src_pos,
                   int64_t n_src, int64_t n_dst, int64_t E, int H, int C, float negative_slope,
                   float p_drop, uint64_t seed, const uint64_t* seed_dev /*or NULL*/, int training,
-                  const float* stat_max, const float* stat_den, float* grad_x_l, int64_t ld_gl, float* grad_x_r,
+                  const float* stat_max, const float* stat_den,
+                  const float* e_logit /*or NULL: what sgb_gatv2_fwd left there for the same graph and inputs*/,
+                  float* grad_x_l, int64_t ld_gl, float* grad_x_r,
                   int64_t ld_gr, float* grad_att, float* grad_bias /*or NULL*/, void* ws,
                   size_t ws_bytes, void* stream);
 

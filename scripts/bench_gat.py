@@ -64,16 +64,20 @@ def main():
             "tb": (y[:, 2 * F:], y_bd, csr_tb, gb, n_tx, n_cells, touched_tb),
         }.items():
             fb, bb = bench.gat_bytes(touched, nd, ns, csr.E, H, C)
-            out, act, smax, sden = ops.gatv2_fwd(xl, xr, att, bias, csr, H, C, 0.2, 0.2, True, 7, True)
+            # "quad_nolg": the backward recomputes the logits (A/B of the saved-logit dst pass)
+            want_lg = path in ("quad", "quad_nosort")
+            out, act, smax, sden, lg = ops.gatv2_fwd(xl, xr, att, bias, csr, H, C, 0.2, 0.2, True, 7, True, want_logits=True)
+            if not want_lg:
+                lg = None
             G = torch.zeros(ns, F, device=dev)
             Gr = torch.zeros(nd, F, device=dev)
             r = ops.gatv2_bwd(xl, xr, att, bias, out, gg, True, csr, H, C, 0.2, 0.2, True, 7, smax, sden,
-                              grad_x_l=G, grad_x_r=Gr)
+                              grad_x_l=G, grad_x_r=Gr, e_logit=lg)
             outs[(path, name)] = (act.clone(), G.clone(), Gr.clone(), r[2].clone(), r[3].clone())
-            tf = time_it(lambda: ops.gatv2_fwd(xl, xr, att, bias, csr, H, C, 0.2, 0.2, True, 7, True))
+            tf = time_it(lambda: ops.gatv2_fwd(xl, xr, att, bias, csr, H, C, 0.2, 0.2, True, 7, True, want_logits=want_lg))
             tfe = time_it(lambda: ops.gatv2_fwd(xl, xr, att, bias, csr, H, C, 0.2, 0.0, False, 7, True))
             tb = time_it(lambda: ops.gatv2_bwd(xl, xr, att, bias, out, gg, True, csr, H, C, 0.2, 0.2, True, 7, smax,
-                                               sden, grad_x_l=G, grad_x_r=Gr))
+                                               sden, grad_x_l=G, grad_x_r=Gr, e_logit=lg))
             res[f"{path}.{name}"] = {
                 "fwd_ms": tf * 1e3, "fwd_frac": fb / tf / 1e9 / hbm, "fwd_eval_ms": tfe * 1e3,
                 "bwd_ms": tb * 1e3, "bwd_frac": bb / tb / 1e9 / hbm, "E": csr.E}

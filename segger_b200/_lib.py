@@ -34,13 +34,13 @@ _PROTOS = {
     "sgb_csr_build": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp, c_sz, c_vp]),
     "sgb_gatv2_fwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int,
-                              c_int, c_f32, c_f32, c_u64, c_vp, c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+                              c_int, c_f32, c_f32, c_u64, c_vp, c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "sgb_gatv2_alpha": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int,
                                 c_f32, c_vp, c_vp, c_vp, c_vp]),
     "sgb_gatv2_bwd_workspace_bytes": (c_sz, [c_i64, c_i64, c_int, c_int]),
     "sgb_gatv2_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp,
                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_f32,
-                              c_f32, c_u64, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp,
+                              c_f32, c_u64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp,
                               c_sz, c_vp]),
     "sgb_dropout_mask": (c_int, [c_u64, c_i64, c_int, c_f32, c_vp, c_vp]),
     "sgb_linear_workspace_bytes": (c_sz, [c_i64, c_i64]),

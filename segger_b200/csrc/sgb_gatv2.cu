@@ -690,7 +690,7 @@ extern "C" int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, i
                              const float* bias, const int32_t* dst_rowptr, const int32_t* dst_col,
                              const int32_t* dst_eid, int64_t n_dst, int64_t E, int H, int C, float negative_slope,
                              float p_drop, uint64_t seed, const uint64_t* seed_dev, int training, float* out, int64_t ld_out, float* out_act,
-                             int64_t ld_act, float* stat_max, float* stat_den, void* stream_) {
+                             int64_t ld_act, float* stat_max, float* stat_den, float* e_logit, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = validate_common("gatv2_fwd", x_l, x_r, att, n_dst, E, H, C);
   if (rc != SGB_OK) return rc;
@@ -709,7 +709,10 @@ extern "C" int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, i
   p.slope = negative_slope; p.training = train ? 1 : 0; p.drop_thr = drop_threshold(p_drop);
   p.keep_scale = 1.0f / (1.0f - p_drop); p.seed = seed; p.seed_dev = seed_dev;
   p.out = out; p.out_act = out_act; p.ld_out = ld_out; p.ld_act = ld_act; p.stat_max = stat_max; p.stat_den = stat_den;
+  p.e_logit = e_logit;
   if (aligned && !legacy_path() && quad_fwd_launch(p, stream)) return check_launch("gatv2_fwd(quad)");
+  SGB_REQUIRE(!e_logit, SGB_ERR_ARG, "gatv2_fwd: e_logit is written by the sub-warp kernels only (sgb_gatv2_quad_supported, "
+              "16-byte aligned operands)");
   if (sh.path == Path::kVec) {
     const unsigned blocks = static_cast<unsigned>(ceil_div(n_dst, 8));
 #define X(V, Cv) if (sh.vec == V && sh.cv == Cv) gatv2_fwd_vec_kernel<V, Cv><<<blocks, 256, 0, stream>>>(p);
@@ -781,7 +784,7 @@ extern "C" int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, i
                              const int32_t* dst_eid, const int32_t* src_rowptr, const int32_t* src_dst,
                              const int32_t* src_pos, int64_t n_src, int64_t n_dst, int64_t E, int H, int C,
                              float negative_slope, float p_drop, uint64_t seed, const uint64_t* seed_dev, int training, const float* stat_max,
-                             const float* stat_den, float* grad_x_l, int64_t ld_gl, float* grad_x_r, int64_t ld_gr,
+                             const float* stat_den, const float* e_logit, float* grad_x_l, int64_t ld_gl, float* grad_x_r, int64_t ld_gr,
                              float* grad_att, float* grad_bias, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = validate_common("gatv2_bwd", x_l, x_r, att, n_dst, E, H, C);
@@ -819,9 +822,11 @@ extern "C" int sgb_gatv2_bwd(const float* x_l, int64_t ld_l, const float* x_r, i
   p.partial = reinterpret_cast<float*>(w + bwd_edge_region(E, H, C));
   p.grad_x_l = grad_x_l; p.grad_x_r = grad_x_r; p.ld_gl = ld_gl; p.ld_gr = ld_gr;
   p.t_rowptr = src_rowptr; p.t_dst = src_dst; p.t_pos = src_pos;
+  p.e_logit = const_cast<float*>(e_logit);
 
   if (n_dst > 0 && aligned && !legacy_path() && quad_bwd_launch(p, grad_att, grad_bias, stream))
     return check_launch("gatv2_bwd(quad)");
+  SGB_REQUIRE(!e_logit || n_dst == 0, SGB_ERR_ARG, "gatv2_bwd: e_logit is read by the sub-warp kernels only");
   SGB_REQUIRE(!direct_src, SGB_ERR_ARG, "gatv2_bwd: the one-source-per-edge form (src_rowptr == NULL) needs a shape covered by "
               "the sub-warp kernels (sgb_gatv2_quad_supported)");
   if (n_dst == 0) {

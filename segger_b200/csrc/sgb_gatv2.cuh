@@ -36,6 +36,8 @@ struct GatParams {
   float *out, *out_act;
   int64_t ld_out, ld_act;
   float *stat_max, *stat_den;
+  float* e_logit;            // optional [E, H] raw attention logits in dst-CSR order: written by the sub-warp forward,
+                             // read by the sub-warp backward (which then skips the att . lrelu(z) recomputation)
   // backward
   const float* grad_out;
   int64_t ld_g;

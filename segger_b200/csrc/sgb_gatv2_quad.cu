@@ -317,6 +317,12 @@ __global__ void __launch_bounds__(kQThreads) gatv2_fwd_quad_kernel(const GatPara
         }
         const int e = eid_next;
         if (training && k + 1 < c_deg) eid_next = __ldg(p.eid + c_beg + k + 1);
+        if (p.e_logit != nullptr && act && s < H) {   // raw logits in dst-CSR order: the backward skips att . lrelu(z)
+          float lv = lg[0];
+#pragma unroll
+          for (int h = 1; h < H; ++h) lv = s == h ? lg[h] : lv;
+          p.e_logit[static_cast<int64_t>(c_beg + k) * H + s] = lv;
+        }
 
         if (k == 0) {
 #pragma unroll
@@ -571,6 +577,237 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
       if (rvalid) {
 #pragma unroll
         for (int t = 0; t < V; ++t) st4(p.grad_x_r + row * p.ld_gr + (t * LPR + s) * 4, gr[t]);
+      }
+    }
+  }
+
+  // ---- CTA-level ordered reduction -> partial[blockIdx][2][F] ------------------------------------
+  float4 gb[V];
+#pragma unroll
+  for (int t = 0; t < V; ++t) {
+    gb[t] = lds4(gb_addr + t * 512);
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {   // sum over the G lane groups (same columns, different rows)
+      gatt[t].x += __shfl_xor_sync(kFull, gatt[t].x, o); gatt[t].y += __shfl_xor_sync(kFull, gatt[t].y, o);
+      gatt[t].z += __shfl_xor_sync(kFull, gatt[t].z, o); gatt[t].w += __shfl_xor_sync(kFull, gatt[t].w, o);
+      gb[t].x += __shfl_xor_sync(kFull, gb[t].x, o); gb[t].y += __shfl_xor_sync(kFull, gb[t].y, o);
+      gb[t].z += __shfl_xor_sync(kFull, gb[t].z, o); gb[t].w += __shfl_xor_sync(kFull, gb[t].w, o);
+    }
+  }
+  __syncthreads();   // every warp is done with its ring; reuse the start of shared memory
+  float4* red = q_smem;   // [2][kQW][F4]
+  if (g == 0) {
+#pragma unroll
+    for (int t = 0; t < V; ++t) {
+      red[(0 * kQW + warp) * F4 + t * LPR + s] = gatt[t];
+      red[(1 * kQW + warp) * F4 + t * LPR + s] = gb[t];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * F4; i += kQThreads) {
+    const int which = i / F4, f = i % F4;
+    float4 tsum = red[(which * kQW + 0) * F4 + f];
+#pragma unroll
+    for (int w = 1; w < kQW; ++w) tsum = add4(tsum, red[(which * kQW + w) * F4 + f]);
+    st4(p.partial + (static_cast<int64_t>(blockIdx.x) * 2 + which) * (F4 * 4) + f * 4, tsum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dst pass, saved-logit form (p.e_logit != NULL: the forward left the raw logit of every (edge, head) in dst-CSR order).
+// Same results as the kernel above up to rounding; per edge and element it no longer evaluates
+// lrelu(z) and att . lrelu(z) (the logit is read back, 4H bytes per edge) and it keeps neither `att` nor a copy of z in
+// registers:
+//   dL/dz_e = delta_e * lrelu'(z_e) (.) att            sel_e := delta_e * lrelu'(z_e)   (delta or delta * slope per element)
+//   grad_x_r[i] = att (.) sum_e sel_e                   (att applied once per row, from shared memory)
+//   grad_att   += sel_e (.) z_e                         (lrelu(z) = lrelu'(z) z)
+// Two sweeps over the staged source row per edge (g . x first: delta needs it), both from the ring slot.
+// ------------------------------------------------------------------------------------------------
+template <int V, int LPR, int H, int D, int MINB>
+__global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_lg_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks, const int sort) {
+  const uint64_t seed_eff = p.training ? gat_seed(p) : 0;
+  constexpr int G = 32 / LPR, VPH = V / H, F4 = V * LPR;
+  constexpr int SH = rec_scalars(H), RSB = rec_bytes(H, LPR);
+  extern __shared__ float4 q_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = lane % LPR, g = lane / LPR;
+  using P = Pipe<LPR, D, V, 3>;
+  P pipe;
+  // per warp: ring D*V*512 B, V*512 B of grad_bias accumulators, V*512 B holding this lane's slice of att (lane-private)
+  float4* wbase = q_smem + warp * ((D + 2) * V * 32);
+  pipe.ring = static_cast<uint32_t>(__cvta_generic_to_shared(wbase + lane));
+  const uint32_t gb_addr = pipe.ring + D * V * 512;
+  const uint32_t att_addr = gb_addr + V * 512;
+#pragma unroll
+  for (int i = 0; i < (D + 1) * V; ++i) sts4(pipe.ring + i * 512, make_float4(0.f, 0.f, 0.f, 0.f));
+  float4 gatt[V];
+#pragma unroll
+  for (int t = 0; t < V; ++t) {
+    sts4(att_addr + t * 512, ldg4(p.att + (t * LPR + s) * 4));
+    gatt[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float slope = p.slope;
+  const bool training = p.training != 0;
+  const bool direct_src = p.t_rowptr == nullptr;   // one source per edge: this pass also writes grad_x_l
+
+  for (int64_t chunk = static_cast<int64_t>(blockIdx.x) * kQW + warp; chunk < nchunks;
+       chunk += static_cast<int64_t>(gridDim.x) * kQW) {
+    const int64_t wrow0 = chunk * rpw;
+    const int nrows = static_cast<int>(min(static_cast<int64_t>(rpw), p.n_dst - wrow0));
+    const int nq = (nrows + G - 1) / G;
+    int rp_b, rp_d, rp_o;
+    chunk_rows<LPR>(p.rowptr, wrow0, nrows, p.n_dst, lane, sort != 0, rp_b, rp_d, rp_o);
+    pipe.start(nq, rp_b, rp_d, rp_o, g);
+
+    const float* nsrc = nullptr;
+    bool nact = false;
+    auto gen = [&]() {
+      nact = false;
+      if (pipe.pq < pipe.nq) {
+        if (pipe.pk < 3) {
+          const int64_t row = wrow0 + pipe.p_off;
+          nact = row < p.n_dst;
+          nsrc = pipe.pk == 0 ? p.x_r + row * p.ld_r : (pipe.pk == 1 ? p.grad_out + row * p.ld_g : p.out + row * p.ld_out);
+        } else {
+          const int k = pipe.pk - 3;
+          if (k < pipe.p_deg) {
+            nact = true;
+            nsrc = p.x_l + static_cast<int64_t>(__ldg(p.col + pipe.p_beg + k)) * p.ld_l;
+          }
+        }
+        pipe.advance();
+      }
+    };
+    auto issue = [&]() {
+      if (nact) {
+#pragma unroll
+        for (int t = 0; t < V; ++t) cp_async16(pipe.issue_addr(t), nsrc + (t * LPR + s) * 4);
+      }
+      pipe.committed();
+    };
+    gen();
+#pragma unroll
+    for (int i = 0; i < D - 1; ++i) { issue(); gen(); }
+
+    for (int q = 0; q < nq; ++q) {
+      int c_beg, c_deg, c_off, c_mx;
+      quad_info<LPR>(rp_b, rp_d, rp_o, q, g, c_beg, c_deg, c_off, c_mx);
+      const int64_t row = wrow0 + c_off;
+      const bool rvalid = row < p.n_dst;
+      float m[H], inv[H], lgn[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        m[h] = rvalid ? __ldg(p.stat_max + row * H + h) : 0.f;
+        inv[h] = rvalid ? __ldg(p.stat_den + row * H + h) : 1.f;
+        lgn[h] = c_deg > 0 ? __ldg(p.e_logit + static_cast<int64_t>(c_beg) * H + h) : 0.f;
+      }
+      int eid_next = (training && c_deg > 0) ? __ldg(p.eid + c_beg) : 0;
+
+      float4 r[V], g4[V], sacc[V];
+      issue(); gen(); cp_wait<D - 1>();
+#pragma unroll
+      for (int t = 0; t < V; ++t) r[t] = lds4(pipe.read_addr(t));
+      pipe.consumed();
+      issue(); gen(); cp_wait<D - 1>();
+#pragma unroll
+      for (int t = 0; t < V; ++t) g4[t] = lds4(pipe.read_addr(t));
+      pipe.consumed();
+      issue(); gen(); cp_wait<D - 1>();
+      float cdot[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) cdot[h] = 0.f;
+#pragma unroll
+      for (int t = 0; t < V; ++t) {
+        const int off = (t * LPR + s) * 4;
+        const float4 o4 = lds4(pipe.read_addr(t));
+        if (!rvalid) g4[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.gelu_fused) {
+          g4[t].x *= gelu_erf_grad(o4.x); g4[t].y *= gelu_erf_grad(o4.y);
+          g4[t].z *= gelu_erf_grad(o4.z); g4[t].w *= gelu_erf_grad(o4.w);
+          if (rvalid) st4(p.g_buf + row * p.ld_g + off, g4[t]);
+        }
+        const float4 b4 = p.bias ? ldg4(p.bias + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        cdot[t / VPH] += dot4(g4[t], sub4(o4, b4));
+        const uint32_t ga = gb_addr + t * 512;
+        sts4(ga, add4(lds4(ga), g4[t]));
+        sacc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      pipe.consumed();
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        cdot[h] = group_sum<LPR>(cdot[h]);
+        inv[h] = 1.0f / inv[h];
+      }
+
+      for (int k = 0; k < c_mx; ++k) {
+        issue(); gen(); cp_wait<D - 1>();
+        const bool act = k < c_deg;
+        float dd[H], lg[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {           // sweep 1: g_i . x_l[j] per head
+          float2 pd = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < VPH; ++u) {
+            const int t = h * VPH + u;
+            dot4p(pd, g4[t], lds4(pipe.read_addr(t)));
+          }
+          dd[h] = group_sum<LPR>(pd.x + pd.y);
+          lg[h] = lgn[h];
+        }
+        if (k + 1 < c_deg) {
+#pragma unroll
+          for (int h = 0; h < H; ++h) lgn[h] = __ldg(p.e_logit + static_cast<int64_t>(c_beg + k + 1) * H + h);
+        }
+        const int e = eid_next;
+        if (training && k + 1 < c_deg) eid_next = __ldg(p.eid + c_beg + k + 1);
+        const int jcol = (direct_src && act) ? __ldg(p.col + c_beg + k) : 0;
+        uint32_t eh = 0;
+        if (training) eh = rng_edge(seed_eff, static_cast<uint32_t>(e));
+        float delta[H], alk[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float alpha = act ? __expf(lg[h] - m[h]) * inv[h] : 0.f;
+          float ks = 1.0f;
+          if (training) ks = rng_head(eh, seed_eff, h) >= p.drop_thr ? p.keep_scale : 0.f;
+          delta[h] = alpha * (dd[h] * ks - cdot[h]);
+          alk[h] = alpha * ks;
+        }
+        char* rec_ptr = reinterpret_cast<char*>(p.e_delta) + static_cast<int64_t>(c_beg + k) * RSB;
+        if (act && !direct_src && s < SH / 4) {
+          float rec[SH];
+#pragma unroll
+          for (int i = 0; i < SH; ++i) rec[i] = i < H ? delta[i] : (i < 2 * H ? alk[i - H] : 0.f);
+          float4 out4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < SH / 4; ++i)
+            if (s == i) out4 = make_float4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
+          st4(reinterpret_cast<float*>(rec_ptr) + s * 4, out4);
+        }
+        uint32_t zbits = 0;
+#pragma unroll
+        for (int t = 0; t < V; ++t) {           // sweep 2: z = x_l[j] + x_r[i], sel = delta * lrelu'(z)
+          const float d = delta[t / VPH], ds = d * slope;
+          const float4 zz = add4p(lds4(pipe.read_addr(t)), r[t]);
+          const bool px = zz.x > 0.f, py = zz.y > 0.f, pz = zz.z > 0.f, pw = zz.w > 0.f;
+          const float4 sel = make_float4(px ? d : ds, py ? d : ds, pz ? d : ds, pw ? d : ds);
+          sacc[t] = add4p(sacc[t], sel);
+          fma4v(gatt[t], sel, zz);
+          if (!direct_src) {
+            zbits |= (px ? 1u : 0u) << (4 * t) | (py ? 2u : 0u) << (4 * t) | (pz ? 4u : 0u) << (4 * t) | (pw ? 8u : 0u) << (4 * t);
+          } else if (act) {                     // one source per edge: grad_x_l[j] = dL/dz_e + alpha'_e g_i
+            const float4 dz = mul4p(sel, lds4(att_addr + t * 512));
+            const float ak = alk[t / VPH];
+            st4(p.grad_x_l + static_cast<int64_t>(jcol) * p.ld_gl + (t * LPR + s) * 4,
+                make_float4(fmaf(ak, g4[t].x, dz.x), fmaf(ak, g4[t].y, dz.y), fmaf(ak, g4[t].z, dz.z), fmaf(ak, g4[t].w, dz.w)));
+          }
+        }
+        pipe.consumed();
+        if (act && !direct_src) *reinterpret_cast<uint16_t*>(rec_ptr + SH * 4 + 2 * s) = static_cast<uint16_t>(zbits);
+      }
+      if (rvalid) {
+#pragma unroll
+        for (int t = 0; t < V; ++t)
+          st4(p.grad_x_r + row * p.ld_gr + (t * LPR + s) * 4, mul4p(lds4(att_addr + t * 512), sacc[t]));
       }
     }
   }
@@ -863,7 +1100,18 @@ bool quad_bwd_launch(const GatParams& p, float* grad_att, float* grad_bias, cuda
     const int64_t nchunks = ceil_div(p.n_dst, rpw);
     const int nb = quad_dst_blocks(p.n_dst, rpw);
 #define X(V, L, Hh)                                                                                   \
-  if (qs.v == V && qs.lpr == L && p.H == Hh) {                                                        \
+  if (qs.v == V && qs.lpr == L && p.H == Hh && p.e_logit != nullptr) {                                \
+    const size_t smem = static_cast<size_t>(kQW) * (kDDst + 2) * V * 512;                             \
+    if (quad_dst_minb() == 4) {                                                                       \
+      auto kern = gatv2_bwd_dst_lg_quad_kernel<V, L, Hh, kDDst, 4>;                                   \
+      if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                    \
+      kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks, quad_sort());                            \
+    } else {                                                                                          \
+      auto kern = gatv2_bwd_dst_lg_quad_kernel<V, L, Hh, kDDst, 3>;                                   \
+      if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                    \
+      kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks, quad_sort());                            \
+    }                                                                                                 \
+  } else if (qs.v == V && qs.lpr == L && p.H == Hh) {                                                 \
     const size_t smem = static_cast<size_t>(kQW) * (kDDst + 1) * V * 512;                             \
     if (quad_dst_minb() == 4) {                                                                       \
       auto kern = gatv2_bwd_dst_quad_kernel<V, L, Hh, kDDst, 4>;                                      \

@@ -278,14 +278,23 @@ class ISTEncoder(torch.nn.Module):
             set_num_graphs(b, v + 1)
         ops._apply_status(todo, [vals[2 * i:2 * i + 2] for i in range(len(todo))])
 
+    def _build_csrs(self, x_dict, edge_index_dict, mark):
+        need_t = torch.is_grad_enabled()
+        N, M = x_dict["tx"].size(0), x_dict["bd"].size(0)
+        pending = ops.csr_build_overlapped([(edge_index_dict[TT], N, N), (edge_index_dict[TB], N, M)], need_t, after=mark)
+        pending.join()
+        pending.resolve()                       # status words of a new graph, read from the side stream's copy
+        self._resolve_meta(pending.csrs, None)  # (deferred / cached CSRs: the original path)
+        return pending
+
     def _forward(self, x_dict, edge_index_dict, pos_dict, batch_dict):
         fused = (len(self.conv_layers) > 0 and self.conv_layers[0]._fusable(x_dict, edge_index_dict))
+        # new graphs are built on a side stream while this stream runs the input stage (ops.csr_build_overlapped):
+        # the input stage is enqueued first, the builds wait for the mark recorded here
+        mark = ops.csr_overlap_mark(edge_index_dict[TT]) if fused else None
         csr, pending = None, None
-        if fused:
-            # new graphs are built on a side stream while this stream runs the input stage (ops.csr_build_overlapped)
-            need_t = torch.is_grad_enabled()
-            N, M = x_dict["tx"].size(0), x_dict["bd"].size(0)
-            pending = ops.csr_build_overlapped([(edge_index_dict[TT], N, N), (edge_index_dict[TB], N, M)], need_t)
+        if fused and mark is None:                  # no overlap: build (and validate) first, as a plain caller would
+            pending = self._build_csrs(x_dict, edge_index_dict, None)
             csr = {TT: pending.csrs[0], TB: pending.csrs[1]}
         self._resolve_meta([], batch_dict)          # tile counts of the batch vectors (the input stage needs them)
         # The transcript input is cat(GELU(Embedding[gene]), GELU(pos MLP)): its first half takes only n_genes distinct
@@ -306,10 +315,9 @@ class ISTEncoder(torch.nn.Module):
         tx_factor = None
         if factor:
             tx_factor = (x_dict["tx"].contiguous(), _GeluFn.apply(first_tx.weight))
-        if pending is not None:
-            pending.join()
-            pending.resolve()                       # status words of a new graph, read from the side stream's copy
-            self._resolve_meta(pending.csrs, None)  # (deferred / cached CSRs: the original path)
+        if fused and mark is not None:
+            pending = self._build_csrs(x_dict, edge_index_dict, mark)
+            csr = {TT: pending.csrs[0], TB: pending.csrs[1]}
         # Graph convolutions with GATv2 + GELU (ist_encoder.py:323-325)
         if fused:
             for li, conv_layer in enumerate(self.conv_layers):

@@ -257,25 +257,39 @@ class CsrJoin:
             _apply_status([c for c, _ in pairs], [f for _, f in pairs])
 
 
-def csr_build_overlapped(specs, transpose: bool) -> CsrJoin:
+def csr_overlap_mark(edge_index: Tensor):
+    """Event on the current stream marking "the edge lists are ready" -- recorded BEFORE the caller enqueues the work the
+    CSR builds are to overlap with.  None when the builds will not use the side stream."""
+    if os.environ.get("SEGGER_B200_CSR_OVERLAP", "1") == "0" or torch.cuda.is_current_stream_capturing():
+        return None
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(edge_index.device))
+    return ev
+
+
+def csr_build_overlapped(specs, transpose: bool, after=None) -> CsrJoin:
     """``specs`` = [(edge_index, n_src, n_dst), ...] -> CsrJoin with ``.csrs`` in the same order.
 
     A CSR build is ~55 small dependent launches per edge type (radix passes, scans, checks): ~1.2 ms of a 16 ms
     training step at 1M transcripts, almost all of it launch latency.  Nothing before the first graph convolution needs
     the CSRs, so new graphs are built on a side stream while the caller's stream runs the input stage (embedding,
-    positional MLP); ``join()`` orders the caller's stream behind them.  Cache hits (static graphs, CUDA-graph
-    capture) and ``SEGGER_B200_CSR_OVERLAP=0`` stay on the caller's stream."""
+    positional MLP); ``join()`` orders the caller's stream behind them.  The caller enqueues the input stage FIRST and
+    passes the event it recorded before it (``after`` = ``csr_overlap_mark``): one host thread issues every launch, so
+    the few long input-stage kernels must already be queued when the ~110 short build launches are issued.  Cache hits
+    (static graphs, CUDA-graph capture) and ``SEGGER_B200_CSR_OVERLAP=0`` stay on the caller's stream."""
     dev = specs[0][0].device
     miss = [not CSR_CACHE.has(ei, ns, nd, transpose) for ei, ns, nd in specs]
-    side_ok = (any(miss) and os.environ.get("SEGGER_B200_CSR_OVERLAP", "1") != "0"
-               and not torch.cuda.is_current_stream_capturing())
+    side_ok = any(miss) and after is not None
     if not side_ok:
         return CsrJoin([CSR_CACHE.get(ei, ns, nd, transpose) for ei, ns, nd in specs])
     main = torch.cuda.current_stream(dev)
     side = _CSR_STREAMS.get(dev)
     if side is None:
         side = _CSR_STREAMS[dev] = torch.cuda.Stream(dev)
-    side.wait_stream(main)          # inputs are ready; memory the allocator recycles for the build is no longer read
+    if after is not None:
+        side.wait_event(after)      # the edge lists are ready (recorded before the work this build overlaps with)
+    else:
+        side.wait_stream(main)
     status_host, todo = None, []
     with torch.cuda.stream(side):
         csrs = [CSR_CACHE.get(ei, ns, nd, transpose) for ei, ns, nd in specs]
@@ -512,11 +526,22 @@ def act_fwd(x: Tensor, act: int, y: Optional[Tensor] = None) -> Tensor:
     return y
 
 
+def _quad_path(H: int, C: int, slope: float, *tensors) -> bool:
+    """True iff sgb_gatv2_fwd / sgb_gatv2_bwd will run the sub-warp kernels on these operands (the library's own rule:
+    shape covered, 0 <= slope <= 1, 16-byte aligned pointers, leading dimensions a multiple of 4 floats)."""
+    return (bool(_lib.load().sgb_gatv2_quad_supported(H, C)) and 0.0 <= slope <= 1.0
+            and os.environ.get("SEGGER_B200_GAT") != "legacy"
+            and all(t is None or (t.data_ptr() % 16 == 0 and (t.dim() < 2 or _ld(t) % 4 == 0)) for t in tensors))
+
+
 def gatv2_fwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], csr: EdgeCSR, H: int, C: int,
               slope: float, p_drop: float, training: bool, seed: int, want_act: bool,
-              out: Optional[Tensor] = None, out_act: Optional[Tensor] = None, want_pre: bool = True):
+              out: Optional[Tensor] = None, out_act: Optional[Tensor] = None, want_pre: bool = True,
+              want_logits: Optional[bool] = False):
     """-> (out_pre|None, out_act|None, stat_max, stat_den).  ``want_pre=False`` (with ``want_act``) writes only
-    the activated output: the pre-activation is needed by the backward alone."""
+    the activated output: the pre-activation is needed by the backward alone.  ``want_logits=True`` appends a fifth
+    element: the raw attention logits [E, H] in dst-CSR order for ``gatv2_bwd(e_logit=...)`` (None where the sub-warp
+    kernels do not apply; ``SEGGER_B200_GAT_LOGITS=0`` turns the saved-logit backward off)."""
     x_l, x_r = _rowmajor(x_l), _rowmajor(x_r)
     F = H * C
     dev = x_r.device
@@ -534,20 +559,27 @@ def gatv2_fwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], csr
     sden = torch.empty(n_dst, H, dtype=torch.float32, device=dev)
     att, bias = _vec(att.reshape(-1)), _vec(bias)
     seed_val, seed_dev = _split_seed(seed)
+    e_logit = None
+    if (want_logits and csr.E > 0 and n_dst > 0 and os.environ.get("SEGGER_B200_GAT_LOGITS", "1") != "0"
+            and _quad_path(H, C, slope, x_l, x_r, att, bias, out, out_act)):
+        e_logit = torch.empty(csr.E, H, dtype=torch.float32, device=dev)
     check(_lib.load().sgb_gatv2_fwd(ptr(x_l), _ld(x_l), ptr(x_r), _ld(x_r), ptr(att), ptr(bias), ptr(csr.rowptr),
                                     ptr(csr.col), ptr(csr.eid), n_dst, csr.E, H, C, slope, p_drop, seed_val,
                                     ptr(seed_dev), int(training), ptr(out), _ld(out) if out is not None else 0, ptr(out_act),
-                                    _ld(out_act) if out_act is not None else 0, ptr(smax), ptr(sden),
+                                    _ld(out_act) if out_act is not None else 0, ptr(smax), ptr(sden), ptr(e_logit),
                                     stream_ptr(dev)), "gatv2_fwd")
     _count(1)
+    if want_logits is not False:       # (None: "fifth element wanted, no logits" -- callers that always unpack five)
+        return out, out_act, smax, sden, e_logit
     return out, out_act, smax, sden
 
 
 def gatv2_bwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], out_pre: Tensor, grad_out: Tensor,
               gelu_fused: bool, csr: EdgeCSR, H: int, C: int, slope: float, p_drop: float, training: bool,
               seed: int, smax: Tensor, sden: Tensor, grad_x_l: Optional[Tensor] = None,
-              grad_x_r: Optional[Tensor] = None):
-    """-> (grad_x_l, grad_x_r, grad_att [H*C], grad_bias [H*C])."""
+              grad_x_r: Optional[Tensor] = None, e_logit: Optional[Tensor] = None):
+    """-> (grad_x_l, grad_x_r, grad_att [H*C], grad_bias [H*C]).  ``e_logit``: what ``gatv2_fwd(want_logits=True)``
+    returned for the same inputs (the dst pass then reads the logits back instead of recomputing them)."""
     if csr.t_rowptr is None:
         raise RuntimeError("gatv2_bwd needs the transposed CSR (build_csr(..., transpose=True))")
     x_l, x_r, out_pre, grad_out = _rowmajor(x_l), _rowmajor(x_r), _rowmajor(out_pre), _rowmajor(grad_out)
@@ -572,10 +604,14 @@ def gatv2_bwd(x_l: Tensor, x_r: Tensor, att: Tensor, bias: Optional[Tensor], out
               and all(t.data_ptr() % 16 == 0 and _ld(t) % 4 == 0 for t in (x_l, x_r, out_pre, grad_out, grad_x_l, grad_x_r)))
     t_rowptr, t_dst, t_pos = (None, None, None) if direct else (csr.t_rowptr, csr.t_dst, csr.t_pos)
     seed_val, seed_dev = _split_seed(seed)
+    if e_logit is not None and (n_dst == 0 or tuple(e_logit.shape) != (csr.E, H) or not e_logit.is_contiguous() or not
+                                _quad_path(H, C, slope, x_l, x_r, att, bias, out_pre, grad_out, g_buf, grad_x_l, grad_x_r)):
+        e_logit = None
     check(lib.sgb_gatv2_bwd(ptr(x_l), _ld(x_l), ptr(x_r), _ld(x_r), ptr(att), ptr(bias), ptr(out_pre), _ld(out_pre),
                             ptr(grad_out), _ld(grad_out), int(gelu_fused), ptr(g_buf), ptr(csr.rowptr), ptr(csr.col),
                             ptr(csr.eid), ptr(t_rowptr), ptr(t_dst), ptr(t_pos), n_src, n_dst, csr.E,
-                            H, C, slope, p_drop, seed_val, ptr(seed_dev), int(training), ptr(smax), ptr(sden), ptr(grad_x_l),
+                            H, C, slope, p_drop, seed_val, ptr(seed_dev), int(training), ptr(smax), ptr(sden), ptr(e_logit),
+                            ptr(grad_x_l),
                             _ld(grad_x_l), ptr(grad_x_r), _ld(grad_x_r), ptr(g_att), ptr(g_bias), ptr(ws),
                             ws.numel(), stream_ptr(dev)), "gatv2_bwd")
     _count(3)
@@ -649,19 +685,19 @@ class GATv2AggregateFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_l, x_r, att, bias, csr, H, C, slope, p_drop, training, seed, apply_gelu):
         require_cuda(x_l, x_r, att, bias)
-        out, out_act, smax, sden = gatv2_fwd(x_l, x_r, att, bias, csr, H, C, slope, p_drop, training, seed,
-                                             apply_gelu)
+        out, out_act, smax, sden, lg = gatv2_fwd(x_l, x_r, att, bias, csr, H, C, slope, p_drop, training, seed,
+                                                 apply_gelu, want_logits=True if any(ctx.needs_input_grad[:4]) else None)
         ctx.csr, ctx.cfg = csr, (H, C, slope, p_drop, training, seed, apply_gelu)
         ctx.att_shape = att.shape
-        ctx.save_for_backward(x_l, x_r, att, bias, out, smax, sden)
+        ctx.save_for_backward(x_l, x_r, att, bias, out, smax, sden, lg)
         return out_act if apply_gelu else out
 
     @staticmethod
     def backward(ctx, dout):
-        x_l, x_r, att, bias, out, smax, sden = ctx.saved_tensors
+        x_l, x_r, att, bias, out, smax, sden, lg = ctx.saved_tensors
         H, C, slope, p_drop, training, seed, apply_gelu = ctx.cfg
         gl, gr, ga, gb = gatv2_bwd(x_l, x_r, att, bias, out, dout.contiguous(), apply_gelu, ctx.csr, H, C, slope,
-                                   p_drop, training, seed, smax, sden)
+                                   p_drop, training, seed, smax, sden, e_logit=lg)
         return gl, gr, ga.view(ctx.att_shape), gb, None, None, None, None, None, None, None, None
 
 
@@ -733,17 +769,20 @@ class SkipGATLayerFn(torch.autograd.Function):
             y_tb = y_tx[:, 2 * F:]
         y_bd, _ = linear_fwd(x_bd, wr_tb, br_tb, exact=exact)
         want_pre = bool(exact) or not apply_gelu      # `exact` = autograd is recording: the backward needs v
-        v_tx, h_tx, smax_tt, sden_tt = gatv2_fwd(y_tx[:, :F], y_tx[:, F:2 * F], att_tt, bias_tt, csr_tt, H, C,
-                                                 slope, p_drop, training, seed_tt, apply_gelu, want_pre=want_pre)
-        v_bd, h_bd, smax_tb, sden_tb = gatv2_fwd(y_tb, y_bd, att_tb, bias_tb, csr_tb_run, H, C, slope,
-                                                 p_drop, training, seed_tb, apply_gelu, want_pre=want_pre)
+        # (`exact` = autograd is recording: the sub-warp forward then also leaves the raw logits for the backward)
+        v_tx, h_tx, smax_tt, sden_tt, lg_tt = gatv2_fwd(y_tx[:, :F], y_tx[:, F:2 * F], att_tt, bias_tt, csr_tt, H, C,
+                                                        slope, p_drop, training, seed_tt, apply_gelu, want_pre=want_pre,
+                                                        want_logits=True if exact else None)
+        v_bd, h_bd, smax_tb, sden_tb, lg_tb = gatv2_fwd(y_tb, y_bd, att_tb, bias_tb, csr_tb_run, H, C, slope,
+                                                        p_drop, training, seed_tb, apply_gelu, want_pre=want_pre,
+                                                        want_logits=True if exact else None)
         ctx.csr = (csr_tt, csr_tb, csr_tb_run)
         ctx.cfg = (H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu, subset)
         ctx.att_shape = att_tt.shape
         ctx.D1 = D1
         ctx.save_for_backward(x_tx, x_bd, w_cat, wr_tb, y_tx, y_bd, v_tx, v_bd, att_tt, bias_tt, att_tb, bias_tb,
                               smax_tt, sden_tt, smax_tb, sden_tb, xs, y_tb if subset else None, wl_tb if subset else None,
-                              tx_ids, tx_table, ids_s)
+                              tx_ids, tx_table, ids_s, lg_tt, lg_tb)
         if apply_gelu:
             return h_tx, h_bd
         return v_tx, v_bd
@@ -751,7 +790,7 @@ class SkipGATLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_tx, d_bd):
         (x_tx, x_bd, w_cat, wr_tb, y_tx, y_bd, v_tx, v_bd, att_tt, bias_tt, att_tb, bias_tb, smax_tt, sden_tt,
-         smax_tb, sden_tb, xs, y_tb, wl_tb, tx_ids, tx_table, ids_s) = ctx.saved_tensors
+         smax_tb, sden_tb, xs, y_tb, wl_tb, tx_ids, tx_table, ids_s, lg_tt, lg_tb) = ctx.saved_tensors
         D1 = ctx.D1
         csr_tt, csr_tb, csr_tb_run = ctx.csr
         H, C, slope, p_drop, training, seed_tt, seed_tb, apply_gelu, subset = ctx.cfg
@@ -770,10 +809,10 @@ class SkipGATLayerFn(torch.autograd.Function):
             y_tb, g_tb = y_tx[:, 2 * F:], g_tx[:, 2 * F:]
         _, _, ga_tt, gb_tt = gatv2_bwd(y_tx[:, :F], y_tx[:, F:2 * F], att_tt, bias_tt, v_tx, d_tx.contiguous(),
                                        apply_gelu, csr_tt, H, C, slope, p_drop, training, seed_tt, smax_tt, sden_tt,
-                                       grad_x_l=g_tx[:, :F], grad_x_r=g_tx[:, F:2 * F])
+                                       grad_x_l=g_tx[:, :F], grad_x_r=g_tx[:, F:2 * F], e_logit=lg_tt)
         _, _, ga_tb, gb_tb = gatv2_bwd(y_tb, y_bd, att_tb, bias_tb, v_bd, d_bd.contiguous(), apply_gelu,
                                        csr_tb_run, H, C, slope, p_drop, training, seed_tb, smax_tb, sden_tb,
-                                       grad_x_l=g_tb, grad_x_r=g_bd)
+                                       grad_x_l=g_tb, grad_x_r=g_bd, e_logit=lg_tb)
         d_table = None
         n_genes = tx_table.size(0) if D1 else 0
         want_table = D1 > 0 and ctx.needs_input_grad[26]

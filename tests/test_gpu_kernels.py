@@ -425,3 +425,57 @@ def test_gatv2_bwd_one_source_per_edge_form(H, C):
     assert torch.equal(a[2], b[2])                     # grad_att: same products, same order
     a2 = ops.gatv2_bwd(x_l, x_r, att, bias, out, go, True, v, H, C, 0.2, 0.2, True, 5, smax, sden)
     assert all(torch.equal(u, w) for u, w in zip(a, a2))
+
+
+@pytest.mark.parametrize("H,C", [(2, 64), (1, 128), (4, 32), (3, 32), (4, 128), (1, 512)])
+@pytest.mark.parametrize("direct", [False, True])
+def test_gatv2_bwd_saved_logits_equal_recomputed(H, C, direct):
+    """The sub-warp forward leaves the raw logits [E, H] (dst-CSR order); a backward handed that buffer reads them back
+    instead of recomputing att . lrelu(x_l[j] + x_r[i]) and applies att once per row.  Must equal the recomputing
+    backward to rounding -- two-pass form and one-source-per-edge form, dropout on, fused GELU' -- and must match the
+    logits the oracle computes."""
+    F = H * C
+    g = torch.Generator().manual_seed(10 * C + H)
+    if direct:
+        n_src, n_dst, E = 5000, 300, 2100
+        src = torch.sort(torch.randperm(n_src, generator=g)[:E]).values
+        ei = torch.stack([src, torch.randint(0, n_dst - 20, (E,), generator=g)])
+        csr = ops.build_csr(ei.cuda(), n_src, n_dst).per_edge_sources()
+        n_l = E
+    else:
+        n_src, n_dst, E = 700, 401, 4000
+        ei = random_graph(n_src, n_dst, E, seed=C)
+        csr = ops.build_csr(ei.cuda(), n_src, n_dst)
+        n_l = n_src
+    x_l, x_r = torch.randn(n_l, F, generator=g).cuda(), torch.randn(n_dst, F, generator=g).cuda()
+    att, bias = (torch.randn(F, generator=g) * 0.3).cuda(), (torch.randn(F, generator=g) * 0.1).cuda()
+    go = torch.randn(n_dst, F, generator=g).cuda()
+    out, act, smax, sden, lg = ops.gatv2_fwd(x_l, x_r, att, bias, csr, H, C, 0.2, 0.2, True, 5, True, want_logits=True)
+    assert lg is not None and tuple(lg.shape) == (csr.E, H)
+    out0, act0, smax0, sden0 = ops.gatv2_fwd(x_l, x_r, att, bias, csr, H, C, 0.2, 0.2, True, 5, True)
+    assert torch.equal(out, out0) and torch.equal(act, act0) and torch.equal(smax, smax0) and torch.equal(sden, sden0)
+    # logits vs a direct evaluation (dst-CSR order: source = csr.col, destination = row of the position)
+    dst_of = torch.repeat_interleave(torch.arange(n_dst, device="cuda"), (csr.rowptr[1:] - csr.rowptr[:-1]).long())
+    z = torch.nn.functional.leaky_relu(x_l[csr.col.long()] + x_r[dst_of], 0.2).view(-1, H, C)
+    ref_lg = (z * att.view(1, H, C)).sum(-1)
+    assert rel_err(lg, ref_lg) < 1e-5
+    a = ops.gatv2_bwd(x_l, x_r, att, bias, out, go, True, csr, H, C, 0.2, 0.2, True, 5, smax, sden, e_logit=lg)
+    b = ops.gatv2_bwd(x_l, x_r, att, bias, out, go, True, csr, H, C, 0.2, 0.2, True, 5, smax, sden)
+    for u, w in zip(a, b):
+        assert rel_err(u, w) < 2e-6
+    a2 = ops.gatv2_bwd(x_l, x_r, att, bias, out, go, True, csr, H, C, 0.2, 0.2, True, 5, smax, sden, e_logit=lg)
+    assert all(torch.equal(u, w) for u, w in zip(a, a2))          # deterministic
+
+
+def test_gatv2_logits_not_offered_outside_the_subwarp_kernels(monkeypatch):
+    """Shapes / modes the sub-warp kernels do not cover return no logit buffer (the backward then recomputes)."""
+    H, C = 5, 7
+    x_l, x_r, att, bias, ei = _gat_case(100, 80, 600, H, C, seed=3)
+    csr = ops.build_csr(ei.cuda(), 100, 80)
+    r = ops.gatv2_fwd(x_l.cuda(), x_r.cuda(), att.cuda(), bias.cuda(), csr, H, C, 0.2, 0.0, False, 0, False, want_logits=True)
+    assert len(r) == 5 and r[4] is None
+    monkeypatch.setenv("SEGGER_B200_GAT_LOGITS", "0")
+    x_l, x_r, att, bias, ei = _gat_case(100, 80, 600, 2, 64, seed=3)
+    csr = ops.build_csr(ei.cuda(), 100, 80)
+    r = ops.gatv2_fwd(x_l.cuda(), x_r.cuda(), att.cuda(), bias.cuda(), csr, 2, 64, 0.2, 0.0, False, 0, False, want_logits=True)
+    assert r[4] is None
