@@ -820,7 +820,7 @@ template <int MODE, int PW>
 __device__ __forceinline__ void ts_write_rows(const float* __restrict__ stg_lane /* stg + sub * ld + c4 */, float* __restrict__ dst,
                                               int64_t row_step /* floats between row groups */, int rows_left /* - sub */,
                                               const float4 b, float* __restrict__ dst_act, int64_t act_step, int act,
-                                              const float* const (&trow)[PW / 4]) {
+                                              const float4 (&tabv)[PW / 4] /* MODE 1: table values, loaded by the caller */) {
   constexpr int LR = PW / 4;
   constexpr int kStgLd = PW + 4;
   float4 t[LR];
@@ -836,7 +836,7 @@ __device__ __forceinline__ void ts_write_rows(const float* __restrict__ stg_lane
       v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
     }
     if (MODE == 1) {
-      const float4 o = ldg4(trow[it]);
+      const float4 o = tabv[it];
       v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
     }
     st4(d, v);
@@ -1125,6 +1125,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       for (int pass = 0; pass < CW / PW; ++pass) {
         const int c0 = pass * PW;
         if (p.dbg & 8) break;
+        const int64_t n = n0 + c0 + c4;
+        // table gather: the four row groups' table chunks of this pass are requested before the register -> staging
+        // copy, so their (L2) latency overlaps it instead of being exposed once per row group inside the write loop
+        // (measured: the first-layer projection with the gather cost twice the plain one)
+        float4 tabv[LR];
+#pragma unroll
+        for (int it = 0; it < LR; ++it)
+          tabv[it] = (wmode == 1 && fast_trow[it] != nullptr && n + 4 <= p.N) ? ldg4(fast_trow[it] + c0)
+                                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < CW / PW; ++k) {
@@ -1136,7 +1145,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
           }
         }
         __syncwarp();
-        const int64_t n = n0 + c0 + c4;
         if (n < p.N) {
           const bool whole = n + 4 <= p.N;
           float b4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1148,14 +1156,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
             const float4 bv = make_float4(b4[0], b4[1], b4[2], b4[3]);
             const float* sl = stg + sub * kStgLd + c4;
             float* d = fast_dst + c0;
-            if (wmode == 0) ts_write_rows<0, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, fast_trow);
-            else if (wmode == 1) {
-              const float* tr[LR];
-#pragma unroll
-              for (int it = 0; it < LR; ++it) tr[it] = fast_trow[it] + c0;
-              ts_write_rows<1, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, tr);
-            } else if (wmode == 2) ts_write_rows<2, PW>(sl, d, fast_step, fast_rows, bv, fast_dst_act + c0, fast_act_step, p.act, fast_trow);
-            else ts_write_rows<3, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, fast_trow);
+            if (wmode == 0) ts_write_rows<0, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, tabv);
+            else if (wmode == 1) ts_write_rows<1, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, tabv);
+            else if (wmode == 2) ts_write_rows<2, PW>(sl, d, fast_step, fast_rows, bv, fast_dst_act + c0, fast_act_step, p.act, tabv);
+            else ts_write_rows<3, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, tabv);
             continue;
           }
 #pragma unroll 1
