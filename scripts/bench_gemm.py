@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="", help="comma list of ops to run (fwd, dgrad, wgrad); default all")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     R = a.rows
@@ -40,7 +41,10 @@ def main():
     rows = []
     shapes = [("fwd", R, 384, 256), ("fwd", R, 384, 128), ("fwd", 2 * R, 64, 256), ("fwd", 2 * R, 64, 64), ("fwd", R, 64, 128),
               ("dgrad", R, 384, 256), ("dgrad", R, 384, 128), ("dgrad", R, 64, 128), ("dgrad", 2 * R, 64, 64),
-              ("wgrad", R, 384, 256), ("wgrad", R, 384, 128), ("wgrad", 2 * R, 64, 256), ("wgrad", R, 64, 128)]
+              ("wgrad", R, 384, 256), ("wgrad", R, 384, 128), ("wgrad", 2 * R, 64, 256), ("wgrad", R, 64, 128),
+              ("wgrad", 2 * R, 64, 64), ("wgrad", R, 256, 128)]
+    if a.only:
+        shapes = [sh for sh in shapes if sh[0] in a.only.split(",")]
     for op, M, N, K in shapes:
         S = min(M, 65536)
         if op == "fwd":

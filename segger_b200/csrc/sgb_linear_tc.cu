@@ -72,6 +72,8 @@ struct TcParams {
   int stages;
   int terms;                // 3: hi*hi + lo*hi + hi*lo (~2^-22);  4: + lo*lo (fp32-exact products)
   int kc;                   // K=8 steps per TMEM chunk (1, 2 or 4): accumulations done inside the tensor core
+  int ks;                   // SS kernel, kc == BK/8 only: k-STAGES per TMEM chunk (wgrad: the chunk read-back, not the
+                            // tensor core, paced the 32-deep chunks of a reduction over 10^6 rows); 0 / 1 = one stage
   float* colsum;            // wgrad only: column sums of A's source (db = sum_m dy[m, :]): [splits][M] partials, or db itself
   int colsum_accumulate;    // splits == 1: add into db
   int dbg;                  // timing experiments only (SEGGER_B200_TC_DBG bitmask): results are wrong when set
@@ -589,6 +591,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
       constexpr uint32_t b_lbo = B_MN ? 512u : 16u, b_sbo = B_MN ? (BN / 32) * 512u : 1024u, b_step = B_MN ? 2 * b_sbo : 32u;
       constexpr uint32_t a_lt = A_MN ? 1u : 2u, b_lt = B_MN ? 1u : 2u;
       const int kc = p.kc;
+      const int ks = (p.kc == BK / 8 && p.ks > 1) ? p.ks : 1;
+      int in_chunk = 0;              // stages already accumulated into the current chunk (ks > 1)
       int stage = 0;
       uint32_t phase = 0;
       uint32_t cc = 0;               // chunk counter: TMEM buffer = cc % kAccBufs
@@ -600,6 +604,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
           tc_fence_after();
           const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * kStageBytes);
           const uint32_t a_hi = st, a_lo = st + kATile, b_hi = st + 2 * kATile, b_lo = b_hi + kBTile;
+          if (ks > 1) {           // a chunk spans ks stages (the last chunk of a split may be shorter)
+            const uint32_t buf = cc % kAccBufs;
+            if (in_chunk == 0) {
+              mbar_wait(smem_u32(&bar_tempty[buf]), ((cc / kAccBufs) & 1u) ^ 1u);
+              tc_fence_after();
+            }
+            const uint32_t d_tmem = tmem_base + buf * BN;
+            uint32_t accum = in_chunk == 0 ? 0u : 1u;
+            for (int term = ((p.dbg & 4) ? 3 : (p.terms >= 4 ? 0 : 1)); term < 4; ++term) {
+              const uint32_t ab = (term == 3 || term == 2) ? a_hi : a_lo;
+              const uint32_t bb = (term == 3 || term == 1) ? b_hi : b_lo;
+              for (int j = 0; j < BK / 8; ++j) {
+                tc_mma_tf32(d_tmem, make_sdesc(ab + j * a_step, a_lbo, a_sbo, a_lt), make_sdesc(bb + j * b_step, b_lbo, b_sbo, b_lt),
+                            idesc, accum);
+                accum = 1u;
+              }
+            }
+            if (++in_chunk == ks || k0 + BK >= ke) {
+              tc_commit(smem_u32(&bar_tfull[buf]));
+              ++cc;
+              in_chunk = 0;
+            }
+          } else
           for (int j0 = 0; j0 < BK / 8; j0 += kc, ++cc) {
             const uint32_t buf = cc % kAccBufs;
             mbar_wait(smem_u32(&bar_tempty[buf]), ((cc / kAccBufs) & 1u) ^ 1u);
@@ -636,7 +663,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
       const int64_t nb = tile % num_n, mb = (tile / num_n) % num_m, sp = tile / (num_n * num_m);
       const int64_t n0 = nb * BN + half * CW;
       const int64_t kb = sp * p.k_per_split, ke = min(p.K, kb + p.k_per_split);
-      const int64_t nchunks = ((ke - kb + BK - 1) / BK) * chunks_per_stage;
+      const int64_t nstages = (ke - kb + BK - 1) / BK;
+      const int64_t nchunks = (p.kc == BK / 8 && p.ks > 1) ? (nstages + p.ks - 1) / p.ks : nstages * chunks_per_stage;
       float acc[CW];
 #pragma unroll
       for (int i = 0; i < CW; ++i) acc[i] = 0.f;
@@ -1451,6 +1479,20 @@ int tc_linear_dgrad(const float* dy, int64_t ldy, const float* w, int64_t ldw, i
   return run_packed(p, w, ldw, 1, ws, stream);
 }
 
+// k-stages per TMEM chunk of the weight-gradient GEMM (SEGGER_B200_TC_WGRAD_KS, read per call for A/B runs).
+// Measured on B200 (scripts/bench_gemm.py --only wgrad; error = max |dw - fp64| / max |fp64| over 10^6-row reductions):
+//   ks   1M x 384 x 256   1M x 256 x 128   2M x 64 x 64     error
+//   1       1.81 ms          0.61 ms          0.57 ms       5.0 .. 7.4e-7
+//   2       1.49             0.50             0.43          5.1 .. 6.8e-7
+//   4       1.45             0.49             0.42          0.9 .. 1.1e-6
+//   8       1.45             0.49             0.42          1.7 .. 2.0e-6
+// 64-deep chunks take the read-back hand-over off the critical path at no measurable cost in accuracy; deeper ones buy
+// 2 % more and start to show the tensor core's truncating accumulation.
+static int tc_wgrad_ks() {
+  const char* e = getenv("SEGGER_B200_TC_WGRAD_KS");
+  const int v = e ? atoi(e) : 2;
+  return v < 1 ? 1 : (v > 16 ? 16 : v);
+}
 static int tc_wgrad_splits(int64_t M, int64_t N, int64_t K) {
   const int64_t bn = pick_bn(K);
   const int64_t tiles = ceil_div(N, BM) * ceil_div(K, bn);
@@ -1477,6 +1519,7 @@ int tc_linear_wgrad(const float* dy, int64_t ldy, const float* x, int64_t ldx, i
   p.k_per_split = ceil_div(ceil_div(M, splits0), BK) * BK;
   p.terms = tc_terms(false);
   p.kc = tc_kc(false);
+  p.ks = tc_wgrad_ks();
   // every split must own at least one k-stage
   while (p.splits > 1 && static_cast<int64_t>(p.splits - 1) * p.k_per_split >= M) --p.splits;
   const bool narrow = pick_bn(K) == 64;
