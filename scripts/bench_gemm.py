@@ -51,7 +51,7 @@ def main():
             # post-GELU-like inputs (mostly positive) are the hard case for a truncating accumulator
             x = torch.nn.functional.gelu(torch.randn(M, K, device=dev, generator=g))
             w = torch.randn(N, K, device=dev, generator=g) / K ** 0.5
-            for exact in (0, 1, 2):
+            for exact in ((0, 1) if a.only else (0, 1, 2)):
                 t = time_it(lambda: ops.linear_fwd(x, w, None, exact=exact))
                 y, _ = ops.linear_fwd(x[:S], w, None, exact=exact)
                 ref = x[:S].double() @ w.double().t()
