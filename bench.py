@@ -668,15 +668,18 @@ def kernel_rooflines(d, n_tx, n_cells, H, C, n_layers, device, hbm_peak, bf16_pe
     # tx-neighbors-tx conv
     fwd_b, bwd_b = gat_bytes(touched_tt, n_tx, n_tx, csr_tt.E, H, C)
     g = torch.randn(n_tx, F, device=device)
-    out, _, smax, sden = ops.gatv2_fwd(y[:, :F], y[:, F:], att, bias, csr_tt, H, C, 0.2, 0.0, False, 0, True)
+    # the launches a training step makes: the forward also leaves the raw logits [E, H] the backward's dst pass reads back
+    # (want_logits: 4H bytes per edge each way, NOT counted in the algorithmic bytes below)
+    out, _, smax, sden, lg = ops.gatv2_fwd(y[:, :F], y[:, F:], att, bias, csr_tt, H, C, 0.2, 0.2, True, 7, True, want_logits=True)
     G = torch.empty(n_tx, 2 * F, device=device)
-    t_fwd = _time_alone(lambda: ops.gatv2_fwd(y[:, :F], y[:, F:], att, bias, csr_tt, H, C, 0.2, 0.2, True, 7, True), flush)
+    t_fwd = _time_alone(lambda: ops.gatv2_fwd(y[:, :F], y[:, F:], att, bias, csr_tt, H, C, 0.2, 0.2, True, 7, True,
+                                              want_logits=True), flush)
     t_bwd = _time_alone(lambda: ops.gatv2_bwd(y[:, :F], y[:, F:], att, bias, out, g, True, csr_tt, H, C, 0.2, 0.2, True,
-                                              7, smax, sden, grad_x_l=G[:, :F], grad_x_r=G[:, F:]), flush)
+                                              7, smax, sden, grad_x_l=G[:, :F], grad_x_r=G[:, F:], e_logit=lg), flush)
     path = "sub-warp (quad) kernels" if quad else "row-per-warp kernels"
     ents = [entry(f"gatv2 forward, tx-neighbors-tx, H={H} C={C} ({path}: fused logits + segment softmax + dropout + "
                   "aggregate + bias + GELU)", fwd_b, t_fwd, f"gatv2_fwd_tt_{workload}"),
-            entry(f"gatv2 backward, tx-neighbors-tx, H={H} C={C} ({path}: dst pass + src pass + column sums)", bwd_b, t_bwd,
+            entry(f"gatv2 backward, tx-neighbors-tx, H={H} C={C} ({path}: saved-logit dst pass + src pass + column sums)", bwd_b, t_bwd,
                   f"gatv2_bwd_tt_{workload}")]
     # tx-belongs-bd conv on one virtual source per edge (what SkipGATLayerFn runs when the belongs list is unique)
     vcsr = csr_tb.per_edge_sources() if csr_tb.sources_unique_increasing() else csr_tb
@@ -685,10 +688,10 @@ def kernel_rooflines(d, n_tx, n_cells, H, C, n_layers, device, hbm_peak, bf16_pe
     xr_b = torch.randn(n_cells, F, device=device)
     gb = torch.randn(n_cells, F, device=device)
     fb, bb = gat_bytes(touched_tb, n_cells, n_src_b, vcsr.E, H, C)
-    out_b, _, smax_b, sden_b = ops.gatv2_fwd(xl_b, xr_b, att, bias, vcsr, H, C, 0.2, 0.0, False, 0, True)
-    t_fwd_b = _time_alone(lambda: ops.gatv2_fwd(xl_b, xr_b, att, bias, vcsr, H, C, 0.2, 0.2, True, 7, True), flush)
+    out_b, _, smax_b, sden_b, lg_b = ops.gatv2_fwd(xl_b, xr_b, att, bias, vcsr, H, C, 0.2, 0.2, True, 7, True, want_logits=True)
+    t_fwd_b = _time_alone(lambda: ops.gatv2_fwd(xl_b, xr_b, att, bias, vcsr, H, C, 0.2, 0.2, True, 7, True, want_logits=True), flush)
     t_bwd_b = _time_alone(lambda: ops.gatv2_bwd(xl_b, xr_b, att, bias, out_b, gb, True, vcsr, H, C, 0.2, 0.2, True, 7,
-                                                smax_b, sden_b), flush)
+                                                smax_b, sden_b, e_logit=lg_b), flush)
     ents += [entry("gatv2 forward, tx-belongs-bd", fb, t_fwd_b), entry("gatv2 backward, tx-belongs-bd", bb, t_bwd_b)]
     mp_t = n_layers * (t_fwd + t_bwd + t_fwd_b + t_bwd_b)
     mp_bytes = n_layers * (fwd_b + bwd_b + fb + bb)

@@ -32,9 +32,9 @@ def main():
     gt = torch.randn(n_tx, F, device=dev, generator=g)
     G = torch.empty(n_tx, 2 * F, device=dev)
     torch.cuda.synchronize()
-    out, _, smax, sden = ops.gatv2_fwd(y[:, :F], y[:, F:], att, bias, csr_tt, H, C, 0.2, 0.2, True, 7, True)
+    out, _, smax, sden, lg = ops.gatv2_fwd(y[:, :F], y[:, F:], att, bias, csr_tt, H, C, 0.2, 0.2, True, 7, True, want_logits=True)
     ops.gatv2_bwd(y[:, :F], y[:, F:], att, bias, out, gt, True, csr_tt, H, C, 0.2, 0.2, True, 7, smax, sden,
-                  grad_x_l=G[:, :F], grad_x_r=G[:, F:])
+                  grad_x_l=G[:, :F], grad_x_r=G[:, F:], e_logit=lg)
     x = torch.nn.functional.gelu(torch.randn(n_tx, 128, device=dev, generator=g))
     w = torch.randn(2 * F, 128, device=dev, generator=g) / 11
     ops.linear_fwd(x, w, None, exact=1)

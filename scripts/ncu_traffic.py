@@ -61,7 +61,7 @@ quad, tc = "segger_b200/csrc/sgb_gatv2_quad.cu", "segger_b200/csrc/sgb_linear_tc
 gemms = [l for l in launches if "gemm_tf32x3" in l["name"]]
 db = {"captured": tag, "command": "ncu --set full --clock-control none python scripts/ncu_targets_r2.py", "kernels": {
     "gatv2_fwd_tt_cfg2": entry(first(lambda n: "gatv2_fwd_quad" in n), quad),
-    "gatv2_bwd_tt_cfg2": entry(first(lambda n: "gatv2_bwd_dst_quad" in n) + first(lambda n: "gatv2_bwd_src_quad" in n), quad),
+    "gatv2_bwd_tt_cfg2": entry(first(lambda n: "gatv2_bwd_dst_quad" in n or "gatv2_bwd_dst_lg_quad" in n) + first(lambda n: "gatv2_bwd_src_quad" in n), quad),
     "gemm_fwd_cfg2": entry(gemms[:1], tc), "gemm_dgrad_cfg2": entry(gemms[1:2], tc), "gemm_wgrad_cfg2": entry(gemms[2:3], tc)}}
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as f:
