@@ -73,13 +73,14 @@ SGB_API int sgb_csr_build(const void* edge_index, int idx_bytes, int64_t row_str
  * out = pre-activation (o + bias); out_act (optional) = GELU(out) (fuses ist_encoder.py:325).
  * out may be NULL when out_act is given (inference: only the activated output is written).
  * stat_max/stat_den [n_dst,H] are saved for the backward.  seed/p_drop/training drive the
- * e_logit (optional, [E, H]): where the sub-warp kernels run (sgb_gatv2_quad_supported) the forward leaves the raw
- * logit of every (edge, head) there, in dst-CSR order, and a backward that is handed the same buffer reads it back
- * instead of re-evaluating att . leaky_relu(x_l[j] + x_r[i]) (4H bytes per edge against ~3 instructions per edge and
- * feature).  Other kernel paths ignore it (sgb_gatv2_bwd then must be given NULL as well).
  * counter-based dropout keyed on (seed, original edge id, head).  seed_dev (or NULL) points to one device-resident
  * 64-bit word that is ADDED to seed when the kernel runs: a captured CUDA graph freezes by-value arguments, so a
  * replayed training step advances that word to draw a fresh mask (forward and backward read the same word).
+ * e_logit (optional, [E, H]): where the sub-warp kernels run (sgb_gatv2_quad_supported, 16-byte aligned operands) the
+ * forward leaves the raw logit of every (edge, head) there, in dst-CSR order, and a backward that is handed the same
+ * buffer reads it back instead of re-evaluating att . leaky_relu(x_l[j] + x_r[i]) (4H bytes per edge against ~3
+ * instructions per edge and feature).  The other kernel paths neither write nor read it: passing it to them is an
+ * error (SGB_ERR_ARG), not a silent no-op.
  * ---------------------------------------------------------------------------------------- */
 SGB_API int sgb_gatv2_fwd(const float* x_l, int64_t ld_l, const float* x_r, int64_t ld_r, const float* att,
                   const float* bias /*or NULL*/, const int32_t* dst_rowptr, const int32_t* dst_col,

@@ -848,9 +848,20 @@ template <int MODE, int PW>
 __device__ __forceinline__ void ts_write_rows(const float* __restrict__ stg_lane /* stg + sub * ld + c4 */, float* __restrict__ dst,
                                               int64_t row_step /* floats between row groups */, int rows_left /* - sub */,
                                               const float4 b, float* __restrict__ dst_act, int64_t act_step, int act,
-                                              const float4 (&tabv)[PW / 4] /* MODE 1: table values, loaded by the caller */) {
+                                              const float* const (&trow)[PW / 4]) {
   constexpr int LR = PW / 4;
   constexpr int kStgLd = PW + 4;
+  // MODE 1: the table chunks of all row groups are requested up front, so their (L2) latencies overlap each other and
+  // the shared-memory reads instead of being exposed once per row group inside the loop (the gather epilogue cost the
+  // first-layer projection 2x the plain one).  Kept inside this instantiation: hoisting the loads above the register ->
+  // staging copy of the caller made every OTHER epilogue mode 20 % slower (16 more live registers in the pass loop), and a
+  // register-free prefetch.global.L1 there cost the plain mode 10 % as well (the pass loop is instruction-fetch bound).
+  float4 tabv[LR];
+  if (MODE == 1) {
+#pragma unroll
+    for (int it = 0; it < LR; ++it)
+      tabv[it] = it * (32 / LR) < rows_left ? ldg4(trow[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float4 t[LR];
 #pragma unroll
   for (int it = 0; it < LR; ++it) t[it] = *reinterpret_cast<const float4*>(stg_lane + it * (32 / LR) * kStgLd);
@@ -1050,15 +1061,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       if constexpr (B_RES) {
         if (blockIdx.x < tiles) mbar_wait(smem_u32(&bar_bres), 0);
       }
-      const int64_t cks = p.ks > 1 ? p.ks : 1;      // k-stages per TMEM chunk
+      const int cks = p.ks > 1 ? p.ks : 1;          // k-stages per TMEM chunk
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int in_chunk = 0;                             // (no division on this thread: it paces the tensor core)
         for (int64_t ks = 0; ks < num_ks; ++ks) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
           tc_fence_after();
           const uint32_t b_hi = smem_u32(smem_b + static_cast<size_t>(B_RES ? ks : stage) * kBStage), b_lo = b_hi + kBTile;
           const uint32_t a_hi = tmem_base + kTsACol0 + static_cast<uint32_t>(stage) * 64u, a_lo = a_hi + 32u;
           const uint32_t buf = cc % kTsAcc;
-          const bool first = ks % cks == 0, last = (ks + 1) % cks == 0 || ks + 1 == num_ks;
+          const bool first = in_chunk == 0;
+          const bool last = ++in_chunk == cks || ks + 1 == num_ks;
+          if (last) in_chunk = 0;
           if (first) {
             mbar_wait(smem_u32(&bar_tempty[buf]), ((cc / kTsAcc) & 1u) ^ 1u);
             tc_fence_after();
@@ -1161,15 +1175,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       for (int pass = 0; pass < CW / PW; ++pass) {
         const int c0 = pass * PW;
         if (p.dbg & 8) break;
-        const int64_t n = n0 + c0 + c4;
-        // table gather: the four row groups' table chunks of this pass are requested before the register -> staging
-        // copy, so their (L2) latency overlaps it instead of being exposed once per row group inside the write loop
-        // (measured: the first-layer projection with the gather cost twice the plain one)
-        float4 tabv[LR];
-#pragma unroll
-        for (int it = 0; it < LR; ++it)
-          tabv[it] = (wmode == 1 && fast_trow[it] != nullptr && n + 4 <= p.N) ? ldg4(fast_trow[it] + c0)
-                                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < CW / PW; ++k) {
@@ -1181,6 +1186,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
           }
         }
         __syncwarp();
+        const int64_t n = n0 + c0 + c4;
         if (n < p.N) {
           const bool whole = n + 4 <= p.N;
           float b4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1192,10 +1198,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
             const float4 bv = make_float4(b4[0], b4[1], b4[2], b4[3]);
             const float* sl = stg + sub * kStgLd + c4;
             float* d = fast_dst + c0;
-            if (wmode == 0) ts_write_rows<0, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, tabv);
-            else if (wmode == 1) ts_write_rows<1, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, tabv);
-            else if (wmode == 2) ts_write_rows<2, PW>(sl, d, fast_step, fast_rows, bv, fast_dst_act + c0, fast_act_step, p.act, tabv);
-            else ts_write_rows<3, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, tabv);
+            if (wmode == 0) ts_write_rows<0, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, fast_trow);
+            else if (wmode == 1) {
+              const float* tr[LR];
+#pragma unroll
+              for (int it = 0; it < LR; ++it) tr[it] = fast_trow[it] + c0;
+              ts_write_rows<1, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, tr);
+            } else if (wmode == 2) ts_write_rows<2, PW>(sl, d, fast_step, fast_rows, bv, fast_dst_act + c0, fast_act_step, p.act, fast_trow);
+            else ts_write_rows<3, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, fast_trow);
             continue;
           }
 #pragma unroll 1
