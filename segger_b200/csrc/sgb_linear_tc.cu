@@ -844,11 +844,11 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
 // that loop at ~7 cycles per instruction (branches, address arithmetic, one exposed shared-memory load per row group).
 // MODE 0: C = acc + bias.  1: + table[gid[row]].  2: + C_act = act(C).  3: C += acc + bias.  All need whole, 16-byte
 // aligned float4 columns; the four row groups of the pass are unrolled so their loads overlap.
-template <int MODE, int PW>
+template <int MODE, int PW, bool PRELOADED = false>
 __device__ __forceinline__ void ts_write_rows(const float* __restrict__ stg_lane /* stg + sub * ld + c4 */, float* __restrict__ dst,
                                               int64_t row_step /* floats between row groups */, int rows_left /* - sub */,
                                               const float4 b, float* __restrict__ dst_act, int64_t act_step, int act,
-                                              const float* const (&trow)[PW / 4]) {
+                                              const float* const (&trow)[PW / 4], const float4* pre = nullptr) {
   constexpr int LR = PW / 4;
   constexpr int kStgLd = PW + 4;
   // MODE 1: the table chunks of all row groups are requested up front, so their (L2) latencies overlap each other and
@@ -856,11 +856,12 @@ __device__ __forceinline__ void ts_write_rows(const float* __restrict__ stg_lane
   // first-layer projection 2x the plain one).  Kept inside this instantiation: hoisting the loads above the register ->
   // staging copy of the caller made every OTHER epilogue mode 20 % slower (16 more live registers in the pass loop), and a
   // register-free prefetch.global.L1 there cost the plain mode 10 % as well (the pass loop is instruction-fetch bound).
+  // (PRELOADED: the WM = 1 kernel requested them even earlier, before the register -> staging copy)
   float4 tabv[LR];
   if (MODE == 1) {
 #pragma unroll
     for (int it = 0; it < LR; ++it)
-      tabv[it] = it * (32 / LR) < rows_left ? ldg4(trow[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      tabv[it] = PRELOADED ? pre[it] : (it * (32 / LR) < rows_left ? ldg4(trow[it]) : make_float4(0.f, 0.f, 0.f, 0.f));
   }
   float4 t[LR];
 #pragma unroll
@@ -884,7 +885,11 @@ __device__ __forceinline__ void ts_write_rows(const float* __restrict__ stg_lane
   }
 }
 
-template <int BN, int S, bool B_RES, bool PP>
+// WM: write-out class compiled into this instantiation -- 0 plain, 1 + table gather, 2 + activated copy (the host
+// checked their alignment preconditions), 4 every option behind run-time flags.  The epilogue warps run one or two to a
+// scheduler and their pass loop is bound by instruction fetch and live registers, so the ~1.4k-instruction general body
+// is only compiled into the WM = 4 kernels.
+template <int BN, int S, bool B_RES, bool PP, int WM>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t kBTile = BN * 128;            // bytes of one hi (or lo) B tile of a k-stage
@@ -1145,7 +1150,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       const bool vec_p = p.act_pre && (p.ld_pre % 4 == 0) && aligned16(p.act_pre) && (n0 % 4 == 0);
       const bool vec_g = p.gtab && (p.ld_gtab % 4 == 0) && aligned16(p.gtab) && (n0 % 4 == 0);
       // epilogue class of this launch (uniform): 0 plain, 1 + table gather, 2 + activated copy, 3 accumulate, 4 general
-      const int wmode = (!vec_c || p.act_pre) ? 4
+      const int wmode = WM < 4 ? WM
+                        : (!vec_c || p.act_pre) ? 4
                         : p.gtab ? ((vec_g && !p.accumulate && !p.C_act) ? 1 : 4)
                         : p.C_act ? ((vec_a && !p.accumulate) ? 2 : 4)
                         : p.accumulate ? 3 : 0;
@@ -1175,6 +1181,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       for (int pass = 0; pass < CW / PW; ++pass) {
         const int c0 = pass * PW;
         if (p.dbg & 8) break;
+        // WM = 1 (this instantiation only gathers): the pass's table chunks are requested before the register -> staging
+        // copy so their L2 latency overlaps it
+        float4 pre[WM == 1 ? LR : 1];
+        if constexpr (WM == 1) {
+#pragma unroll
+          for (int it = 0; it < LR; ++it)
+            pre[it] = fast_trow[it] != nullptr ? ldg4(fast_trow[it] + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < CW / PW; ++k) {
@@ -1188,11 +1202,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
         __syncwarp();
         const int64_t n = n0 + c0 + c4;
         if (n < p.N) {
-          const bool whole = n + 4 <= p.N;
+          const bool whole = WM < 4 || n + 4 <= p.N;      // (WM < 4: N % 4 == 0, checked by the host)
           float b4[4] = {0.f, 0.f, 0.f, 0.f};
           if (p.bias) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) if (n + e < p.N) b4[e] = __ldg(p.bias + n + e);
+            for (int e = 0; e < 4; ++e) if (WM < 4 || n + e < p.N) b4[e] = __ldg(p.bias + n + e);
           }
           if (whole && wmode != 4) {
             const float4 bv = make_float4(b4[0], b4[1], b4[2], b4[3]);
@@ -1200,14 +1214,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
             float* d = fast_dst + c0;
             if (wmode == 0) ts_write_rows<0, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, fast_trow);
             else if (wmode == 1) {
-              const float* tr[LR];
+              if constexpr (WM == 1) {
+                ts_write_rows<1, PW, true>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, fast_trow, pre);
+              } else {
+                const float* tr[LR];
 #pragma unroll
-              for (int it = 0; it < LR; ++it) tr[it] = fast_trow[it] + c0;
-              ts_write_rows<1, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, tr);
+                for (int it = 0; it < LR; ++it) tr[it] = fast_trow[it] + c0;
+                ts_write_rows<1, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, tr);
+              }
             } else if (wmode == 2) ts_write_rows<2, PW>(sl, d, fast_step, fast_rows, bv, fast_dst_act + c0, fast_act_step, p.act, fast_trow);
             else ts_write_rows<3, PW>(sl, d, fast_step, fast_rows, bv, nullptr, 0, 0, fast_trow);
             continue;
           }
+          if constexpr (WM == 4) {
 #pragma unroll 1
           for (int it = 0; it < LR; ++it) {
             const int r = it * (32 / LR) + sub;
@@ -1266,6 +1285,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
               }
             }
           }
+          }   // WM == 4
         }
       }
     }
@@ -1345,15 +1365,15 @@ size_t packed_b_bytes(int64_t N, int64_t K) {
   return align_up(static_cast<size_t>(ceil_div(N, bn)) * ceil_div(K, BK) * (2 * bn * 128));
 }
 
-template <int BN, int S, bool B_RES, bool PP>
-int launch_ts_pp(TcParams p, cudaStream_t stream) {
+template <int BN, int S, bool B_RES, bool PP, int WM>
+int launch_ts_wm(TcParams p, cudaStream_t stream) {
   p.stages = S;
   p.dbg = env_int("SEGGER_B200_TC_DBG", 0, 255, 0);
   constexpr size_t smem = static_cast<size_t>(S) * (2 * BN * 128) + static_cast<size_t>(kTsRaw) * (BM * 128) + stg_bytes(kPW) + 1024;
   static_assert(smem + 512 <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_ts_kernel<BN, S, B_RES, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_ts_kernel<BN, S, B_RES, PP, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return set_error(SGB_ERR_CUDA, "tc gemm (ts): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -1364,8 +1384,28 @@ int launch_ts_pp(TcParams p, cudaStream_t stream) {
     grid = grid / num_n * num_n;
     if (grid < num_n) grid = num_n < tiles ? num_n : tiles;
   }
-  gemm_tf32x3_ts_kernel<BN, S, B_RES, PP><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
+  gemm_tf32x3_ts_kernel<BN, S, B_RES, PP, WM><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
   return check_launch("gemm_tf32x3_ts");
+}
+
+// write-out class of a launch (the kernel's own rule, evaluated once on the host): see gemm_tf32x3_ts_kernel's WM
+static int ts_write_mode(const TcParams& p) {
+  static int force_general = env_int("SEGGER_B200_GEMM_WM", 0, 1, 1) == 0;     // SEGGER_B200_GEMM_WM=0: general kernels only
+  const bool vec_c = p.ldc % 4 == 0 && aligned16(p.C) && p.N % 4 == 0;
+  if (force_general || !vec_c || p.act_pre || p.accumulate) return 4;
+  if (p.gtab) return (p.ld_gtab % 4 == 0 && aligned16(p.gtab) && !p.C_act) ? 1 : 4;
+  if (p.C_act) return (p.ldca % 4 == 0 && aligned16(p.C_act)) ? 2 : 4;
+  return 0;
+}
+
+template <int BN, int S, bool B_RES, bool PP>
+int launch_ts_pp(TcParams p, cudaStream_t stream) {
+  switch (ts_write_mode(p)) {
+    case 0: return launch_ts_wm<BN, S, B_RES, PP, 0>(p, stream);
+    case 1: return launch_ts_wm<BN, S, B_RES, PP, 1>(p, stream);
+    case 2: return launch_ts_wm<BN, S, B_RES, PP, 2>(p, stream);
+    default: return launch_ts_wm<BN, S, B_RES, PP, 4>(p, stream);
+  }
 }
 
 // Epilogue mode, chosen from scripts/bench_gemm.py on B200 (profiles/r2_gemm_epilogue_modes.md): alternating tile groups
