@@ -86,6 +86,17 @@ struct TcParams {
   int64_t ld_gtab;
 };
 
+// Timing knock-outs (SEGGER_B200_TC_DBG, scripts/gemm_knockouts*.sh) exist only in -DSGB_TC_DEBUG builds: the flag
+// tests sat in the hottest loops of warp roles whose instruction count is the critical path.
+__device__ __forceinline__ int tc_dbg(const TcParams& p) {
+#ifdef SGB_TC_DEBUG
+  return p.dbg;
+#else
+  (void)p;
+  return 0;
+#endif
+}
+
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -512,8 +523,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
     while (ci.live) {
       cp_async_wait<S - 2>();                       // this thread's chunks of slab `ci` have landed
       uint8_t* st = smem + static_cast<size_t>(cstage) * kStageBytes;
-      if (!(p.dbg & 2)) split_slab<BM, A_MN, kColsum>(st, st, st + kATile, t, cs);
-      if constexpr (!B_PACKED) if (!(p.dbg & 2)) split_slab<BN, B_MN, false, kNvB>(st + 2 * kATile, st + 2 * kATile, st + 2 * kATile + kBTile, t);
+      if (!(tc_dbg(p) & 2)) split_slab<BM, A_MN, kColsum>(st, st, st + kATile, t, cs);
+      if constexpr (!B_PACKED) if (!(tc_dbg(p) & 2)) split_slab<BN, B_MN, false, kNvB>(st + 2 * kATile, st + 2 * kATile, st + 2 * kATile + kBTile, t);
       fence_proxy_async();
       mbar_arrive(smem_u32(&bar_full[cstage]));
       if (++cstage == S) cstage = 0;
@@ -570,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
         while (ci.live) {
           cp_async_wait<S - 2>();
           uint8_t* st = smem + static_cast<size_t>(cstage) * kStageBytes;
-          if (!(p.dbg & 2)) split_slab_helper<BN>(st + 2 * kATile, st + 2 * kATile + kBTile, ht);
+          if (!(tc_dbg(p) & 2)) split_slab_helper<BN>(st + 2 * kATile, st + 2 * kATile + kBTile, ht);
           fence_proxy_async();
           mbar_arrive(smem_u32(&bar_full[cstage]));
           if (++cstage == S) cstage = 0;
@@ -612,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
             }
             const uint32_t d_tmem = tmem_base + buf * BN;
             uint32_t accum = in_chunk == 0 ? 0u : 1u;
-            for (int term = ((p.dbg & 4) ? 3 : (p.terms >= 4 ? 0 : 1)); term < 4; ++term) {
+            for (int term = ((tc_dbg(p) & 4) ? 3 : (p.terms >= 4 ? 0 : 1)); term < 4; ++term) {
               const uint32_t ab = (term == 3 || term == 2) ? a_hi : a_lo;
               const uint32_t bb = (term == 3 || term == 1) ? b_hi : b_lo;
               for (int j = 0; j < BK / 8; ++j) {
@@ -634,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
             const uint32_t d_tmem = tmem_base + buf * BN;
             uint32_t accum = 0;
             // small terms first: the truncating accumulator then sees the big hi*hi products last
-            for (int term = ((p.dbg & 4) ? 3 : (p.terms >= 4 ? 0 : 1)); term < 4; ++term) {
+            for (int term = ((tc_dbg(p) & 4) ? 3 : (p.terms >= 4 ? 0 : 1)); term < 4; ++term) {
               const uint32_t ab = (term == 3 || term == 2) ? a_hi : a_lo;      // 0: lo*lo  1: lo*hi  2: hi*lo  3: hi*hi
               const uint32_t bb = (term == 3 || term == 1) ? b_hi : b_lo;
               for (int j = j0; j < j0 + kc; ++j) {
@@ -676,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
         // 32-column read-back is in flight per warp; two epilogue warps per sub-partition interleave
 #pragma unroll
         for (int c0 = 0; c0 < CW; c0 += 32) {
-          if (p.dbg & 1) break;
+          if (tc_dbg(p) & 1) break;
           uint32_t r0[32];
           tc_ld32(lane_base + buf * BN + c0, r0);
           tc_wait_ld();
@@ -703,7 +714,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const TcParams
 #pragma unroll 1
       for (int pass = 0; pass < CW / PW; ++pass) {
         const int c0 = pass * PW;
-        if (p.dbg & 8) break;
+        if (tc_dbg(p) & 8) break;
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < CW / PW; ++k) {
@@ -1000,7 +1011,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       // this thread's row of the slab: 8 x 16 B at the swizzled chunk positions
       const uint8_t* rt = smem_rawa + static_cast<size_t>(crslot) * kRawTile;
       uint32_t hi[32], lo[32];
-      if (p.dbg & 2) {
+      if (tc_dbg(p) & 2) {
 #pragma unroll
         for (int e = 0; e < 32; ++e) { hi[e] = 0u; lo[e] = 0u; }
       } else
@@ -1019,7 +1030,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
       mbar_wait(smem_u32(&bar_empty[aslot]), aphase ^ 1u);             // the MMAs that read this A slot have retired
       tc_fence_after();
       const uint32_t a_addr = tmem_base + lane_field + kTsACol0 + static_cast<uint32_t>(aslot) * 64u;
-      if (!(p.dbg & 16)) {
+      if (!(tc_dbg(p) & 16)) {
         tc_st32(a_addr, hi);
         tc_st32(a_addr + 32u, lo);
         tc_wait_st();
@@ -1085,7 +1096,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
           const uint32_t d_tmem = tmem_base + buf * BN;
           uint32_t accum = first ? 0u : 1u;
           // small terms first: lo*hi, hi*lo, then hi*hi (terms >= 4 adds lo*lo in front)
-          for (int term = ((p.dbg & 4) ? 3 : (p.terms >= 4 ? 0 : 1)); term < 4; ++term) {
+          for (int term = ((tc_dbg(p) & 4) ? 3 : (p.terms >= 4 ? 0 : 1)); term < 4; ++term) {
             const uint32_t ab = (term == 3 || term == 2) ? a_hi : a_lo;
             const uint32_t bb = (term == 3 || term == 1) ? b_hi : b_lo;
             for (int j = 0; j < BK / 8; ++j) {
@@ -1131,7 +1142,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
         tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < CW; c0 += 32) {
-          if (p.dbg & 1) break;
+          if (tc_dbg(p) & 1) break;
           uint32_t r0[32];
           tc_ld32(lane_base + buf * BN + c0, r0);
           tc_wait_ld();
@@ -1180,7 +1191,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_ts_kernel(const TcPar
 #pragma unroll 1
       for (int pass = 0; pass < CW / PW; ++pass) {
         const int c0 = pass * PW;
-        if (p.dbg & 8) break;
+        if (tc_dbg(p) & 8) break;
         // WM = 1 (this instantiation only gathers): the pass's table chunks are requested before the register -> staging
         // copy so their L2 latency overlaps it
         float4 pre[WM == 1 ? LR : 1];
