@@ -233,6 +233,7 @@ class _CsrCache:
 CSR_CACHE = _CsrCache()
 
 _CSR_STREAMS: dict = {}
+_CSR_OVERLAP_MIN_EDGES = 2_000_000
 
 
 class CsrJoin:
@@ -260,7 +261,10 @@ class CsrJoin:
 def csr_overlap_mark(edge_index: Tensor):
     """Event on the current stream marking "the edge lists are ready" -- recorded BEFORE the caller enqueues the work the
     CSR builds are to overlap with.  None when the builds will not use the side stream."""
-    if os.environ.get("SEGGER_B200_CSR_OVERLAP", "1") == "0" or torch.cuda.is_current_stream_capturing():
+    # (small graphs are bound by the host's launch rate, where a second stream only adds host work: one tile of
+    # BASELINE configs[0] steps in 4.1 ms on the caller's stream and 4.5 ms with the side stream)
+    if (edge_index.size(-1) < _CSR_OVERLAP_MIN_EDGES or os.environ.get("SEGGER_B200_CSR_OVERLAP", "1") == "0"
+            or torch.cuda.is_current_stream_capturing()):
         return None
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(edge_index.device))
@@ -526,10 +530,16 @@ def act_fwd(x: Tensor, act: int, y: Optional[Tensor] = None) -> Tensor:
     return y
 
 
+_QUAD_SHAPES: dict = {}
+
+
 def _quad_path(H: int, C: int, slope: float, *tensors) -> bool:
     """True iff sgb_gatv2_fwd / sgb_gatv2_bwd will run the sub-warp kernels on these operands (the library's own rule:
     shape covered, 0 <= slope <= 1, 16-byte aligned pointers, leading dimensions a multiple of 4 floats)."""
-    return (bool(_lib.load().sgb_gatv2_quad_supported(H, C)) and 0.0 <= slope <= 1.0
+    ok = _QUAD_SHAPES.get((H, C))
+    if ok is None:
+        ok = _QUAD_SHAPES[(H, C)] = bool(_lib.load().sgb_gatv2_quad_supported(H, C))
+    return (ok and 0.0 <= slope <= 1.0
             and os.environ.get("SEGGER_B200_GAT") != "legacy"
             and all(t is None or (t.data_ptr() % 16 == 0 and (t.dim() < 2 or _ld(t) % 4 == 0)) for t in tensors))
 
