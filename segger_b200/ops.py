@@ -501,12 +501,64 @@ class SelectRowsFn(torch.autograd.Function):
         return dx, None
 
 
-def select_rows(x: Tensor, mask: Tensor) -> Tensor:
-    """x[mask] (boolean row mask) with the gather / scatter done by library kernels."""
-    idx = torch.nonzero(mask, as_tuple=False).flatten()
+def select_rows(x: Tensor, mask: Tensor, idx: Optional[Tensor] = None) -> Tensor:
+    """x[mask] (boolean row mask) with the gather / scatter done by library kernels.  ``idx`` = a precomputed
+    ``torch.nonzero(mask).flatten()`` (callers that resolve their masks off the critical path)."""
+    if idx is None:
+        idx = torch.nonzero(mask, as_tuple=False).flatten()
     if idx.numel() == x.size(0):
         return x
     return SelectRowsFn.apply(x, idx)
+
+
+class side_section:
+    """``with side_section(after_event) as sec:`` -- host-synchronising bookkeeping (mask -> index lists, triplet
+    sampling: ~100 short launches and half a dozen device->host reads that depend only on a batch's labels) runs on a
+    side stream, so its stream synchronisations wait for that stream alone while the caller's stream keeps executing
+    the forward pass it was already given.  ``after_event``: recorded on the caller's stream when the inputs of the
+    section were ready.  On exit the caller's stream waits for the section; ``sec.keep(t, ...)`` marks tensors created
+    inside that the caller's stream will use.  Under CUDA-graph capture (or ``SEGGER_B200_LOSS_OVERLAP=0``) the section
+    runs inline."""
+
+    def __init__(self, after_event, device):
+        self.inline = (after_event is None or os.environ.get("SEGGER_B200_LOSS_OVERLAP", "1") == "0"
+                       or torch.cuda.is_current_stream_capturing())
+        self.after, self.device, self.kept = after_event, device, []
+
+    def keep(self, *tensors):
+        self.kept.extend(t for t in tensors if isinstance(t, Tensor) and t.is_cuda)
+        return tensors[0] if len(tensors) == 1 else tensors
+
+    def __enter__(self):
+        if not self.inline:
+            self.main = torch.cuda.current_stream(self.device)
+            side = _CSR_STREAMS.get(("loss", self.device))
+            if side is None:
+                side = _CSR_STREAMS[("loss", self.device)] = torch.cuda.Stream(self.device)
+            side.wait_event(self.after)
+            self.ctx = torch.cuda.stream(side)
+            self.ctx.__enter__()
+            self.side = side
+        return self
+
+    def __exit__(self, *exc):
+        if not self.inline:
+            for t in self.kept:
+                t.record_stream(self.main)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self.ctx.__exit__(*exc)
+            self.main.wait_event(ev)
+        return False
+
+
+def section_mark(t: Tensor):
+    """Event on the current stream ("everything enqueued so far"), or None where a side section would run inline."""
+    if not t.is_cuda or os.environ.get("SEGGER_B200_LOSS_OVERLAP", "1") == "0" or torch.cuda.is_current_stream_capturing():
+        return None
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(t.device))
+    return ev
 
 
 def act_bwd(dy: Tensor, pre: Tensor, act: int, dx: Optional[Tensor] = None) -> Tensor:

@@ -223,10 +223,12 @@ class TripletLoss(torch.nn.Module):
         self.eps = float(kwargs.get("eps", 1e-6))
         self.selector = FastTripletSelector(cluster_similarity)
 
-    def forward(self, embeddings: Tensor, labels: Tensor):
+    def forward(self, embeddings: Tensor, labels: Tensor, triplets=None):
+        """``triplets`` = a ``selector.sample_triplets(labels)`` result drawn ahead of time (LitISTEncoder.get_losses
+        samples on a side stream while the forward pass runs); sampling depends on the labels only."""
         if labels.numel() == 0:
             return 0.
-        positives, negatives, _, _ = self.selector.sample_triplets(labels)
+        positives, negatives, _, _ = self.selector.sample_triplets(labels) if triplets is None else triplets
         return triplet_margin(embeddings, embeddings, embeddings, None, positives, negatives, self.margin, self.eps)
 
 
@@ -236,10 +238,10 @@ class MetricLoss:
     def __init__(self, cluster_similarity: Tensor) -> None:
         self.selector = FastTripletSelector(cluster_similarity)
 
-    def forward(self, embeddings: Tensor, labels: Tensor):
+    def forward(self, embeddings: Tensor, labels: Tensor, triplets=None):
         if labels.numel() == 0:
             return 0.
-        positives, negatives, dists_pos, dists_neg = self.selector.sample_triplets(labels)
+        positives, negatives, dists_pos, dists_neg = self.selector.sample_triplets(labels) if triplets is None else triplets
         return (cosine_mse(embeddings, embeddings, None, positives, 1 - dists_pos)
                 + cosine_mse(embeddings, embeddings, None, negatives, 1 - dists_neg))
 
