@@ -623,7 +623,10 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_quad_kernel(con
 //   grad_att   += sel_e (.) z_e                         (lrelu(z) = lrelu'(z) z)
 // Two sweeps over the staged source row per edge (g . x first: delta needs it), both from the ring slot.
 // ------------------------------------------------------------------------------------------------
-template <int V, int LPR, int H, int D, int MINB>
+// LEAN: x_r[i] and the grad_att accumulators live in lane-private shared memory as well and att is read through L1 at the
+// row end, which frees ~32 registers per thread for a fourth resident CTA per SM (the pass is bound by dependent-issue
+// latency at 3 warps per scheduler, not by instruction count): 8 more shared-memory accesses per 4-edge step.
+template <int V, int LPR, int H, int D, int MINB, bool LEAN>
 __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_lg_quad_kernel(const GatParams p, const int rpw, const int64_t nchunks, const int sort) {
   const uint64_t seed_eff = p.training ? gat_seed(p) : 0;
   constexpr int G = 32 / LPR, VPH = V / H, F4 = V * LPR;
@@ -633,19 +636,26 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_lg_quad_kernel(
   const int s = lane % LPR, g = lane / LPR;
   using P = Pipe<LPR, D, V, 3>;
   P pipe;
-  // per warp: ring D*V*512 B, V*512 B of grad_bias accumulators, V*512 B holding this lane's slice of att (lane-private)
-  float4* wbase = q_smem + warp * ((D + 2) * V * 32);
+  // per warp (lane-private columns): ring D*V*512 B, V*512 B of grad_bias accumulators, then
+  //   !LEAN: V*512 B holding this lane's slice of att;   LEAN: V*512 B for x_r[i] and V*512 B of grad_att accumulators
+  constexpr int kExtra = LEAN ? 3 : 2;
+  float4* wbase = q_smem + warp * ((D + kExtra) * V * 32);
   pipe.ring = static_cast<uint32_t>(__cvta_generic_to_shared(wbase + lane));
   const uint32_t gb_addr = pipe.ring + D * V * 512;
-  const uint32_t att_addr = gb_addr + V * 512;
+  const uint32_t att_addr = gb_addr + V * 512;        // !LEAN
+  const uint32_t r_addr = gb_addr + V * 512;          // LEAN
+  const uint32_t gatt_addr = r_addr + V * 512;        // LEAN
 #pragma unroll
-  for (int i = 0; i < (D + 1) * V; ++i) sts4(pipe.ring + i * 512, make_float4(0.f, 0.f, 0.f, 0.f));
-  float4 gatt[V];
+  for (int i = 0; i < (D + kExtra) * V; ++i) sts4(pipe.ring + i * 512, make_float4(0.f, 0.f, 0.f, 0.f));
+  float4 gatt[LEAN ? 1 : V];
+  if constexpr (!LEAN) {
 #pragma unroll
-  for (int t = 0; t < V; ++t) {
-    sts4(att_addr + t * 512, ldg4(p.att + (t * LPR + s) * 4));
-    gatt[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < V; ++t) {
+      sts4(att_addr + t * 512, ldg4(p.att + (t * LPR + s) * 4));
+      gatt[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
+  auto att_of = [&](int t) { return LEAN ? ldg4(p.att + (t * LPR + s) * 4) : lds4(att_addr + t * 512); };
   const float slope = p.slope;
   const bool training = p.training != 0;
   const bool direct_src = p.t_rowptr == nullptr;   // one source per edge: this pass also writes grad_x_l
@@ -703,10 +713,13 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_lg_quad_kernel(
       }
       int eid_next = (training && c_deg > 0) ? __ldg(p.eid + c_beg) : 0;
 
-      float4 r[V], g4[V], sacc[V];
+      float4 r[LEAN ? 1 : V], g4[V], sacc[V];
       issue(); gen(); cp_wait<D - 1>();
 #pragma unroll
-      for (int t = 0; t < V; ++t) r[t] = lds4(pipe.read_addr(t));
+      for (int t = 0; t < V; ++t) {
+        if constexpr (LEAN) sts4(r_addr + t * 512, lds4(pipe.read_addr(t)));
+        else r[t] = lds4(pipe.read_addr(t));
+      }
       pipe.consumed();
       issue(); gen(); cp_wait<D - 1>();
 #pragma unroll
@@ -787,15 +800,23 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_lg_quad_kernel(
 #pragma unroll
         for (int t = 0; t < V; ++t) {           // sweep 2: z = x_l[j] + x_r[i], sel = delta * lrelu'(z)
           const float d = delta[t / VPH], ds = d * slope;
-          const float4 zz = add4p(lds4(pipe.read_addr(t)), r[t]);
+          float4 rt;
+          if constexpr (LEAN) rt = lds4(r_addr + t * 512); else rt = r[t];
+          const float4 zz = add4p(lds4(pipe.read_addr(t)), rt);
           const bool px = zz.x > 0.f, py = zz.y > 0.f, pz = zz.z > 0.f, pw = zz.w > 0.f;
           const float4 sel = make_float4(px ? d : ds, py ? d : ds, pz ? d : ds, pw ? d : ds);
           sacc[t] = add4p(sacc[t], sel);
-          fma4v(gatt[t], sel, zz);
+          if constexpr (LEAN) {
+            float4 ga = lds4(gatt_addr + t * 512);
+            fma4v(ga, sel, zz);
+            sts4(gatt_addr + t * 512, ga);
+          } else {
+            fma4v(gatt[t], sel, zz);
+          }
           if (!direct_src) {
             zbits |= (px ? 1u : 0u) << (4 * t) | (py ? 2u : 0u) << (4 * t) | (pz ? 4u : 0u) << (4 * t) | (pw ? 8u : 0u) << (4 * t);
           } else if (act) {                     // one source per edge: grad_x_l[j] = dL/dz_e + alpha'_e g_i
-            const float4 dz = mul4p(sel, lds4(att_addr + t * 512));
+            const float4 dz = mul4p(sel, att_of(t));
             const float ak = alk[t / VPH];
             st4(p.grad_x_l + static_cast<int64_t>(jcol) * p.ld_gl + (t * LPR + s) * 4,
                 make_float4(fmaf(ak, g4[t].x, dz.x), fmaf(ak, g4[t].y, dz.y), fmaf(ak, g4[t].z, dz.z), fmaf(ak, g4[t].w, dz.w)));
@@ -807,13 +828,18 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_lg_quad_kernel(
       if (rvalid) {
 #pragma unroll
         for (int t = 0; t < V; ++t)
-          st4(p.grad_x_r + row * p.ld_gr + (t * LPR + s) * 4, mul4p(lds4(att_addr + t * 512), sacc[t]));
+          st4(p.grad_x_r + row * p.ld_gr + (t * LPR + s) * 4, mul4p(att_of(t), sacc[t]));
       }
     }
   }
 
   // ---- CTA-level ordered reduction -> partial[blockIdx][2][F] ------------------------------------
-  float4 gb[V];
+  float4 gb[V], gsum[V];
+#pragma unroll
+  for (int t = 0; t < V; ++t) {
+    if constexpr (LEAN) gsum[t] = lds4(gatt_addr + t * 512); else gsum[t] = gatt[t];
+  }
+#define gatt gsum
 #pragma unroll
   for (int t = 0; t < V; ++t) {
     gb[t] = lds4(gb_addr + t * 512);
@@ -842,6 +868,7 @@ __global__ void __launch_bounds__(kQThreads, MINB) gatv2_bwd_dst_lg_quad_kernel(
     for (int w = 1; w < kQW; ++w) tsum = add4(tsum, red[(which * kQW + w) * F4 + f]);
     st4(p.partial + (static_cast<int64_t>(blockIdx.x) * 2 + which) * (F4 * 4) + f * 4, tsum);
   }
+#undef gatt
 }
 
 // fixed-order column sums of partial[nb][cols] -> grad_att | grad_bias.  block = (32, 8)
@@ -1020,6 +1047,7 @@ int pick_rpw(int64_t n_rows, int G) {
 }
 
 constexpr int kDFwd = 4, kDDst = 4, kDSrc = 4;
+constexpr int kDDstLean = 3;   // 4 resident CTAs per SM: (3 + 3) * V * 512 B per warp = 48 KB per CTA at V = 4
 
 // SEGGER_B200_GAT_SORT=0: rows keep their chunk order inside a warp (A/B of the degree-ordered quads); read per call
 int quad_sort() {
@@ -1071,10 +1099,18 @@ static int quad_dst_minb() {
   }
   return v;
 }
-static int quad_dst_blocks(int64_t n_dst, int rpw) {
+// The saved-logit dst pass runs its LEAN form (4 resident CTAs per SM) on two-pass graphs: measured on the cfg-2
+// tx-neighbors-tx conv 1.475 -> 1.422 ms for dst + src; the one-source-per-edge form (tx-belongs-bd) needs att on every
+// step and is faster with it in shared memory (0.205 against 0.220 ms).  SEGGER_B200_GAT_DST_OCC=3 / 4 forces a form.
+static bool quad_dst_lean(const GatParams& p) {
+  static const int forced = [] { const char* e = getenv("SEGGER_B200_GAT_DST_OCC"); return e ? atoi(e) : 0; }();
+  if (p.e_logit == nullptr) return false;
+  return forced == 4 || (forced != 3 && p.t_rowptr != nullptr);
+}
+static int quad_dst_blocks(int64_t n_dst, int rpw, int per_sm) {
   const int64_t nchunks = ceil_div(n_dst > 0 ? n_dst : 1, rpw);
   const int64_t want = ceil_div(nchunks, kQW);
-  const int64_t cap = static_cast<int64_t>(sm_count()) * quad_dst_minb();
+  const int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
   return static_cast<int>(want < cap ? want : cap);
 }
 
@@ -1098,16 +1134,17 @@ bool quad_bwd_launch(const GatParams& p, float* grad_att, float* grad_bias, cuda
   if (p.n_dst > 0) {
     const int rpw = pick_rpw(p.n_dst, G);
     const int64_t nchunks = ceil_div(p.n_dst, rpw);
-    const int nb = quad_dst_blocks(p.n_dst, rpw);
+    const int nb = quad_dst_blocks(p.n_dst, rpw, quad_dst_lean(p) ? 4 : quad_dst_minb());
 #define X(V, L, Hh)                                                                                   \
   if (qs.v == V && qs.lpr == L && p.H == Hh && p.e_logit != nullptr) {                                \
     const size_t smem = static_cast<size_t>(kQW) * (kDDst + 2) * V * 512;                             \
-    if (quad_dst_minb() == 4) {                                                                       \
-      auto kern = gatv2_bwd_dst_lg_quad_kernel<V, L, Hh, kDDst, 4>;                                   \
-      if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                    \
-      kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks, quad_sort());                            \
+    if (quad_dst_lean(p)) {                                                                           \
+      const size_t smem4 = static_cast<size_t>(kQW) * (kDDstLean + 3) * V * 512;                      \
+      auto kern = gatv2_bwd_dst_lg_quad_kernel<V, L, Hh, kDDstLean, 4, true>;                         \
+      if (smem4 > 48 * 1024 && !set_smem(kern, smem4)) return false;                                  \
+      kern<<<nb, kQThreads, smem4, stream>>>(p, rpw, nchunks, quad_sort());                           \
     } else {                                                                                          \
-      auto kern = gatv2_bwd_dst_lg_quad_kernel<V, L, Hh, kDDst, 3>;                                   \
+      auto kern = gatv2_bwd_dst_lg_quad_kernel<V, L, Hh, kDDst, 3, false>;                            \
       if (smem > 48 * 1024 && !set_smem(kern, smem)) return false;                                    \
       kern<<<nb, kQThreads, smem, stream>>>(p, rpw, nchunks, quad_sort());                            \
     }                                                                                                 \
