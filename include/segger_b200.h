@@ -288,6 +288,16 @@ SGB_API int sgb_triplet_margin_bwd(const float* ta, int64_t lda, const int64_t* 
                            const int64_t* ip, const float* tn, int64_t ldn, const int64_t* in_, int64_t T, int D,
                            float margin, float eps, const float* d_ap, const float* d_an, const float* grad,
                            float* ga /*[T,D]*/, float* gp /*[T,D]*/, float* gn /*[T,D]*/, void* stream);
+/* The same backward for TripletLoss's own call shape (triplet_loss.py:150-160: anchors = all T rows of `emb`, positives /
+ * negatives = sampled rows of the SAME matrix), as ONE row-owner pass: gout[r] = d loss / d emb[r], the anchor term of
+ * triplet r plus the terms of every triplet that sampled r, summed in a fixed order.  p_rowptr/p_tid (n_*): CSR over
+ * ip (in_) -- p_tid[p_rowptr[r] .. p_rowptr[r+1]) = the triplets t with ip[t] == r, t increasing (sgb_csr_build of the
+ * edge list (t -> ip[t])).  D in {32, 64, 128} (sgb_triplet_self_bwd_supported). */
+SGB_API int sgb_triplet_self_bwd_supported(int D);
+SGB_API int sgb_triplet_self_bwd(const float* emb, int64_t ld, const int64_t* ip, const int64_t* in_, int64_t T, int D,
+                         float margin, float eps, const float* d_ap, const float* d_an, const float* grad,
+                         const int32_t* p_rowptr, const int32_t* p_tid, const int32_t* n_rowptr, const int32_t* n_tid,
+                         float* gout /*[T, D]*/, int64_t ldg, void* stream);
 /* mode 0: mse_loss(cosine_similarity(a, b, eps), target, 'mean') -- MetricLoss (triplet_loss.py:193-204);
  * mode 1: BCEWithLogitsLoss()(sum(a * b, -1), target) -- segmentation BCE (lightning_model.py:188-205).
  * val [T] receives the cosine / the logit (saved for the backward). */

@@ -68,6 +68,9 @@ _PROTOS = {
     "sgb_loss_workspace_bytes": (c_sz, [c_i64]),
     "sgb_triplet_margin_fwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_f32, c_f32,
                                        c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "sgb_triplet_self_bwd_supported": (c_int, [c_int]),
+    "sgb_triplet_self_bwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                     c_vp, c_vp, c_vp, c_i64, c_vp]),
     "sgb_triplet_margin_bwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_f32, c_f32,
                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sgb_pair_loss_fwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_f32, c_vp, c_vp, c_vp,

@@ -149,6 +149,62 @@ triplet_bwd_kernel(const float* __restrict__ ta, int64_t lda, const int64_t* __r
   }
 }
 
+// Row-owner backward of the triplet loss when anchors, positives and negatives are rows of ONE table and triplet t has
+// anchor row t (TripletLoss over an embedding matrix): LPR = D/4 lanes own row r and sum, in a fixed order,
+//   the anchor term of triplet r, then -u_p(t) for every triplet t that sampled r as its positive (CSR over ip, t
+//   increasing), then +u_n(t) for every t that sampled r as its negative,
+// each term computed exactly as triplet_bwd_kernel writes it -- but nothing of width D is materialised per triplet, sorted
+// or segment-summed: per row ~2 + |P(r)| + |N(r)| gathered rows instead of 3 written + 3 re-read + 2 sorted.
+template <int LPR>
+__global__ void __launch_bounds__(kLossThreads)
+triplet_self_bwd_kernel(const float* __restrict__ emb, int64_t ld, const int64_t* __restrict__ ip,
+                        const int64_t* __restrict__ in_, int64_t T, float margin, float eps,
+                        const float* __restrict__ d_ap, const float* __restrict__ d_an, const float* __restrict__ grad,
+                        const int32_t* __restrict__ p_rowptr, const int32_t* __restrict__ p_tid,
+                        const int32_t* __restrict__ n_rowptr, const int32_t* __restrict__ n_tid,
+                        float* __restrict__ gout, int64_t ldg) {
+  const int s = threadIdx.x % LPR;
+  const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
+  if (r >= T) return;
+  const float g0 = __ldg(grad) / static_cast<float>(T);
+  // coefficient pair of triplet t: (g / d_ap, g / d_an) if the hinge is active, else 0 (triplet_bwd_kernel's rule)
+  auto coef = [&](int64_t t, float& cp, float& cn) {
+    const float dap = __ldg(d_ap + t), dan = __ldg(d_an + t);
+    const float g = (margin + dap - dan > 0.f) ? g0 : 0.f;
+    cp = dap > 0.f ? g / dap : 0.f;
+    cn = dan > 0.f ? g / dan : 0.f;
+  };
+  const float4 e = ldg4(emb + r * ld + 4 * s);
+  float4 acc;
+  {
+    float cp, cn;
+    coef(r, cp, cn);
+    const float4 p = ldg4(emb + __ldg(ip + r) * ld + 4 * s);
+    const float4 n = ldg4(emb + __ldg(in_ + r) * ld + 4 * s);
+    acc.x = (e.x - p.x + eps) * cp - (e.x - n.x + eps) * cn;
+    acc.y = (e.y - p.y + eps) * cp - (e.y - n.y + eps) * cn;
+    acc.z = (e.z - p.z + eps) * cp - (e.z - n.z + eps) * cn;
+    acc.w = (e.w - p.w + eps) * cp - (e.w - n.w + eps) * cn;
+  }
+  for (int k = __ldg(p_rowptr + r), ke = __ldg(p_rowptr + r + 1); k < ke; ++k) {
+    const int64_t t = __ldg(p_tid + k);
+    float cp, cn;
+    coef(t, cp, cn);
+    const float4 a = ldg4(emb + t * ld + 4 * s);
+    acc.x += -((a.x - e.x + eps) * cp); acc.y += -((a.y - e.y + eps) * cp);
+    acc.z += -((a.z - e.z + eps) * cp); acc.w += -((a.w - e.w + eps) * cp);
+  }
+  for (int k = __ldg(n_rowptr + r), ke = __ldg(n_rowptr + r + 1); k < ke; ++k) {
+    const int64_t t = __ldg(n_tid + k);
+    float cp, cn;
+    coef(t, cp, cn);
+    const float4 a = ldg4(emb + t * ld + 4 * s);
+    acc.x += (a.x - e.x + eps) * cn; acc.y += (a.y - e.y + eps) * cn;
+    acc.z += (a.z - e.z + eps) * cn; acc.w += (a.w - e.w + eps) * cn;
+  }
+  st4(gout + r * ldg + 4 * s, acc);
+}
+
 // pair losses: mode 0 = mse(cosine_similarity(a, b), target) (ATen formula: sum (a / max(|a|, eps)) (b / max(|b|, eps)));
 //              mode 1 = binary_cross_entropy_with_logits(a . b, target)
 __global__ void __launch_bounds__(kLossThreads)
@@ -268,6 +324,30 @@ extern "C" int sgb_triplet_margin_bwd(const float* ta, int64_t lda, const int64_
   triplet_bwd_kernel<<<warp_blocks(T), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       ta, lda, ia, tp, ldp, ip, tn, ldn, in_, T, D, margin, eps, d_ap, d_an, grad, ga, gp, gn);
   return check_launch("triplet_margin_bwd");
+}
+
+extern "C" int sgb_triplet_self_bwd_supported(int D) { return (D == 32 || D == 64 || D == 128) ? 1 : 0; }
+
+extern "C" int sgb_triplet_self_bwd(const float* emb, int64_t ld, const int64_t* ip, const int64_t* in_, int64_t T, int D,
+                                    float margin, float eps, const float* d_ap, const float* d_an, const float* grad,
+                                    const int32_t* p_rowptr, const int32_t* p_tid, const int32_t* n_rowptr,
+                                    const int32_t* n_tid, float* gout, int64_t ldg, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SGB_REQUIRE(T >= 0 && T < (int64_t(1) << 31), SGB_ERR_RANGE, "triplet_self_bwd: T out of range");
+  SGB_REQUIRE(sgb_triplet_self_bwd_supported(D), SGB_ERR_ARG, "triplet_self_bwd: D must be 32, 64 or 128 (got %d)", D);
+  if (T == 0) return SGB_OK;
+  SGB_REQUIRE(emb && ip && in_ && d_ap && d_an && grad && p_rowptr && p_tid && n_rowptr && n_tid && gout, SGB_ERR_ARG,
+              "triplet_self_bwd: null tensor");
+  SGB_REQUIRE(aligned16(emb) && ld % 4 == 0 && aligned16(gout) && ldg % 4 == 0, SGB_ERR_ALIGN,
+              "triplet_self_bwd: rows must be 16-byte aligned");
+  const int lpr = D / 4;
+  const unsigned blocks = static_cast<unsigned>(ceil_div(T * lpr, kLossThreads));
+#define SGB_TSB(L)                                                                                                      \
+  triplet_self_bwd_kernel<L><<<blocks, kLossThreads, 0, stream>>>(emb, ld, ip, in_, T, margin, eps, d_ap, d_an, grad, p_rowptr, \
+                                                                  p_tid, n_rowptr, n_tid, gout, ldg)
+  if (lpr == 8) SGB_TSB(8); else if (lpr == 16) SGB_TSB(16); else SGB_TSB(32);
+#undef SGB_TSB
+  return check_launch("triplet_self_bwd");
 }
 
 extern "C" int sgb_pair_loss_fwd(const float* ta, int64_t lda, const int64_t* ia, const float* tb, int64_t ldb,

@@ -10,6 +10,7 @@ them, so ``torch.manual_seed`` governs sampling as before.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -57,6 +58,11 @@ class _TripletMarginFn(torch.autograd.Function):
                                          ptr(ws), ws.numel(), stream_ptr(dev)), "triplet_margin_fwd")
         ops._count(2)
         ctx.cfg = (T, D, float(margin), float(eps))
+        # TripletLoss's own call shape: one embedding matrix three times, anchors = all its rows -> row-owner backward
+        ctx.shared = (ia is None and ip is not None and in_ is not None and T == ta.size(0) and T > 0
+                      and ta.data_ptr() == tp.data_ptr() == tn.data_ptr() and ta.shape == tp.shape == tn.shape
+                      and ta.stride() == tp.stride() == tn.stride() and ta.data_ptr() % 16 == 0 and ops._ld(ta) % 4 == 0
+                      and bool(lib.sgb_triplet_self_bwd_supported(D)) and os.environ.get("SEGGER_B200_LOSS_FUSED", "1") != "0")
         ctx.save_for_backward(ta, tp, tn, ia, ip, in_, d_ap, d_an)
         return loss
 
@@ -67,6 +73,20 @@ class _TripletMarginFn(torch.autograd.Function):
         dev = ta.device
         if T == 0:
             return torch.zeros_like(ta), torch.zeros_like(tp), torch.zeros_like(tn), None, None, None, None, None
+        if ctx.shared:
+            # d loss / d emb[r] in ONE pass over the rows: CSRs of the sampled positives / negatives (which triplets
+            # point at row r; two key sorts) replace three [T, D] per-triplet gradient tensors, two sorts + segment sums
+            # of them and the two [T, D] additions autograd would make of the three results
+            ar = torch.arange(T, dtype=torch.int64, device=dev)
+            csr_p = ops.build_csr(torch.stack([ar, ip]), T, T, transpose=False)
+            csr_n = ops.build_csr(torch.stack([ar, in_]), T, T, transpose=False)
+            gout = torch.empty(T, D, dtype=torch.float32, device=dev)
+            g = dloss.to(torch.float32).contiguous()
+            check(_lib.load().sgb_triplet_self_bwd(ptr(ta), ops._ld(ta), ptr(ip), ptr(in_), T, D, margin, eps, ptr(d_ap),
+                                                   ptr(d_an), ptr(g), ptr(csr_p.rowptr), ptr(csr_p.col), ptr(csr_n.rowptr),
+                                                   ptr(csr_n.col), ptr(gout), D, stream_ptr(dev)), "triplet_self_bwd")
+            ops._count(1)
+            return gout, None, None, None, None, None, None, None
         ga = torch.empty(T, D, dtype=torch.float32, device=dev)
         gp, gn = torch.empty_like(ga), torch.empty_like(ga)
         g = dloss.to(torch.float32).contiguous()

@@ -192,3 +192,28 @@ def test_losses_against_committed_golden_fixture():
     for got, key in ((l_t, "loss_triplet"), (l_m, "loss_metric"), (l_s, "loss_seg_triplet"), (l_b, "loss_seg_bce")):
         assert abs(float(got.detach()) - float(gd[key])) < 2e-6
     assert rel_err(e.grad, gd["grad"]) < 1e-5
+
+
+@pytest.mark.parametrize("N,D", [(50_000, 64), (3001, 32), (129, 128)])
+def test_triplet_row_owner_backward_equals_per_triplet_backward(N, D, monkeypatch):
+    """TripletLoss's call shape (one matrix three times, anchors = all rows) takes the one-pass row-owner backward
+    (sgb_triplet_self_bwd over CSRs of the sampled indices); it must equal the per-triplet rows + segment sums of the
+    general path to rounding, with heavily repeated positives / negatives and rows nobody sampled."""
+    g = torch.Generator().manual_seed(N + D)
+    emb = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1)
+    hot = max(2, N // 50)                                   # most triplets point at a few rows
+    pos = torch.randint(0, hot, (N,), generator=g)
+    neg = torch.randint(0, N, (N,), generator=g)
+    neg[: N // 3] = N - 1 - torch.randint(0, hot, (N // 3,), generator=g)
+    grads = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SEGGER_B200_LOSS_FUSED", flag)
+        e = emb.clone().cuda().requires_grad_()
+        loss = TL.triplet_margin(e, e, e, None, pos.cuda(), neg.cuda(), 0.4)
+        (loss * 2.0).backward()
+        grads[flag] = (float(loss.detach()), e.grad.clone())
+    assert grads["0"][0] == grads["1"][0]
+    assert rel_err(grads["1"][1], grads["0"][1]) < 2e-6
+    e_ref = emb.clone().double().requires_grad_()
+    R.triplet_loss_ref(e_ref, pos, neg, 0.4).backward()
+    assert rel_err(grads["1"][1] / 2.0, e_ref.grad) < 1e-5
