@@ -186,21 +186,30 @@ triplet_self_bwd_kernel(const float* __restrict__ emb, int64_t ld, const int64_t
     acc.z = (e.z - p.z + eps) * cp - (e.z - n.z + eps) * cn;
     acc.w = (e.w - p.w + eps) * cp - (e.w - n.w + eps) * cn;
   }
+  // a row that many triplets sampled (a small cluster next to large ones) sums thousands of terms: compensated (Kahan)
+  // accumulation keeps the left fold as accurate as the chunked segment sums it replaces, at 3 adds per term
+  float4 cmp = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto kadd = [](float& sum, float& c, float term) {
+    const float y = __fsub_rn(term, c);
+    const float tsum = __fadd_rn(sum, y);
+    c = __fsub_rn(__fsub_rn(tsum, sum), y);
+    sum = tsum;
+  };
   for (int k = __ldg(p_rowptr + r), ke = __ldg(p_rowptr + r + 1); k < ke; ++k) {
     const int64_t t = __ldg(p_tid + k);
     float cp, cn;
     coef(t, cp, cn);
     const float4 a = ldg4(emb + t * ld + 4 * s);
-    acc.x += -((a.x - e.x + eps) * cp); acc.y += -((a.y - e.y + eps) * cp);
-    acc.z += -((a.z - e.z + eps) * cp); acc.w += -((a.w - e.w + eps) * cp);
+    kadd(acc.x, cmp.x, -((a.x - e.x + eps) * cp)); kadd(acc.y, cmp.y, -((a.y - e.y + eps) * cp));
+    kadd(acc.z, cmp.z, -((a.z - e.z + eps) * cp)); kadd(acc.w, cmp.w, -((a.w - e.w + eps) * cp));
   }
   for (int k = __ldg(n_rowptr + r), ke = __ldg(n_rowptr + r + 1); k < ke; ++k) {
     const int64_t t = __ldg(n_tid + k);
     float cp, cn;
     coef(t, cp, cn);
     const float4 a = ldg4(emb + t * ld + 4 * s);
-    acc.x += (a.x - e.x + eps) * cn; acc.y += (a.y - e.y + eps) * cn;
-    acc.z += (a.z - e.z + eps) * cn; acc.w += (a.w - e.w + eps) * cn;
+    kadd(acc.x, cmp.x, (a.x - e.x + eps) * cn); kadd(acc.y, cmp.y, (a.y - e.y + eps) * cn);
+    kadd(acc.z, cmp.z, (a.z - e.z + eps) * cn); kadd(acc.w, cmp.w, (a.w - e.w + eps) * cn);
   }
   st4(gout + r * ldg + 4 * s, acc);
 }

@@ -217,3 +217,19 @@ def test_triplet_row_owner_backward_equals_per_triplet_backward(N, D, monkeypatc
     e_ref = emb.clone().double().requires_grad_()
     R.triplet_loss_ref(e_ref, pos, neg, 0.4).backward()
     assert rel_err(grads["1"][1] / 2.0, e_ref.grad) < 1e-5
+
+
+def test_triplet_row_owner_backward_heavy_rows():
+    """A row that thousands of triplets sampled (a tiny cluster beside large ones): the compensated left fold of the
+    row-owner backward stays within 1e-5 of float64."""
+    g = torch.Generator().manual_seed(4)
+    N, D = 20_000, 64
+    emb = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1)
+    pos = torch.randint(0, 3, (N,), generator=g)            # three rows share all the positives
+    neg = N - 1 - torch.randint(0, 2, (N,), generator=g)    # two rows share all the negatives
+    e = emb.clone().cuda().requires_grad_()
+    TL.triplet_margin(e, e, e, None, pos.cuda(), neg.cuda(), 0.4).backward()
+    e_ref = emb.clone().double().requires_grad_()
+    R.triplet_loss_ref(e_ref, pos, neg, 0.4).backward()
+    assert rel_err(e.grad, e_ref.grad) < 1e-5
+    assert rel_err(e.grad[:3], e_ref.grad[:3]) < 1e-5 and rel_err(e.grad[-2:], e_ref.grad[-2:]) < 1e-5
