@@ -60,8 +60,8 @@ class Positional2dEmbedderRef(torch.nn.Module):
             pos = pos / pos.max(dim=0).values
         else:
             nb = int(batch.max()) + 1
-            mins = torch.zeros((nb, 2))
-            maxs = torch.zeros((nb, 2))
+            mins = torch.zeros((nb, 2), device=pos.device)      # (device: bench.py --impl torch_cuda runs this on the GPU)
+            maxs = torch.zeros((nb, 2), device=pos.device)
             for b in range(nb):
                 mask = batch == b
                 if mask.any():
