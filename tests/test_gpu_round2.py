@@ -280,3 +280,78 @@ def test_factored_first_layer_equals_dense_form(monkeypatch):
     sum((out[k] * g[k]).sum() for k in g).backward()
     assert prod.lin_first["tx"].weight.grad is None
     assert rel_err(prod.pos_emb.mlp[0].weight.grad, res["1"][1]["pos_emb.mlp.0.weight"]) < 1e-6
+
+
+def test_side_stream_csr_builds_equal_inline_builds(monkeypatch):
+    """Graphs of >= 2M edges get their CSRs built on a side stream while the input stage runs (ops.csr_build_overlapped).
+    Forced here on a small graph: forward, gradients and the IndexError of a malformed edge list must equal the inline
+    path bit for bit, under autograd and under inference_mode."""
+    ts, x, edges, pos, bat = synth_batch(5000, 50, seed=21)
+    _, prod = make_models(ts.n_genes, ts.bd_x.shape[1], 32, 64, 64, 0, 2, seed=0)
+    prod.eval()                                            # (dropout off: the two runs must be comparable)
+    args = (to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat))
+    res = {}
+    for name, min_edges in (("inline", 1 << 60), ("side", 0)):
+        monkeypatch.setattr(ops, "_CSR_OVERLAP_MIN_EDGES", min_edges)
+        ops.CSR_CACHE.clear()
+        prod.zero_grad(set_to_none=True)
+        out = prod(*args)
+        (out["tx"].square().sum() + out["bd"].sum()).backward()
+        torch.cuda.synchronize()
+        res[name] = (out["tx"].detach().clone(), out["bd"].detach().clone(),
+                     {n: p.grad.clone() for n, p in prod.named_parameters() if p.grad is not None})
+    assert torch.equal(res["inline"][0], res["side"][0]) and torch.equal(res["inline"][1], res["side"][1])
+    assert res["inline"][2].keys() == res["side"][2].keys() and len(res["side"][2]) > 10
+    assert all(torch.equal(res["inline"][2][n], res["side"][2][n]) for n in res["side"][2])
+    # repeated new graphs on the side stream (allocator reuse across streams), then a malformed one
+    for _ in range(3):
+        ops.CSR_CACHE.clear()
+        with torch.inference_mode():
+            again = prod(*(to_dev(x), to_dev(edges), to_dev(pos), to_dev(bat)))["tx"]
+        assert torch.equal(again, res["side"][0])
+    bad = {k: v.clone() for k, v in edges.items()}
+    bad[TT][1, 7] = 5000
+    ops.CSR_CACHE.clear()
+    with pytest.raises(IndexError), torch.no_grad():
+        prod(to_dev(x), to_dev(bad), to_dev(pos), to_dev(bat))
+
+
+def test_loss_bookkeeping_on_the_side_stream_equals_inline(monkeypatch):
+    """LitISTEncoder.get_losses resolves masks / labels and samples the triplets on a side stream while the forward
+    runs: same draws, same losses, same gradients as the inline order (SEGGER_B200_LOSS_OVERLAP=0)."""
+    ts, x, edges, pos, bat = synth_batch(4000, 40, seed=5)
+    g = torch.Generator().manual_seed(6)
+
+    def sim(c):
+        a = torch.rand(c, c, generator=g) * 2 - 1
+        return ((a + a.t()) / 2).contiguous()
+
+    s_tx, s_bd = sim(8), sim(4)
+    b = HeteroBatch()
+    for k in ("tx", "bd"):
+        b[k]["x"], b[k]["pos"], b[k]["batch"] = x[k], pos[k], bat[k]
+    b["tx"]["mask"] = torch.rand(4000, generator=g) < 0.8
+    b["tx"]["cluster"] = torch.randint(0, 8, (4000,), generator=g)
+    b["bd"]["mask"] = torch.rand(40, generator=g) < 0.9
+    b["bd"]["cluster"] = torch.randint(-1, 4, (40,), generator=g)
+    b[TT]["edge_index"], b[TB]["edge_index"] = edges[TT], edges[TB]
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SEGGER_B200_LOSS_OVERLAP", flag)
+        torch.manual_seed(0)
+        lit = LitISTEncoder(ts.n_genes, in_channels=32, hidden_channels=32, out_channels=32, n_mid_layers=0).cuda().eval()
+        lit.setup_losses(s_tx.clone(), s_bd.clone())
+        lit.set_epoch(2, 10)
+        bc = b.cuda()
+        with torch.no_grad():
+            lit.forward(bc)                                 # lazy parameters
+        torch.manual_seed(33)
+        ops.CSR_CACHE.clear()
+        losses = lit.get_losses(bc)
+        losses[3].backward()
+        torch.cuda.synchronize()
+        res[flag] = ([float(v.detach()) if torch.is_tensor(v) else float(v) for v in losses],
+                     {n: p.grad.clone() for n, p in lit.model.named_parameters() if p.grad is not None})
+    assert res["0"][0] == res["1"][0]
+    assert res["0"][1].keys() == res["1"][1].keys()
+    assert all(torch.equal(res["0"][1][n], res["1"][1][n]) for n in res["0"][1])
