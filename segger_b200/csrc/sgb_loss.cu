@@ -149,6 +149,71 @@ triplet_bwd_kernel(const float* __restrict__ ta, int64_t lda, const int64_t* __r
   }
 }
 
+// 128-bit variants of the two kernels above (D in {32, 64, 128}, 16-byte aligned rows): LPR = D/4 lanes per triplet, a
+// warp handles 32/LPR triplets.  Same per-element arithmetic; the squared distances are summed four elements per lane and
+// then across the LPR lanes (a different -- still fixed -- order than the 32-bit kernel's).
+template <int LPR>
+__global__ void __launch_bounds__(kLossThreads)
+triplet_fwd_vec_kernel(const float* __restrict__ ta, int64_t lda, const int64_t* __restrict__ ia, const float* __restrict__ tp,
+                       int64_t ldp, const int64_t* __restrict__ ip, const float* __restrict__ tn, int64_t ldn,
+                       const int64_t* __restrict__ in_, int64_t T, float margin, float eps, float* __restrict__ d_ap,
+                       float* __restrict__ d_an, float* __restrict__ partial) {
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31, s = lane % LPR, gq = lane / LPR;
+  const int64_t i = ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * G + gq;
+  float sp = 0.f, sn = 0.f;
+  if (i < T) {
+    const float4 a = ldg4(row_ptr(ta, lda, ia, i) + 4 * s);
+    const float4 p = ldg4(row_ptr(tp, ldp, ip, i) + 4 * s);
+    const float4 n = ldg4(row_ptr(tn, ldn, in_, i) + 4 * s);
+    float d;
+    d = a.x - p.x + eps; sp = fmaf(d, d, sp); d = a.y - p.y + eps; sp = fmaf(d, d, sp);
+    d = a.z - p.z + eps; sp = fmaf(d, d, sp); d = a.w - p.w + eps; sp = fmaf(d, d, sp);
+    d = a.x - n.x + eps; sn = fmaf(d, d, sn); d = a.y - n.y + eps; sn = fmaf(d, d, sn);
+    d = a.z - n.z + eps; sn = fmaf(d, d, sn); d = a.w - n.w + eps; sn = fmaf(d, d, sn);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o >= 1; o >>= 1) {
+    sp += __shfl_xor_sync(kFull, sp, o);
+    sn += __shfl_xor_sync(kFull, sn, o);
+  }
+  float loss = 0.f;
+  if (i < T) {
+    const float dap = sqrtf(sp), dan = sqrtf(sn);
+    if (s == 0) { d_ap[i] = dap; d_an[i] = dan; }
+    loss = fmaxf(margin + dap - dan, 0.f);
+  }
+  float wl = 0.f;      // the warp's triplets, in order
+#pragma unroll
+  for (int g2 = 0; g2 < G; ++g2) wl += __shfl_sync(kFull, loss, g2 * LPR);
+  block_partial(wl, lane == 0, partial);
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(kLossThreads)
+triplet_bwd_vec_kernel(const float* __restrict__ ta, int64_t lda, const int64_t* __restrict__ ia, const float* __restrict__ tp,
+                       int64_t ldp, const int64_t* __restrict__ ip, const float* __restrict__ tn, int64_t ldn,
+                       const int64_t* __restrict__ in_, int64_t T, float margin, float eps, const float* __restrict__ d_ap,
+                       const float* __restrict__ d_an, const float* __restrict__ grad, float* __restrict__ ga,
+                       float* __restrict__ gp, float* __restrict__ gn) {
+  constexpr int D = 4 * LPR;
+  const int s = threadIdx.x % LPR;
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
+  if (i >= T) return;
+  const float dap = d_ap[i], dan = d_an[i];
+  const bool active = margin + dap - dan > 0.f;
+  const float g = active ? __ldg(grad) / static_cast<float>(T) : 0.f;
+  const float cp = dap > 0.f ? g / dap : 0.f, cn = dan > 0.f ? g / dan : 0.f;
+  const float4 a = ldg4(row_ptr(ta, lda, ia, i) + 4 * s);
+  const float4 p = ldg4(row_ptr(tp, ldp, ip, i) + 4 * s);
+  const float4 n = ldg4(row_ptr(tn, ldn, in_, i) + 4 * s);
+  const float4 up = make_float4((a.x - p.x + eps) * cp, (a.y - p.y + eps) * cp, (a.z - p.z + eps) * cp, (a.w - p.w + eps) * cp);
+  const float4 un = make_float4((a.x - n.x + eps) * cn, (a.y - n.y + eps) * cn, (a.z - n.z + eps) * cn, (a.w - n.w + eps) * cn);
+  st4(ga + i * D + 4 * s, make_float4(up.x - un.x, up.y - un.y, up.z - un.z, up.w - un.w));
+  st4(gp + i * D + 4 * s, make_float4(-up.x, -up.y, -up.z, -up.w));
+  st4(gn + i * D + 4 * s, un);
+}
+
 // Row-owner backward of the triplet loss when anchors, positives and negatives are rows of ONE table and triplet t has
 // anchor row t (TripletLoss over an embedding matrix): LPR = D/4 lanes own row r and sum, in a fixed order,
 //   the anchor term of triplet r, then -u_p(t) for every triplet t that sampled r as its positive (CSR over ip, t
@@ -282,6 +347,11 @@ pair_bwd_kernel(const float* __restrict__ ta, int64_t lda, const int64_t* __rest
   }
 }
 
+// the 128-bit triplet kernels: D in {32, 64, 128}, rows of all three tables 16-byte aligned
+bool triplet_vec_ok(int D, const float* ta, int64_t lda, const float* tp, int64_t ldp, const float* tn, int64_t ldn) {
+  return (D == 32 || D == 64 || D == 128) && aligned16(ta) && aligned16(tp) && aligned16(tn) && lda % 4 == 0 && ldp % 4 == 0 &&
+         ldn % 4 == 0;
+}
 unsigned warp_blocks(int64_t T) { return static_cast<unsigned>(ceil_div(T > 0 ? T : 1, kLossWarps)); }
 
 }  // namespace
@@ -317,6 +387,15 @@ extern "C" int sgb_triplet_margin_fwd(const float* ta, int64_t lda, const int64_
   SGB_REQUIRE(ta && tp && tn && d_ap && d_an && lda >= D && ldp >= D && ldn >= D, SGB_ERR_ARG, "triplet_margin_fwd: null tensor");
   SGB_REQUIRE(ws && ws_bytes >= sgb_loss_workspace_bytes(T), SGB_ERR_WORKSPACE, "triplet_margin_fwd: workspace too small");
   float* partial = static_cast<float*>(ws);
+  if (triplet_vec_ok(D, ta, lda, tp, ldp, tn, ldn)) {
+    const int lpr = D / 4, per_block = kLossWarps * (32 / lpr);
+    const unsigned nbv = static_cast<unsigned>(ceil_div(T, per_block));       // <= warp_blocks(T): the workspace fits
+#define SGB_TFV(L) triplet_fwd_vec_kernel<L><<<nbv, kLossThreads, 0, stream>>>(ta, lda, ia, tp, ldp, ip, tn, ldn, in_, T, margin, eps, d_ap, d_an, partial)
+    if (lpr == 8) SGB_TFV(8); else if (lpr == 16) SGB_TFV(16); else SGB_TFV(32);
+#undef SGB_TFV
+    mean_reduce_kernel<<<1, 1024, 0, stream>>>(partial, nbv, 1.0f / static_cast<float>(T), loss);
+    return check_launch("triplet_margin_fwd(vec)");
+  }
   const unsigned nb = warp_blocks(T);
   triplet_fwd_kernel<<<nb, kLossThreads, 0, stream>>>(ta, lda, ia, tp, ldp, ip, tn, ldn, in_, T, D, margin, eps, d_ap, d_an, partial);
   mean_reduce_kernel<<<1, 1024, 0, stream>>>(partial, nb, 1.0f / static_cast<float>(T), loss);
@@ -330,6 +409,14 @@ extern "C" int sgb_triplet_margin_bwd(const float* ta, int64_t lda, const int64_
   SGB_REQUIRE(T >= 0 && D >= 1, SGB_ERR_ARG, "triplet_margin_bwd: bad argument");
   if (T == 0) return SGB_OK;
   SGB_REQUIRE(ta && tp && tn && d_ap && d_an && grad && ga && gp && gn, SGB_ERR_ARG, "triplet_margin_bwd: null tensor");
+  if (triplet_vec_ok(D, ta, lda, tp, ldp, tn, ldn) && aligned16(ga) && aligned16(gp) && aligned16(gn)) {
+    const int lpr = D / 4;
+    const unsigned nbv = static_cast<unsigned>(ceil_div(T * lpr, kLossThreads));
+#define SGB_TBV(L) triplet_bwd_vec_kernel<L><<<nbv, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(ta, lda, ia, tp, ldp, ip, tn, ldn, in_, T, margin, eps, d_ap, d_an, grad, ga, gp, gn)
+    if (lpr == 8) SGB_TBV(8); else if (lpr == 16) SGB_TBV(16); else SGB_TBV(32);
+#undef SGB_TBV
+    return check_launch("triplet_margin_bwd(vec)");
+  }
   triplet_bwd_kernel<<<warp_blocks(T), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       ta, lda, ia, tp, ldp, ip, tn, ldn, in_, T, D, margin, eps, d_ap, d_an, grad, ga, gp, gn);
   return check_launch("triplet_margin_bwd");
